@@ -1,0 +1,14 @@
+"""B200-native BM25F query-scoring engine behind the Whoosh searcher surface.
+
+Drop-in for one hot path of CodeOptimist/document-search-engine: BM25F scoring of
+parsed query terms over inverted-index posting lists plus top-k collection
+(SURVEY.md §8).  Host code is Python; the GPU is reached through the C ABI in
+``include/bm25f.h`` (``csrc/libbm25f.so``) via ctypes.  There is no CPU fallback.
+"""
+from .index import FlatIndex, Schema
+from .query import And, Every, NullQuery, Or, QueryParser, Term
+from .scoring import BM25F, WeightingModel
+
+__all__ = ["FlatIndex", "Schema", "And", "Or", "Term", "Every", "NullQuery", "QueryParser",
+           "BM25F", "WeightingModel"]
+__version__ = "0.1.0"

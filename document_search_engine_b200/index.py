@@ -1,0 +1,305 @@
+"""Flattened, upload-ready inverted index (CSR posting store).
+
+The reference opens a Whoosh index directory (``my_index.py:226-234``) and hands
+it to the front ends as the module global ``ix`` (``my_flask.py:549``,
+``cli.py:25``).  The engine replaces the *inside* of that object for the scoring
+path: everything the BM25F scorer reads (SURVEY.md §8 b, "Data layout across
+the boundary") is flattened into a handful of arrays that are uploaded to HBM
+once per process:
+
+* ``term_offsets[n_terms+1]`` u64 CSR row pointers; a "term" is a (field, text)
+  pair, numbered field-major;
+* ``docids[P]`` u32, ascending inside a term; ``tfs[P]`` f32 posting weights (W7);
+* ``len_bytes[n_fields, n_docs_all]`` u8 quantised field lengths (W5/W6);
+* ``field_length_total[n_fields]`` exact token totals (W4), ``df`` as stored (W3),
+  ``deleted`` flags (W9) and ``doc_base`` for document shards (W8).
+
+Corpus parsing, analyzers and the on-disk Whoosh format are out of scope
+(SURVEY.md §2); ``from_documents`` exists so tests and small tools can build an
+index from already-tokenised documents.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .numeric import lengths_to_bytes
+
+FORMAT_VERSION = 1
+
+
+class Schema:
+    """Just enough of ``whoosh.fields.Schema`` for ``QueryParser`` and the UI."""
+
+    def __init__(self, names: Sequence[str], stored: Sequence[str] = ()):
+        self._names = list(names)
+        self._stored = list(stored)
+
+    def names(self):
+        return list(self._names)
+
+    def stored_names(self):
+        return list(self._stored)
+
+    def __contains__(self, name):
+        return name in self._names
+
+
+class IndexReader:
+    """``searcher.ixreader`` surface used by the reference (``my_flask.py:254``)."""
+
+    def __init__(self, ix: "FlatIndex"):
+        self._ix = ix
+
+    def frequency(self, fieldname, text) -> float:
+        tid = self._ix.term_id(fieldname, text)
+        if tid < 0:
+            return 0.0
+        a, b = int(self._ix.term_offsets[tid]), int(self._ix.term_offsets[tid + 1])
+        return float(self._ix.tfs[a:b].sum(dtype=np.float64)) if self._ix.term_weight_total is None \
+            else float(self._ix.term_weight_total[tid])
+
+    def doc_frequency(self, fieldname, text) -> int:
+        tid = self._ix.term_id(fieldname, text)
+        return 0 if tid < 0 else int(self._ix.df[tid])
+
+    def doc_count_all(self):
+        return self._ix.doc_count_all()
+
+    def doc_count(self):
+        return self._ix.doc_count()
+
+    def field_length(self, fieldname):
+        return self._ix.field_length(fieldname)
+
+    def __contains__(self, term):
+        return self._ix.term_id(term[0], term[1]) >= 0
+
+
+class FlatIndex:
+    def __init__(self, *, field_names: Sequence[str], n_docs_all: int,
+                 term_offsets: np.ndarray, docids: np.ndarray, tfs: np.ndarray,
+                 term_field: np.ndarray, len_bytes: np.ndarray,
+                 field_length_total: np.ndarray,
+                 terms: Optional[Dict[Tuple[int, object], int]] = None,
+                 vocab_size: Optional[int] = None,
+                 df: Optional[np.ndarray] = None,
+                 deleted: Optional[np.ndarray] = None,
+                 stored: Optional[Sequence[Mapping]] = None,
+                 doc_base: int = 0,
+                 global_doc_count_all: Optional[int] = None,
+                 term_weight_total: Optional[np.ndarray] = None):
+        self.field_names = list(field_names)
+        self.n_docs_all = int(n_docs_all)
+        self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
+        self.docids = np.ascontiguousarray(docids, dtype=np.uint32)
+        self.tfs = np.ascontiguousarray(tfs, dtype=np.float32)
+        self.term_field = np.ascontiguousarray(term_field, dtype=np.uint8)
+        self.len_bytes = np.ascontiguousarray(len_bytes, dtype=np.uint8).reshape(len(self.field_names), self.n_docs_all)
+        self.field_length_total = np.ascontiguousarray(field_length_total, dtype=np.uint64)
+        self.terms = terms
+        self.vocab_size = vocab_size
+        n_terms = self.term_offsets.size - 1
+        if n_terms != self.term_field.size:
+            raise ValueError("term_field must have one entry per posting list")
+        if int(self.term_offsets[-1]) != self.docids.size or self.docids.size != self.tfs.size:
+            raise ValueError("posting arrays do not match term_offsets")
+        # W3: document frequency *as stored* (deleted documents still counted)
+        self.df = (np.diff(self.term_offsets).astype(np.uint32) if df is None
+                   else np.ascontiguousarray(df, dtype=np.uint32))
+        self.deleted = None if deleted is None else np.ascontiguousarray(deleted, dtype=np.uint8)
+        self.stored = stored
+        self.doc_base = int(doc_base)
+        # W8: idf / avgfl come from the whole corpus, never from a shard
+        self.global_doc_count_all = int(self.n_docs_all if global_doc_count_all is None else global_doc_count_all)
+        self.term_weight_total = term_weight_total
+        self.schema = Schema(self.field_names, stored=self._stored_names())
+        self._engine_cache = {}
+
+    # ---- Whoosh Index surface -------------------------------------------------
+    def doc_count_all(self) -> int:
+        return self.global_doc_count_all
+
+    def doc_count(self) -> int:
+        """Undeleted documents (``ix.doc_count()``, ``my_flask.py:225``)."""
+        if self.deleted is None:
+            return self.global_doc_count_all
+        return self.global_doc_count_all - int(self.deleted.sum())
+
+    def is_empty(self):
+        return self.doc_count() == 0
+
+    def reader(self):
+        return IndexReader(self)
+
+    def searcher(self, weighting=None, **kwargs):
+        from .searching import Searcher
+        return Searcher(self, weighting=weighting, **kwargs)
+
+    # ---- dictionary -----------------------------------------------------------
+    @property
+    def n_terms(self) -> int:
+        return self.term_offsets.size - 1
+
+    @property
+    def n_postings(self) -> int:
+        return self.docids.size
+
+    def field_index(self, fieldname) -> int:
+        try:
+            return self.field_names.index(fieldname)
+        except ValueError:
+            return -1
+
+    def term_id(self, fieldname, text) -> int:
+        """Posting-list id of (field, text), or -1 (unknown term/field → empty matcher, W10)."""
+        f = self.field_index(fieldname)
+        if f < 0:
+            return -1
+        if self.terms is not None:
+            return self.terms.get((f, text), -1)
+        # numeric vocabulary: term text is the rank, or "t0000123"
+        try:
+            r = int(text[1:]) if isinstance(text, str) and text[:1] == "t" else int(text)
+        except (TypeError, ValueError):
+            return -1
+        if r < 0 or r >= self.vocab_size:
+            return -1
+        return f * self.vocab_size + r
+
+    def field_length(self, fieldname) -> int:
+        f = self.field_index(fieldname)
+        return 0 if f < 0 else int(self.field_length_total[f])
+
+    def avg_field_length(self, fieldname) -> float:
+        """W4: ``field_length / (doc_count_all or 1)``, then ``or 1``."""
+        return (self.field_length(fieldname) / (self.doc_count_all() or 1)) or 1.0
+
+    def postings(self, tid: int):
+        a, b = int(self.term_offsets[tid]), int(self.term_offsets[tid + 1])
+        return self.docids[a:b], self.tfs[a:b]
+
+    def stored_fields(self, docnum: int) -> Mapping:
+        local = docnum - self.doc_base
+        if self.stored is None:
+            return {}
+        return self.stored[local]
+
+    def _stored_names(self):
+        if not self.stored:
+            return []
+        names = []
+        for d in self.stored[:16]:
+            for k in d:
+                if k not in names:
+                    names.append(k)
+        return names
+
+    # ---- construction ---------------------------------------------------------
+    @classmethod
+    def from_documents(cls, docs: Sequence[Mapping[str, object]], fields: Sequence[str],
+                       analyzer=None, stored: Optional[Sequence[str]] = None,
+                       deleted: Iterable[int] = ()) -> "FlatIndex":
+        """Build from tokenised documents: ``doc[field]`` is a token list or a string
+        split on whitespace by default.  Token boosts are all 1 so ``tf`` is the term
+        count (W7)."""
+        analyzer = analyzer or (lambda text: text.split())
+        n = len(docs)
+        nf = len(fields)
+        postings: Dict[Tuple[int, object], Dict[int, float]] = {}
+        lengths = np.zeros((nf, n), dtype=np.int64)
+        for d, doc in enumerate(docs):
+            for f, name in enumerate(fields):
+                v = doc.get(name)
+                if v is None:
+                    continue
+                toks = analyzer(v) if isinstance(v, str) else list(v)
+                lengths[f, d] = len(toks)
+                for t in toks:
+                    p = postings.setdefault((f, t), {})
+                    p[d] = p.get(d, 0.0) + 1.0
+        keys = sorted(postings.keys(), key=lambda k: (k[0], str(k[1])))
+        terms = {k: i for i, k in enumerate(keys)}
+        offs = np.zeros(len(keys) + 1, dtype=np.uint64)
+        dl: List[int] = []
+        tl: List[float] = []
+        for i, k in enumerate(keys):
+            items = sorted(postings[k].items())
+            dl.extend(d for d, _ in items)
+            tl.extend(w for _, w in items)
+            offs[i + 1] = len(dl)
+        lb = np.stack([lengths_to_bytes(lengths[f]) for f in range(nf)]) if nf else np.zeros((0, n), np.uint8)
+        # a field a document does not have keeps length byte 0 (W5: scored with fl=1)
+        del_arr = None
+        deleted = list(deleted)
+        if deleted:
+            del_arr = np.zeros(n, dtype=np.uint8)
+            del_arr[deleted] = 1
+        stored_docs = None
+        if stored:
+            stored_docs = [{k: doc[k] for k in stored if k in doc} for doc in docs]
+        return cls(field_names=fields, n_docs_all=n, term_offsets=offs,
+                   docids=np.array(dl, dtype=np.uint32), tfs=np.array(tl, dtype=np.float32),
+                   term_field=np.array([k[0] for k in keys], dtype=np.uint8),
+                   len_bytes=lb, field_length_total=lengths.sum(axis=1).astype(np.uint64),
+                   terms=terms, deleted=del_arr, stored=stored_docs)
+
+    # ---- document sharding (W8, SURVEY.md §8 e) ------------------------------
+    def shard(self, g: int, n_shards: int) -> "FlatIndex":
+        """Contiguous document-range shard ``g`` of ``n_shards`` with local docids.
+
+        Global statistics (``df``, ``doc_count_all``, field totals) are carried
+        over unchanged so that idf and avgfl are those of the whole corpus.
+        """
+        if not (0 <= g < n_shards):
+            raise ValueError("shard index out of range")
+        lo = (self.n_docs_all * g) // n_shards
+        hi = (self.n_docs_all * (g + 1)) // n_shards
+        keep = (self.docids >= lo) & (self.docids < hi)
+        csum = np.concatenate([[0], np.cumsum(keep, dtype=np.uint64)])
+        offs = csum[self.term_offsets.astype(np.int64)]
+        return FlatIndex(field_names=self.field_names, n_docs_all=hi - lo, term_offsets=offs,
+                         docids=(self.docids[keep] - np.uint32(lo)), tfs=self.tfs[keep],
+                         term_field=self.term_field, len_bytes=self.len_bytes[:, lo:hi],
+                         field_length_total=self.field_length_total, terms=self.terms,
+                         vocab_size=self.vocab_size, df=self.df,
+                         deleted=None if self.deleted is None else self.deleted[lo:hi],
+                         stored=None if self.stored is None else self.stored[lo:hi],
+                         doc_base=self.doc_base + lo,
+                         global_doc_count_all=self.global_doc_count_all,
+                         term_weight_total=self.term_weight_total)
+
+    # ---- persistence (the "checkpoint": a flattened index file) --------------
+    def save(self, path: str) -> None:
+        if self.terms is not None:
+            tf_ = np.array([k[0] for k in self.terms], dtype=np.uint8)
+            tt_ = np.array([str(k[1]) for k in self.terms])
+            ti_ = np.array(list(self.terms.values()), dtype=np.int64)
+        else:
+            tf_, tt_, ti_ = np.zeros(0, np.uint8), np.zeros(0, "U1"), np.zeros(0, np.int64)
+        np.savez(path, version=FORMAT_VERSION, field_names=np.array(self.field_names),
+                 n_docs_all=self.n_docs_all, term_offsets=self.term_offsets, docids=self.docids,
+                 tfs=self.tfs, term_field=self.term_field, len_bytes=self.len_bytes,
+                 field_length_total=self.field_length_total, df=self.df,
+                 deleted=self.deleted if self.deleted is not None else np.zeros(0, np.uint8),
+                 vocab_size=-1 if self.vocab_size is None else self.vocab_size,
+                 doc_base=self.doc_base, global_doc_count_all=self.global_doc_count_all,
+                 dict_field=tf_, dict_text=tt_, dict_id=ti_)
+
+    @classmethod
+    def load(cls, path: str) -> "FlatIndex":
+        z = np.load(path, allow_pickle=False)
+        if int(z["version"]) != FORMAT_VERSION:
+            raise ValueError("unsupported flat index version %s" % z["version"])
+        terms = None
+        if z["dict_id"].size:
+            terms = {(int(f), str(t)): int(i) for f, t, i in zip(z["dict_field"], z["dict_text"], z["dict_id"])}
+        vs = int(z["vocab_size"])
+        return cls(field_names=[str(s) for s in z["field_names"]], n_docs_all=int(z["n_docs_all"]),
+                   term_offsets=z["term_offsets"], docids=z["docids"], tfs=z["tfs"],
+                   term_field=z["term_field"], len_bytes=z["len_bytes"],
+                   field_length_total=z["field_length_total"], terms=terms,
+                   vocab_size=None if vs < 0 else vs, df=z["df"],
+                   deleted=z["deleted"] if z["deleted"].size else None,
+                   doc_base=int(z["doc_base"]), global_doc_count_all=int(z["global_doc_count_all"]))

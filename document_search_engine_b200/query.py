@@ -1,0 +1,304 @@
+"""Query tree nodes with the Whoosh surface the reference relies on.
+
+The reference builds its trees with ``whoosh.qparser.QueryParser`` (default
+group AND, ``OR`` keyword; reference ``my_flask.py:189-193``, ``:302``) and
+greps ``str(query)`` for ``"<field>:"`` (``my_flask.py:201-205``).  The engine
+needs ``Term`` / ``And`` / ``Or`` (b) plus ``Every`` for the
+CLI probe (``cli.py:8-9``).  A tiny parser for the ``a b OR c field:d`` subset
+is provided so the front ends have something to call; the full query language
+(phrases, wildcards, ranges, NOT) is out of scope.
+
+``normalize()`` lowers a tree to the engine's input form: an AND of groups,
+each group an OR of weighted leaves.  ``Or`` of plain leaves is the one-group
+case.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass
+from typing import Iterable, List, Sequence, Tuple
+
+
+class Query:
+    boost: float = 1.0
+
+    def __and__(self, other):
+        return And([self, other])
+
+    def __or__(self, other):
+        return Or([self, other])
+
+    def leaves(self) -> Iterable["Term"]:
+        raise NotImplementedError
+
+    def all_terms(self):
+        return {(t.fieldname, t.text) for t in self.leaves()}
+
+    def normalize(self) -> "Query":
+        return self
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
+
+
+class _Null(Query):
+    """Matches nothing (what the parser returns for an empty string)."""
+
+    def __repr__(self):
+        return "<_NullQuery>"
+
+    def __str__(self):
+        return ""
+
+    def __eq__(self, other):
+        return isinstance(other, _Null)
+
+    def __hash__(self):
+        return hash("_Null")
+
+    def leaves(self):
+        return iter(())
+
+
+NullQuery = _Null()
+
+
+class Term(Query):
+    def __init__(self, fieldname: str, text, boost: float = 1.0):
+        self.fieldname = fieldname
+        self.text = text
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return (isinstance(other, Term) and other.fieldname == self.fieldname
+                and other.text == self.text and other.boost == self.boost)
+
+    def __hash__(self):
+        return hash((self.fieldname, self.text, self.boost))
+
+    def __repr__(self):
+        r = "Term(%r, %r" % (self.fieldname, self.text)
+        if self.boost != 1.0:
+            r += ", boost=%s" % self.boost
+        return r + ")"
+
+    def __str__(self):
+        # the reference looks for "<field>:" in this rendering (my_flask.py:203)
+        t = "%s:%s" % (self.fieldname, self.text)
+        if self.boost != 1.0:
+            t += "^%s" % self.boost
+        return t
+
+    def leaves(self):
+        yield self
+
+
+class Every(Query):
+    """All documents that have any term in ``fieldname`` (cli.py:8-9)."""
+
+    def __init__(self, fieldname: str = None, boost: float = 1.0):
+        self.fieldname = fieldname
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return (isinstance(other, Every) and other.fieldname == self.fieldname
+                and other.boost == self.boost)
+
+    def __hash__(self):
+        return hash(("Every", self.fieldname, self.boost))
+
+    def __repr__(self):
+        return "Every(%r)" % (self.fieldname,)
+
+    def __str__(self):
+        return "%s:*" % (self.fieldname or "*")
+
+    def leaves(self):
+        return iter(())
+
+
+class _Compound(Query):
+    JOINT = " ? "
+
+    def __init__(self, subqueries: Sequence[Query], boost: float = 1.0):
+        for q in subqueries:
+            if not isinstance(q, Query):
+                raise TypeError("%r is not a query" % (q,))
+        self.subqueries = list(subqueries)
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return (type(other) is type(self) and other.subqueries == self.subqueries
+                and other.boost == self.boost)
+
+    def __hash__(self):
+        h = hash(type(self).__name__) ^ hash(self.boost)
+        for q in self.subqueries:
+            h ^= hash(q)
+        return h
+
+    def __repr__(self):
+        r = "%s(%r" % (type(self).__name__, self.subqueries)
+        if self.boost != 1.0:
+            r += ", boost=%s" % self.boost
+        return r + ")"
+
+    def __str__(self):
+        r = "(" + self.JOINT.join(str(q) for q in self.subqueries) + ")"
+        if self.boost != 1.0:
+            r += "^%s" % self.boost
+        return r
+
+    def __iter__(self):
+        return iter(self.subqueries)
+
+    def __len__(self):
+        return len(self.subqueries)
+
+    def __getitem__(self, i):
+        return self.subqueries[i]
+
+    def leaves(self):
+        for q in self.subqueries:
+            yield from q.leaves()
+
+    def normalize(self):
+        """Flatten same-type nesting, drop null children, unwrap singletons."""
+        subs: List[Query] = []
+        for q in self.subqueries:
+            q = q.normalize()
+            if isinstance(q, _Null):
+                continue
+            if type(q) is type(self) and q.boost == 1.0:
+                subs.extend(q.subqueries)
+            else:
+                subs.append(q)
+        if not subs:
+            return NullQuery
+        if len(subs) == 1 and self.boost == 1.0:
+            return subs[0]
+        return type(self)(subs, boost=self.boost)
+
+
+class And(_Compound):
+    JOINT = " AND "
+
+
+class Or(_Compound):
+    JOINT = " OR "
+
+
+# --------------------------------------------------------------------------
+# Lowering to the engine's input form
+# --------------------------------------------------------------------------
+
+@dataclass
+class Leaf:
+    fieldname: str
+    text: object
+    boost: float
+    group: int
+
+
+class UnsupportedQuery(NotImplementedError):
+    """Raised for trees the GPU path does not serve (no CPU fallback exists)."""
+
+
+def lower(q: Query) -> Tuple[List[Leaf], int, str]:
+    """Lower ``q`` to ``(leaves, n_groups, kind)``.
+
+    ``kind`` is ``"groups"`` (AND of OR-groups; ``Or`` of leaves is one group),
+    ``"every"`` or ``"null"``.  Boosts on compound nodes are pushed into the
+    leaves, which is exact because W10 scores are sums of leaf scores.
+    """
+    q = q.normalize()
+    if isinstance(q, _Null):
+        return [], 0, "null"
+    if isinstance(q, Every):
+        return [Leaf(q.fieldname, None, q.boost, 0)], 1, "every"
+    if isinstance(q, Term):
+        return [Leaf(q.fieldname, q.text, q.boost, 0)], 1, "groups"
+    if isinstance(q, Or):
+        leaves = []
+        for s in q.subqueries:
+            if not isinstance(s, Term):
+                raise UnsupportedQuery("Or() may only contain Term leaves on the GPU path: %r" % (s,))
+            leaves.append(Leaf(s.fieldname, s.text, s.boost * q.boost, 0))
+        return leaves, 1, "groups"
+    if isinstance(q, And):
+        leaves = []
+        g = 0
+        for s in q.subqueries:
+            if isinstance(s, Term):
+                leaves.append(Leaf(s.fieldname, s.text, s.boost * q.boost, g))
+            elif isinstance(s, Or):
+                for t in s.subqueries:
+                    if not isinstance(t, Term):
+                        raise UnsupportedQuery("And(Or(...)) groups may only contain Term leaves: %r" % (t,))
+                    leaves.append(Leaf(t.fieldname, t.text, t.boost * s.boost * q.boost, g))
+            else:
+                raise UnsupportedQuery("And() may contain Term or Or(Term...) children: %r" % (s,))
+            g += 1
+        return leaves, g, "groups"
+    raise UnsupportedQuery("unsupported query node %r" % (q,))
+
+
+# --------------------------------------------------------------------------
+# Minimal parser (Term / AND / OR / field:term / parentheses-free)
+# --------------------------------------------------------------------------
+
+_TOKEN_RE = re.compile(r"\s*(?:(\w+):)?([^\s()]+)")
+
+
+class QueryParser:
+    """``QueryParser(fieldname, schema)`` for the subset ``a b``, ``a AND b``,
+    ``a OR b``, ``field:a``.  AND binds tighter than OR, as in Whoosh's default
+    grammar.  ``analyzer`` maps a raw token to zero or more index terms
+    (lower-casing, stemming ...); the default lower-cases.
+    """
+
+    def __init__(self, fieldname: str, schema=None, analyzer=None, termclass=Term):
+        self.fieldname = fieldname
+        self.schema = schema
+        self.analyzer = analyzer or (lambda field, text: [text.lower()])
+        self.termclass = termclass
+
+    def add_plugin(self, plugin):  # accepted for call-compatibility (my_flask.py:190)
+        return None
+
+    def parse(self, text: str) -> Query:
+        nodes: List[object] = []          # Query nodes and the markers "AND" / "OR"
+        for m in _TOKEN_RE.finditer(text or ""):
+            field, tok = m.group(1), m.group(2)
+            if field is None and tok in ("AND", "OR"):
+                nodes.append(tok)
+                continue
+            field = field or self.fieldname
+            if self.schema is not None and hasattr(self.schema, "names") and field not in self.schema.names():
+                tok, field = "%s:%s" % (field, tok), self.fieldname
+            terms = [self.termclass(field, t) for t in self.analyzer(field, tok)]
+            if len(terms) == 1:
+                nodes.append(terms[0])
+            elif terms:
+                nodes.append(And(terms))
+        # Infix operators take their immediate neighbours, AND before OR; what is
+        # left side by side is joined by the default group (AND), as the
+        # reference's form explains ("both words", search-form.html:21).
+        for op, cls in (("AND", And), ("OR", Or)):
+            out: List[object] = []
+            i = 0
+            while i < len(nodes):
+                n = nodes[i]
+                if n == op and out and isinstance(out[-1], Query) and i + 1 < len(nodes) \
+                        and isinstance(nodes[i + 1], Query):
+                    out[-1] = cls([out[-1], nodes[i + 1]])
+                    i += 2
+                    continue
+                if n == op:         # dangling operator: drop it
+                    i += 1
+                    continue
+                out.append(n)
+                i += 1
+            nodes = out
+        nodes = [n for n in nodes if isinstance(n, Query)]
+        return And(nodes).normalize() if nodes else NullQuery

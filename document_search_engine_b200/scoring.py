@@ -1,0 +1,81 @@
+"""Weighting models with the ``whoosh.scoring`` surface the reference uses.
+
+The reference passes the *class* ``BM25F`` (or a subclass with a ``final`` hook)
+to ``ix.searcher(weighting=...)`` (``my_flask.py:183-184``) and subclasses it in
+``my_whoosh.py:127-154``.  W1-W4 of SURVEY.md §8 c give the arithmetic; the
+host side evaluates everything that is per-term or per-field in float64 and
+hands the GPU two float32 products:
+
+* per leaf   ``w = idf * (K1 + 1) * boost``
+* per field  ``norm[b] = K1 * ((1 - B_field) + B_field * fl(b) / avgfl)``
+
+so that the per-posting work on the device is ``w * tf / (tf + norm[lb])``.
+"""
+from __future__ import annotations
+
+from math import log
+
+import numpy as np
+
+from .numeric import norm_table
+
+
+class WeightingModel:
+    use_final = False
+
+    def idf(self, searcher, fieldname, text) -> float:
+        """W3: ``log(dc / (df + 1)) + 1`` with corpus-wide dc (incl. deleted) and stored df."""
+        n = searcher.doc_frequency(fieldname, text)
+        dc = searcher.doc_count_all()
+        return log(dc / (n + 1)) + 1
+
+    def final(self, searcher, docnum, score):
+        return score
+
+
+class BM25F(WeightingModel):
+    """``BM25F(B=0.75, K1=1.2, **{"<field>_B": b})`` (W2)."""
+
+    def __init__(self, B=0.75, K1=1.2, **kwargs):
+        self.B = float(B)
+        self.K1 = float(K1)
+        self._field_B = {}
+        for k, v in kwargs.items():
+            if k.endswith("_B"):
+                self._field_B[k[:-2]] = float(v)
+            else:
+                raise TypeError("unexpected BM25F argument %r" % k)
+
+    def field_B(self, fieldname) -> float:
+        return self._field_B.get(fieldname, self.B)
+
+    def supports_block_quality(self):
+        return True
+
+    # -- host-side products consumed by the engine ---------------------------
+    def leaf_weight(self, searcher, fieldname, text, boost=1.0) -> float:
+        return self.idf(searcher, fieldname, text) * (self.K1 + 1.0) * boost
+
+    def norm_tables(self, ix) -> np.ndarray:
+        """float32 ``[n_fields, 256]`` norm tables for index ``ix`` (global avgfl, W4/W8)."""
+        out = np.empty((len(ix.field_names), 256), dtype=np.float32)
+        for f, name in enumerate(ix.field_names):
+            out[f] = norm_table(self.field_B(name), self.K1, ix.avg_field_length(name)).astype(np.float32)
+        return out
+
+    def key(self):
+        return ("BM25F", self.B, self.K1, tuple(sorted(self._field_B.items())))
+
+
+def bm25(idf, tf, fl, avgfl, B, K1):
+    """W1, in exactly this association (float64 when given Python floats)."""
+    return idf * ((tf * (K1 + 1)) / (tf + K1 * ((1 - B) + B * fl / avgfl)))
+
+
+def instantiate(weighting) -> WeightingModel:
+    """A weighting *class* is instantiated with defaults (W2; ``my_flask.py:183``)."""
+    if weighting is None:
+        return BM25F()
+    if isinstance(weighting, type):
+        return weighting()
+    return weighting

@@ -1,0 +1,129 @@
+"""CPU ORACLE (test infrastructure, not product code) — term-at-a-time, vectorised.
+
+PARITY UNPINNED (see ``oracle/whoosh_port.py`` for why): same W1-W14 restatement
+of Whoosh 2.7.4 semantics, evaluated one posting *list* at a time with numpy in
+float64 so that million-document ground truth is affordable.  ``tests/`` checks
+that this and the doc-at-a-time port agree on random indexes; both are pinned
+to KAT-1 of SURVEY.md §8 c.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this module.
+
+Reference call sites this follows: ``my_flask.py:183-184`` (BM25F defaults, W2),
+``:208``/``:211``/``:304`` (limits), ``my_index.py:172-177`` (TEXT fields).
+"""
+from __future__ import annotations
+
+from math import log
+
+import numpy as np
+
+B2L = np.array([int(round((pow(1.033, i) - 1) * 27)) for i in range(256)], dtype=np.float64)
+B2L_SCORING = B2L.copy()
+B2L_SCORING[0] = 1.0            # W5: byte 0 → default length 1
+
+
+def lower_query(q):
+    """``(groups, kind)``: ``groups`` is a list of OR-groups, each a list of
+    ``(fieldname, text, boost)``; all groups must match (W10)."""
+    name = type(q).__name__
+    if name == "_Null":
+        return [], "null"
+    if name == "Every":
+        return [[(q.fieldname, None, q.boost)]], "every"
+    if name == "Term":
+        return [[(q.fieldname, q.text, q.boost)]], "groups"
+    if name == "Or":
+        return [[(t.fieldname, t.text, t.boost * q.boost) for t in q.subqueries]], "groups"
+    if name == "And":
+        groups = []
+        for s in q.subqueries:
+            if type(s).__name__ == "Term":
+                groups.append([(s.fieldname, s.text, s.boost * q.boost)])
+            elif type(s).__name__ == "Or":
+                groups.append([(t.fieldname, t.text, t.boost * s.boost * q.boost) for t in s.subqueries])
+            else:
+                raise NotImplementedError(s)
+        return groups, "groups"
+    raise NotImplementedError(name)
+
+
+class NumpyOracle:
+    def __init__(self, ix, B=0.75, K1=1.2, field_B=None, shards=None):
+        self.ix = ix
+        self.B, self.K1 = B, K1
+        self.field_B = dict(field_B or {})
+        self.shards = list(shards) if shards is not None else [ix]
+
+    def idf(self, fieldname, text):
+        tid = self.ix.term_id(fieldname, text)
+        df = 0 if tid < 0 else int(self.ix.df[tid])
+        return log(self.ix.doc_count_all() / (df + 1)) + 1                      # W3
+
+    def avgfl(self, fieldname):
+        f = self.ix.field_names.index(fieldname)
+        return (int(self.ix.field_length_total[f]) / (self.ix.doc_count_all() or 1)) or 1   # W4
+
+    def leaf_scores(self, sub, fieldname, text, boost):
+        """(local docids, float64 scores) of one leaf in one shard; deleted docs removed (W9)."""
+        tid = sub.term_id(fieldname, text)
+        if tid < 0:
+            return np.zeros(0, np.int64), np.zeros(0, np.float64)
+        a, b = int(sub.term_offsets[tid]), int(sub.term_offsets[tid + 1])
+        d = sub.docids[a:b].astype(np.int64)
+        tf = sub.tfs[a:b].astype(np.float64)
+        f = sub.field_names.index(fieldname)
+        fl = B2L_SCORING[sub.len_bytes[f][d]]
+        B = self.field_B.get(fieldname, self.B)
+        K1 = self.K1
+        s = self.idf(fieldname, text) * ((tf * (K1 + 1)) / (tf + K1 * ((1 - B) + B * fl / self.avgfl(fieldname))))  # W1
+        if boost != 1.0:
+            s = s * boost
+        if sub.deleted is not None:
+            keep = sub.deleted[d] == 0
+            d, s = d[keep], s[keep]
+        return d, s
+
+    def match_all(self, q):
+        """All matches as (global docids ascending, float64 scores)."""
+        groups, kind = lower_query(q)
+        if kind == "null":
+            return np.zeros(0, np.int64), np.zeros(0, np.float64)
+        ds, ss = [], []
+        for sub in self.shards:
+            n = sub.len_bytes.shape[1]
+            if kind == "every":
+                fname, _, boost = groups[0][0]
+                if fname not in sub.field_names:
+                    continue
+                m = sub.len_bytes[sub.field_names.index(fname)] != 0
+                if sub.deleted is not None:
+                    m &= sub.deleted == 0
+                d = np.nonzero(m)[0]
+                ds.append(d + sub.doc_base)
+                ss.append(np.full(d.size, float(boost)))
+                continue
+            acc = np.zeros(n, np.float64)
+            cnt = np.zeros(n, np.int32)
+            for g in groups:
+                hit = np.zeros(n, bool)
+                for fname, text, boost in g:
+                    d, s = self.leaf_scores(sub, fname, text, boost)
+                    acc[d] += s                                                  # W10: sum of leaf scores
+                    hit[d] = True
+                cnt += hit
+            d = np.nonzero(cnt == len(groups))[0]
+            ds.append(d + sub.doc_base)
+            ss.append(acc[d])
+        if not ds:
+            return np.zeros(0, np.int64), np.zeros(0, np.float64)
+        return np.concatenate(ds), np.concatenate(ss)
+
+    def search(self, q, limit=10):
+        """``(top, total)`` with ``top`` = list of ``(score, docnum)`` in W11 order."""
+        d, s = self.match_all(q)
+        total = int(d.size)
+        order = np.lexsort((d, -s))                                              # score desc, docnum asc
+        if limit is not None:
+            order = order[:limit]
+        return [(float(s[i]), int(d[i])) for i in order], total

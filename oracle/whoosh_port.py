@@ -1,0 +1,381 @@
+"""CPU ORACLE (test infrastructure, not product code) — doc-at-a-time port.
+
+PARITY UNPINNED: the algorithm on this path lives in the third-party library
+Whoosh 2.7.4 (reference ``requirements.txt:6``), which is neither vendored under
+``/root/reference`` nor installable here (no network, no wheel).  The reference
+holds no tests, golden vectors or fixtures for this path (SURVEY.md §4, §8 c).
+This file therefore restates the *published* Whoosh 2.7.4 behaviour, item by
+item as W1-W14 of SURVEY.md §8 c, and is anchored on the reference's call sites:
+
+* weighting selection / defaults ........ ``my_flask.py:183-184``  (W2)
+* ``search_page`` / ``search`` limits ..... ``my_flask.py:208``, ``:211``, ``:304``, ``cli.py:9``
+* ``final`` hook contract ................ ``my_whoosh.py:127-154``  (W14)
+* which fields are scorable TEXT ........ ``my_index.py:172-177``
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
+may import this module.  It deliberately mirrors the shape of the library it
+restates (one Python-level step per matching posting: matcher tree → scorer →
+heap collector), because that is what the CPU baseline is meant to time.
+
+The index argument is duck-typed: any object with ``term_offsets``, ``docids``,
+``tfs``, ``len_bytes[f, d]``, ``field_length_total``, ``df``, ``deleted``,
+``doc_base``, ``field_names``, ``doc_count_all()`` and ``term_id(field, text)``.
+Queries are duck-typed on the class names ``Term`` / ``And`` / ``Or`` / ``Every``.
+"""
+from __future__ import annotations
+
+from heapq import heappush, heapreplace
+from math import log
+
+# ---------------------------------------------------------------------------
+# W6 / W5: length quantisation (Whoosh util/numeric.py)
+# ---------------------------------------------------------------------------
+
+
+def length_to_byte(length):
+    if length is None:
+        return 0
+    if length >= 108116:
+        return 255
+    return int(round(log((length / 27.0) + 1, 1.033)))
+
+
+_B2L = [int(round((pow(1.033, i) - 1) * 27)) for i in range(256)]
+
+
+def byte_to_length(b):
+    return _B2L[b]
+
+
+# ---------------------------------------------------------------------------
+# W1-W4: BM25F (Whoosh scoring.py)
+# ---------------------------------------------------------------------------
+
+
+def bm25(idf, tf, fl, avgfl, B, K1):
+    # W1, in exactly this association
+    return idf * ((tf * (K1 + 1)) / (tf + K1 * ((1 - B) + B * fl / avgfl)))
+
+
+class OracleSearcher:
+    """Top-level ("parent") searcher: owns the corpus-wide statistics (W3, W4, W8)."""
+
+    def __init__(self, ix, B=0.75, K1=1.2, field_B=None, final=None, shards=None):
+        self.ix = ix
+        self.B = B
+        self.K1 = K1
+        self.field_B = dict(field_B or {})
+        self.final = final              # W14: callable(searcher, docnum, score) or None
+        # W8: a multi-segment index is a list of sub-indexes with doc offsets
+        self.shards = list(shards) if shards is not None else [ix]
+        self._idf = {}
+
+    def doc_count_all(self):
+        return self.ix.doc_count_all()
+
+    def doc_frequency(self, fieldname, text):
+        tid = self.ix.term_id(fieldname, text)
+        return 0 if tid < 0 else int(self.ix.df[tid])
+
+    def idf(self, fieldname, text):
+        key = (fieldname, text)
+        v = self._idf.get(key)
+        if v is None:
+            # W3: natural log, true division, dc includes deleted documents
+            v = log(self.doc_count_all() / (self.doc_frequency(fieldname, text) + 1)) + 1
+            self._idf[key] = v
+        return v
+
+    def avg_field_length(self, fieldname):
+        f = self.ix.field_names.index(fieldname)
+        # W4
+        return (int(self.ix.field_length_total[f]) / (self.doc_count_all() or 1)) or 1
+
+    # -- searching ----------------------------------------------------------
+    def search(self, q, limit=10):
+        """Returns ``(top, total)``: ``top`` is a list of ``(score, global docnum)`` in
+        W11 order; ``total`` is the exact number of matching documents (W13)."""
+        heap = []
+        allhits = []
+        total = 0
+        for sub in self.shards:
+            m = self._matcher(q, sub)
+            base = sub.doc_base
+            while m.is_active():
+                d = m.id() + base
+                score = m.score()
+                if self.final is not None:
+                    score = self.final(self, d, score)          # W14: before the heap
+                total += 1
+                if limit is None:
+                    allhits.append((score, -d))                 # UnlimitedCollector
+                elif len(heap) < limit:
+                    heappush(heap, (score, -d))
+                elif score > heap[0][0]:                        # W11: strict >
+                    heapreplace(heap, (score, -d))
+                m.next()
+        items = allhits if limit is None else heap
+        items.sort(reverse=True)                                # score desc, docnum asc
+        return [(s, -nd) for s, nd in items], total
+
+    def _matcher(self, q, sub):
+        name = type(q).__name__
+        if name == "Term":
+            tid = sub.term_id(q.fieldname, q.text)
+            if tid < 0:
+                return NullMatcher()                            # W10: unknown term/field
+            a, b = int(sub.term_offsets[tid]), int(sub.term_offsets[tid + 1])
+            f = sub.field_names.index(q.fieldname)
+            scorer = BM25FScorer(self, q.fieldname, q.text,
+                                 self.field_B.get(q.fieldname, self.B), self.K1)
+            m = PostingMatcher(sub.docids[a:b].tolist(), sub.tfs[a:b].tolist(),
+                               sub.len_bytes[f], scorer, sub.deleted)
+            return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
+        if name == "Every":
+            f = sub.field_names.index(q.fieldname) if q.fieldname in sub.field_names else -1
+            if f < 0:
+                return NullMatcher()
+            lb = sub.len_bytes[f]
+            dele = sub.deleted
+            ids = [d for d in range(lb.shape[0]) if lb[d] and not (dele is not None and dele[d])]
+            return ConstMatcher(ids, q.boost)
+        if name in ("And", "Or"):
+            subs = [self._matcher(s, sub) for s in q.subqueries]
+            if not subs:
+                return NullMatcher()
+            cls = IntersectionMatcher if name == "And" else UnionMatcher
+            m = _binary_tree(cls, subs)
+            return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
+        if name == "_Null":
+            return NullMatcher()
+        raise NotImplementedError(name)
+
+
+def _binary_tree(cls, ms):
+    if len(ms) == 1:
+        return ms[0]
+    half = len(ms) // 2
+    return cls(_binary_tree(cls, ms[:half]), _binary_tree(cls, ms[half:]))
+
+
+class BM25FScorer:
+    def __init__(self, parent, fieldname, text, B, K1):
+        self.idf = parent.idf(fieldname, text)                  # parent searcher (W3, W8)
+        self.avgfl = parent.avg_field_length(fieldname) or 1
+        self.B = B
+        self.K1 = K1
+
+    def score(self, weight, length_byte):
+        fl = byte_to_length(length_byte) if length_byte else 1  # W5
+        return bm25(self.idf, weight, fl, self.avgfl, self.B, self.K1)
+
+
+# ---------------------------------------------------------------------------
+# Matchers (Whoosh matching/)
+# ---------------------------------------------------------------------------
+
+
+class NullMatcher:
+    def is_active(self):
+        return False
+
+    def id(self):
+        raise IndexError
+
+    def next(self):
+        pass
+
+    def skip_to(self, d):
+        pass
+
+    def score(self):
+        return 0.0
+
+
+class PostingMatcher:
+    """Leaf: one term's postings, deleted documents filtered out (W9)."""
+
+    def __init__(self, ids, weights, len_bytes, scorer, deleted):
+        self.ids = ids
+        self.weights = weights
+        self.lb = len_bytes
+        self.scorer = scorer
+        self.deleted = deleted
+        self.i = 0
+        self._skip_deleted()
+
+    def _skip_deleted(self):
+        if self.deleted is not None:
+            ids, dele, n = self.ids, self.deleted, len(self.ids)
+            while self.i < n and dele[ids[self.i]]:
+                self.i += 1
+
+    def is_active(self):
+        return self.i < len(self.ids)
+
+    def id(self):
+        return self.ids[self.i]
+
+    def next(self):
+        self.i += 1
+        self._skip_deleted()
+
+    def skip_to(self, d):
+        ids, n = self.ids, len(self.ids)
+        while self.i < n and ids[self.i] < d:
+            self.i += 1
+        self._skip_deleted()
+
+    def score(self):
+        return self.scorer.score(self.weights[self.i], int(self.lb[self.ids[self.i]]))
+
+
+class ConstMatcher:
+    """``Every``: every listed document scores the (boost) constant."""
+
+    def __init__(self, ids, weight):
+        self.ids = ids
+        self.w = weight
+        self.i = 0
+
+    def is_active(self):
+        return self.i < len(self.ids)
+
+    def id(self):
+        return self.ids[self.i]
+
+    def next(self):
+        self.i += 1
+
+    def skip_to(self, d):
+        while self.i < len(self.ids) and self.ids[self.i] < d:
+            self.i += 1
+
+    def score(self):
+        return self.w
+
+
+class BoostMatcher:
+    def __init__(self, child, boost):
+        self.child = child
+        self.boost = boost
+
+    def is_active(self):
+        return self.child.is_active()
+
+    def id(self):
+        return self.child.id()
+
+    def next(self):
+        self.child.next()
+
+    def skip_to(self, d):
+        self.child.skip_to(d)
+
+    def score(self):
+        return self.child.score() * self.boost
+
+
+class UnionMatcher:
+    """W10: documents in either child; score = sum of the children positioned there."""
+
+    def __init__(self, a, b):
+        self.a = a
+        self.b = b
+
+    def is_active(self):
+        return self.a.is_active() or self.b.is_active()
+
+    def id(self):
+        a, b = self.a, self.b
+        if not a.is_active():
+            return b.id()
+        if not b.is_active():
+            return a.id()
+        return min(a.id(), b.id())
+
+    def next(self):
+        a, b = self.a, self.b
+        aa, ba = a.is_active(), b.is_active()
+        if aa and ba:
+            ai, bi = a.id(), b.id()
+            if ai <= bi:
+                a.next()
+            if bi <= ai:
+                b.next()
+        elif aa:
+            a.next()
+        elif ba:
+            b.next()
+
+    def skip_to(self, d):
+        self.a.skip_to(d)
+        self.b.skip_to(d)
+
+    def score(self):
+        a, b = self.a, self.b
+        if not a.is_active():
+            return b.score()
+        if not b.is_active():
+            return a.score()
+        ai, bi = a.id(), b.id()
+        if ai < bi:
+            return a.score()
+        if bi < ai:
+            return b.score()
+        return a.score() + b.score()
+
+
+class IntersectionMatcher:
+    """W10: documents in both children; score = sum of both."""
+
+    def __init__(self, a, b):
+        self.a = a
+        self.b = b
+        self._find()
+
+    def _find(self):
+        a, b = self.a, self.b
+        while a.is_active() and b.is_active():
+            ai, bi = a.id(), b.id()
+            if ai == bi:
+                return
+            if ai < bi:
+                a.skip_to(bi)
+            else:
+                b.skip_to(ai)
+
+    def is_active(self):
+        return self.a.is_active() and self.b.is_active()
+
+    def id(self):
+        return self.a.id()
+
+    def next(self):
+        self.a.next()
+        self._find()
+
+    def skip_to(self, d):
+        self.a.skip_to(d)
+        self.b.skip_to(d)
+        self._find()
+
+    def score(self):
+        return self.a.score() + self.b.score()
+
+
+# ---------------------------------------------------------------------------
+# W13: search_page arithmetic (Whoosh searching.ResultsPage)
+# ---------------------------------------------------------------------------
+
+
+def page_view(total, pagenum, pagelen):
+    """Returns ``(pagenum, offset, pagelen, pagecount)`` after Whoosh's clamping."""
+    if pagenum < 1:
+        raise ValueError("pagenum must be >= 1")
+    pagecount = -(-total // pagelen)
+    pagenum = min(pagecount, pagenum)
+    offset = (pagenum - 1) * pagelen
+    if offset + pagelen > total:
+        pagelen = total - offset
+    return pagenum, offset, pagelen, pagecount
