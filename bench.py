@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Benchmark of the BM25F scoring + top-k hot path (BASELINE.json metric).
+
+``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line on rank 0.
+
+A *step* is one pass of the hot path over one batch of synthetic queries:
+BASELINE.json ``configs[1]`` — 1M synthetic documents (Zipf vocabulary 200k), 10k batched
+2-4-term AND/OR queries, top-10.  For N > 1 (one process per GPU, launched by torchrun) the same
+corpus is document-sharded over the ranks and the local top-k lists are merged after an NCCL
+all-gather, so total work is fixed (``"scaling": "strong"``).
+
+* ``value``   queries/s with the packed query batch and the plan already resident in HBM;
+              timed with CUDA events on the launching stream, max over ranks.
+* ``e2e``     the same metric through the C-ABI entry ``bm25f_search_batch`` (N = 1) /
+              ``ShardedSearcher.search_packed`` (N > 1) with HOST buffers: host planning, H2D of
+              the batch, kernels, (all-gather + merge), D2H of the results, all inside the timed
+              region.
+* ``roofline`` achieved algorithmic posting bytes/s of the scoring kernel (9 B per posting
+              touched, SURVEY.md §8 d) from the library's CUDA events around that kernel, over the
+              same timed steps, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+* ``cpu_baseline`` the oracle's doc-at-a-time Whoosh-semantics port (``oracle/whoosh_port.py``;
+              Whoosh itself is pure Python and not installable here) on a bounded query sample,
+              one worker process per host core.
+
+``--impl reference`` times that CPU port alone (the reference's own implementation of the path
+is Whoosh, which is absent) on the same config/metric/unit.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_PER_POSTING = 9.0      # u32 docid + f32 weight + u8 length byte (SURVEY.md §8 d)
+FALLBACK_HBM_GBS = 6650.0    # B200_PROFILING.md fallback if MEASURED_PEAKS.json is absent
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (the oracle port; the only place bench.py executes oracle/)
+# ----------------------------------------------------------------------------------------------
+_CPU_IX = None
+_CPU_K = 10
+
+
+def _cpu_worker(queries):
+    from oracle.whoosh_port import OracleSearcher
+    s = OracleSearcher(_CPU_IX)
+    t = time.perf_counter()
+    n = 0
+    for q in queries:
+        s.search(q, limit=_CPU_K)
+        n += 1
+    return n, time.perf_counter() - t
+
+
+def cpu_baseline(ix, queries, k, target_seconds=15.0, cores=None):
+    """Whole-machine throughput of the Whoosh-semantics port on a bounded sample."""
+    global _CPU_IX, _CPU_K
+    _CPU_IX, _CPU_K = ix, k
+    cores = cores or os.cpu_count() or 1
+    # pilot on one core to size the sample
+    pilot = queries[:8]
+    _, dt = _cpu_worker(pilot)
+    per_q = max(dt / len(pilot), 1e-6)
+    n = int(min(len(queries), max(cores * 4, target_seconds * cores / per_q)))
+    sample = queries[:n]
+    chunks = [sample[i::cores] for i in range(cores)]
+    chunks = [c for c in chunks if c]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(len(chunks)) as pool:
+        done = pool.map(_cpu_worker, chunks)
+    wall = time.perf_counter() - t0
+    nq = sum(d[0] for d in done)
+    return {"value": nq / wall, "unit": "queries/s", "cores": len(chunks), "kind": "port",
+            "sample": "first %d of the step's queries, doc-at-a-time Python port of Whoosh 2.7.4 semantics "
+                      "(oracle/whoosh_port.py), %d fork workers, %.1f s wall" % (nq, len(chunks), wall)}
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+def workload(args):
+    from document_search_engine_b200.corpus import CONFIGS
+    c = dict(CONFIGS[args.config])
+    if args.docs:
+        c["n_docs"] = args.docs
+    if args.queries:
+        c["n_queries"] = args.queries
+    if args.k:
+        c["k"] = args.k
+    return c
+
+
+def config_json(args, c, world):
+    return {"workload": "BASELINE configs[%d]: %d synthetic docs (Zipf s=1 vocab %d, lognormal(5,0.6) lengths), "
+                        "%d batched %d-%d-term %s queries, top-%d" % (
+                            args.config - 1, c["n_docs"], c["vocab"], c["n_queries"], c["min_terms"], c["max_terms"],
+                            "AND-of-variant-OR" if c.get("variants") else {"mixed": "AND/OR", "and": "AND", "or": "OR"}[c["mode"]],
+                            c["k"]),
+            "n_docs": c["n_docs"], "n_queries": c["n_queries"], "k": c["k"],
+            "sharding": "none" if world == 1 else "documents, %d contiguous ranges, NCCL all-gather of local top-k" % world,
+            "l2": "inputs larger than L2: a step streams the batch's posting lists out of a %.2f GiB "
+                  "device-resident index (L2 is 126 MB)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from document_search_engine_b200.corpus import config_corpus, config_queries
+    c = workload(args)
+    t0 = time.perf_counter()
+    ix = config_corpus(args.config, device="cpu" if not _cuda() else None, n_docs=c["n_docs"])
+    qs = config_queries(args.config, c["n_queries"])
+    log("reference arm: corpus ready in %.1f s" % (time.perf_counter() - t0))
+    target = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        # rotate the sample so steps do not re-time identical queries
+        off = (i * 997) % max(1, len(qs.queries) - 1)
+        sample = qs.queries[off:] + qs.queries[:off]
+        last = cpu_baseline(ix, sample, c["k"], target_seconds=target)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    cfg = config_json(args, c, 1)
+    cfg["l2"] = "n/a (CPU)"
+    last["value"] = v
+    out = {"impl": "reference", "metric": "BM25F top-%d queries/sec" % c["k"], "value": v, "unit": "queries/s",
+           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1000.0 * c["n_queries"] / v, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "cpu_baseline": last,
+           "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "note": "Whoosh 2.7.4 (pure Python, reference requirements.txt:6) is not installable here; this is the "
+                   "oracle's doc-at-a-time port of its semantics on all host cores; each step is a bounded "
+                   "sample of the workload and ms_per_step is extrapolated to the full batch"}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def _cuda():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2)
+    ap.add_argument("--docs", type=int, default=0)
+    ap.add_argument("--queries", type=int, default=0)
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--tile-docs", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--split", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--check", type=int, default=32, help="queries checked against the oracle before timing")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: the timing rules ask for >= 3 warm-up steps")
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from document_search_engine_b200.corpus import config_corpus, config_queries
+    from document_search_engine_b200.scoring import BM25F
+    from document_search_engine_b200.distributed import ShardedSearcher
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU fallback for the product path")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    c = workload(args)
+    k = c["k"]
+
+    t0 = time.perf_counter()
+    ix = config_corpus(args.config, device="cuda:%d" % local_rank, n_docs=c["n_docs"])
+    qs = config_queries(args.config, c["n_queries"])
+    if rank == 0:
+        log("corpus: %d docs, %d postings, generated in %.1f s" % (ix.n_docs_all, ix.n_postings, time.perf_counter() - t0))
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    ss = ShardedSearcher(ix, rank=rank, world=world, device=local_rank, weighting=BM25F,
+                         tile_docs=args.tile_docs, threads=args.threads, split_postings=args.split)
+    eng = ss.engine
+    batch = ss.pack(qs.queries)
+    if rank == 0:
+        log("upload + pack: %.1f s; engine %s" % (time.perf_counter() - t0, eng.stats()))
+
+    # ---- parity gate on a sample before any number is reported --------------------------------
+    if args.check:
+        from oracle.numpy_oracle import NumpyOracle
+        from tests.parity import assert_query_parity
+        scores, docids, counts, totals = ss.search_packed(batch, k)
+        if rank == 0:
+            o = NumpyOracle(ix)
+            step = max(1, len(qs.queries) // args.check)
+            for i in range(0, len(qs.queries), step):
+                n = int(counts[i])
+                assert_query_parity(o, qs.queries[i], list(zip(scores[i, :n].tolist(), docids[i, :n].tolist())),
+                                    int(totals[i]), k, ctx="bench query %d" % i)
+            log("parity gate: %d sampled queries match the oracle" % len(range(0, len(qs.queries), step)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: plan resident in HBM, CUDA events on the launching stream ----------------------
+    plan = eng.prepare(batch, k)
+    for _ in range(args.warmup):
+        ss.run_plan(plan)
+    barrier()
+    eng.synchronize()
+    eng.reset_stats()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        ss.run_plan(plan)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    eng.synchronize()
+    st = eng.stats()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = c["n_queries"] / (ms_per_step * 1e-3)
+
+    # roofline of the dominant kernel: algorithmic bytes of this rank's shard / its kernel time
+    peak, peak_src = measured_peak()
+    ms_score = st["ms_score"] / max(1, st["n_executes"])
+    achieved = BYTES_PER_POSTING * st["postings_touched"] / (ms_score * 1e-3) / 1e9 if ms_score > 0 else 0.0
+    launches = int(st["n_launches"]) * args.steps + (2 * args.steps if world > 1 else 0)
+
+    # ---- e2e: host buffers through the public entry point ---------------------------------------
+    h2d = batch.nbytes
+    d2h = batch.n_queries * (k * 8 + 4 + 8)
+    for _ in range(min(2, args.warmup)):
+        ss.search_packed(batch, k) if world > 1 else eng.search_batch(batch, k)
+    barrier()
+    eng.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if world > 1:
+            ss.search_packed(batch, k)
+        else:
+            eng.search_batch(batch, k)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = c["n_queries"] * args.steps / float(t.item())
+    plan.close()
+
+    if rank == 0:
+        cfg = config_json(args, c, world)
+        cfg["l2"] = cfg["l2"] % (st["device_bytes"] / 2 ** 30)
+        cfg["engine"] = {"tile_docs": st["tile_docs"], "threads": st["threads"], "ctas_per_sm": st["ctas_per_sm"],
+                         "packed_payload": bool(st["packed_payload"]), "work_items": int(st["n_items"])}
+        out = {"metric": "BM25F top-%d queries/sec" % k, "value": value, "unit": "queries/s", "n_gpus": world,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+               "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h)},
+               "gpu_launches": launches,
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                            "kernel": "k_score_topk", "kernel_ms_per_step": ms_score,
+                            "algorithmic_bytes_per_step": BYTES_PER_POSTING * st["postings_touched"],
+                            "frac_of_nominal_8000": achieved / 8000.0},
+               "kernel_ms": {"bounds": st["ms_bounds"] / max(1, st["n_executes"]), "score": ms_score,
+                             "merge": st["ms_merge"] / max(1, st["n_executes"])},
+               "clocks": clk}
+        if not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline(ix, qs.queries, k)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

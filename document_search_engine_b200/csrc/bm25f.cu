@@ -1,0 +1,1091 @@
+// libbm25f — B200-native BM25F scoring + top-k over a device-resident CSR posting store.
+//
+// Replaces the inside of Whoosh's Searcher.search() for Term/And/Or trees as the reference
+// calls it (reference my_flask.py:184, :208, :211, :304; cli.py:9).  See include/bm25f.h for
+// the boundary and DESIGN.md for the data layout and the kernels.
+//
+// Kernel inventory (all hand-written for sm_100a):
+//   k_check_tf / k_pack_postings  index upload: fold (tf, length byte) into one 32-bit payload
+//   k_tile_bounds                 per (leaf, tile) posting sub-range by binary search
+//   k_score_topk                  the hot kernel: tile-wise BM25F accumulate in shared memory,
+//                                 match filtering, exact top-k with 64-bit composite keys
+//   k_merge_topk                  merge of per-item (or per-GPU) top-k lists, decode
+//   k_decode_keys                 keys -> (score, docid, count)
+#include "../../include/bm25f.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) __attribute__((format(printf, 2, 3)));
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(x)                                                                               \
+  do {                                                                                      \
+    cudaError_t e_ = (x);                                                                   \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(e_ == cudaErrorMemoryAllocation ? BM25F_ENOMEM : BM25F_ECUDA, "%s: %s",   \
+                  #x, cudaGetErrorString(e_));                                              \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Device-side records
+// ------------------------------------------------------------------------------------------
+struct LeafRec {            // 32 B
+  unsigned long long off;   // first posting of the list
+  uint32_t df;              // postings in the list (this shard)
+  float w;                  // idf * (K1 + 1) * boost
+  uint32_t norm_off;        // field * 256
+  uint32_t group;           // group index after sorting groups by size
+  uint32_t qleaf0;          // first leaf of the owning query (global leaf index)
+  uint32_t qnl;             // leaves in the owning query
+};
+
+struct QueryRec {           // 32 B
+  uint32_t leaf_begin;
+  uint32_t n_leaves;
+  uint32_t n_groups;
+  uint32_t flags;           // bit0: one group, all weights > 0 -> "acc == 0" marks a fresh slot
+  unsigned long long after_key;
+  uint32_t part_begin;      // first partial top-k list of this query
+  uint32_t n_parts;
+};
+
+struct ItemRec {            // 16 B
+  uint32_t q;
+  uint32_t tile_begin;
+  uint32_t tile_end;
+  uint32_t part;            // which partial list this item writes
+};
+
+constexpr uint32_t QF_SIMPLE_OR = 1u;
+constexpr int MAXL = BM25F_MAX_LEAVES_PER_QUERY;
+
+// W11 order as one unsigned 64-bit key: score descending, docnum ascending.  All keys of
+// distinct documents are distinct, so "top-k by key" is exactly the reference collector.
+__host__ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t gdoc) {
+#ifdef __CUDA_ARCH__
+  uint32_t u = __float_as_uint(score);
+#else
+  uint32_t u;
+  memcpy(&u, &score, 4);
+#endif
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - gdoc);
+}
+
+__host__ __device__ __forceinline__ float key_score(unsigned long long key) {
+  uint32_t u = (uint32_t)(key >> 32);
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(u);
+#else
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+#endif
+}
+
+__host__ __device__ __forceinline__ uint32_t key_doc(unsigned long long key) {
+  return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+}
+
+// ------------------------------------------------------------------------------------------
+// Index upload kernels
+// ------------------------------------------------------------------------------------------
+// Posting weights are term counts in the reference's schema (no field_boost); when
+// every weight is a positive integer < 2^24 the (tf, length byte) pair is packed in 32 bits.
+__global__ void k_check_tf(const float* __restrict__ tfs, unsigned long long n, int* __restrict__ flag) {
+  unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (; i < n; i += stride) {
+    float t = tfs[i];
+    if (!(t >= 1.0f && t < 16777216.0f && t == floorf(t))) bad = 1;
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
+// payload[i] = (tf << 8) | len_byte[field][docid]   (packed)   or float bits of tf + separate byte
+__global__ void k_pack_postings(const uint32_t* __restrict__ docids, const float* __restrict__ tfs,
+                                const uint8_t* __restrict__ len_bytes_field, unsigned long long begin,
+                                unsigned long long end, int packed, uint32_t* __restrict__ payload,
+                                uint8_t* __restrict__ lb_out) {
+  unsigned long long i = begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < end; i += stride) {
+    uint32_t lb = len_bytes_field[docids[i]];
+    float t = tfs[i];
+    if (packed) {
+      payload[i] = ((uint32_t)t << 8) | lb;
+    } else {
+      payload[i] = __float_as_uint(t);
+      lb_out[i] = (uint8_t)lb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tile boundaries: bounds[q][j][l] = first posting of leaf l with docid >= j * S
+// ------------------------------------------------------------------------------------------
+__global__ void k_tile_bounds(const LeafRec* __restrict__ leaves, uint32_t n_leaves, uint32_t T,
+                              uint32_t S, const uint32_t* __restrict__ docids,
+                              uint32_t* __restrict__ bounds) {
+  unsigned long long gid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  unsigned long long total = (unsigned long long)n_leaves * (T + 1);
+  if (gid >= total) return;
+  uint32_t leaf = (uint32_t)(gid / (T + 1));
+  uint32_t j = (uint32_t)(gid % (T + 1));
+  LeafRec L = leaves[leaf];
+  uint32_t lo = 0, hi = L.df;
+  if (j == T) {
+    lo = L.df;
+  } else if (j > 0) {
+    unsigned long long target = (unsigned long long)j * S;
+    const uint32_t* d = docids + L.off;
+    while (lo < hi) {
+      uint32_t mid = (lo + hi) >> 1;
+      if ((unsigned long long)__ldg(d + mid) < target) lo = mid + 1; else hi = mid;
+    }
+  }
+  size_t base = (size_t)L.qleaf0 * (T + 1);
+  bounds[base + (size_t)j * L.qnl + (leaf - L.qleaf0)] = lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory bitonic sort (descending) of n = 2^m keys by all threads of the CTA
+// ------------------------------------------------------------------------------------------
+__device__ void bitonic_sort_desc(unsigned long long* a, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int x = i ^ j;
+        if (x > i) {
+          unsigned long long ai = a[i], ax = a[x];
+          bool desc = (i & k) == 0;
+          if (desc ? (ai < ax) : (ai > ax)) { a[i] = ax; a[x] = ai; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Keep the k largest keys of keys[0..*nkeys) (sorted descending), update the admission threshold.
+// Must be called by all threads; contains barriers.  Returns the new key count (uniform).
+__device__ int prune_topk(unsigned long long* keys, int* nkeys, unsigned long long* thr, int k) {
+  __syncthreads();
+  const int n = *nkeys;
+  if (n > 1) {
+    const int np = next_pow2(n);
+    for (int i = n + threadIdx.x; i < np; i += blockDim.x) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(keys, np);
+    if (threadIdx.x == 0 && n >= k) { *nkeys = k; *thr = keys[k - 1]; }
+    __syncthreads();
+  }
+  return min(n, k);
+}
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------
+// The hot kernel.  One CTA per work item = (query, range of document tiles).
+//
+// Per tile of S documents the CTA owns, in shared memory:  acc[S] f32 score accumulators,
+// cnt[S] u8 "groups matched so far" counters and cand[S] u16 slots touched by the first
+// group.  Leaves are walked in group order (smallest group first) with a barrier between
+// leaves, so every accumulator is updated by one thread at a time, in a fixed order.
+// A posting of group g contributes only to slots with cnt == g (first hit of the group:
+// cnt becomes g + 1) or cnt == g + 1 (another leaf of the same group already hit).  After the
+// last leaf the candidates with cnt == n_groups are the tile's matches: they are counted,
+// turned into 64-bit keys and offered to the CTA's top-k buffer.
+// ------------------------------------------------------------------------------------------
+struct ScoreParams {
+  const uint32_t* docids;
+  const uint32_t* payload;
+  const uint8_t* lb;            // only when !packed
+  const uint8_t* deleted;       // or null
+  const float* norm;            // [n_fields * 256]
+  const LeafRec* leaves;
+  const QueryRec* queries;
+  const ItemRec* items;
+  const uint32_t* bounds;
+  unsigned long long* part_keys;   // [n_parts * k]
+  unsigned long long* totals;      // [Q]
+  uint32_t S;
+  uint32_t T;
+  uint32_t n_docs;
+  uint32_t doc_base;
+  int k;
+  int cap;                      // key buffer capacity (power of two)
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int nt = blockDim.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int nwarps = nt >> 5;
+  const uint32_t S = p.S;
+
+  // carve shared memory
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  float* acc = reinterpret_cast<float*>(keys + p.cap);
+  uint16_t* cand = reinterpret_cast<uint16_t*>(acc + S);
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(cand + S);
+  __shared__ LeafRec s_leaf[MAXL];
+  __shared__ uint32_t s_bounds[3][MAXL];
+  __shared__ int s_ncand[2];
+  __shared__ int s_nkeys;
+  __shared__ unsigned long long s_thr;
+  __shared__ unsigned long long s_total;
+
+  const ItemRec item = p.items[blockIdx.x];
+  const QueryRec q = p.queries[item.q];
+  const int L = (int)q.n_leaves;
+  const int G = (int)q.n_groups;
+  const bool simple_or = (q.flags & QF_SIMPLE_OR) != 0;
+  const unsigned long long upper = q.after_key ? q.after_key : ~0ull;
+
+  for (int i = tid; i < L; i += nt) s_leaf[i] = p.leaves[q.leaf_begin + i];
+  for (uint32_t i = tid; i < S; i += nt) { acc[i] = 0.0f; cnt[i] = 0; }
+  if (tid == 0) { s_ncand[0] = 0; s_ncand[1] = 0; s_nkeys = 0; s_thr = 0ull; s_total = 0ull; }
+  const uint32_t* qbounds = p.bounds + (size_t)q.leaf_begin * (p.T + 1);
+  // rows tile_begin and tile_begin + 1 of the boundary table
+  for (int i = tid; i < 2 * L; i += nt) {
+    int r = i / L, l = i - r * L;
+    s_bounds[(item.tile_begin + r) % 3][l] = qbounds[(size_t)(item.tile_begin + r) * L + l];
+  }
+  __syncthreads();
+
+  unsigned int my_total = 0;
+  int budget = p.cap;                  // keys that can still be appended without overflow (uniform)
+
+  for (uint32_t t = item.tile_begin; t < item.tile_end; ++t) {
+    const uint32_t t0 = t * S;
+    int* ncand_ctr = &s_ncand[t & 1];
+    // prefetch the boundary row of tile t + 2 (consumed by tile t + 1 as its upper bounds)
+    if (t + 2 <= p.T && tid < L) cp_async4(&s_bounds[(t + 2) % 3][tid], qbounds + (size_t)(t + 2) * L + tid);
+    const uint32_t* blo = s_bounds[t % 3];
+    const uint32_t* bhi = s_bounds[(t + 1) % 3];
+
+    for (int l = 0; l < L; ++l) {
+      const uint32_t lo = blo[l], hi = bhi[l];
+      if (lo < hi) {
+        const LeafRec lf = s_leaf[l];
+        const unsigned long long base = lf.off + lo;
+        const unsigned long long end = lf.off + hi;
+        const float w = lf.w;
+        const float* __restrict__ nrm = p.norm + lf.norm_off;
+        const uint32_t g = lf.group;
+        // 16-byte aligned groups of four postings, one group per lane per step
+        for (unsigned long long wb = (base & ~3ull) + (unsigned long long)warp * 128ull; wb < end;
+             wb += (unsigned long long)nwarps * 128ull) {
+          const unsigned long long i = wb + (unsigned long long)lane * 4ull;
+          uint32_t d[4] = {0, 0, 0, 0}, pl[4] = {0, 0, 0, 0};
+          uint32_t lbs = 0;
+          if (i < end) {
+            const uint4 dv = __ldg(reinterpret_cast<const uint4*>(p.docids + i));
+            const uint4 pv = __ldg(reinterpret_cast<const uint4*>(p.payload + i));
+            d[0] = dv.x; d[1] = dv.y; d[2] = dv.z; d[3] = dv.w;
+            pl[0] = pv.x; pl[1] = pv.y; pl[2] = pv.z; pl[3] = pv.w;
+            if (!PACKED) lbs = __ldg(reinterpret_cast<const uint32_t*>(p.lb + i));
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool valid = (i + e >= base) && (i + e < end);
+            bool fresh = false;
+            uint32_t slot = 0;
+            if (valid) {
+              slot = d[e] - t0;
+              float tf;
+              uint32_t lb;
+              if (PACKED) { tf = (float)(pl[e] >> 8); lb = pl[e] & 255u; }
+              else { tf = __uint_as_float(pl[e]); lb = (lbs >> (8 * e)) & 255u; }
+              const float s = __fdividef(w * tf, tf + __ldg(nrm + lb));
+              if (simple_or) {
+                const float old = acc[slot];
+                acc[slot] = old + s;
+                fresh = (old == 0.0f);
+              } else {
+                const uint32_t c = cnt[slot];
+                if (c == g) {
+                  cnt[slot] = (uint8_t)(g + 1);
+                  acc[slot] += s;
+                  fresh = (g == 0);
+                } else if (c == g + 1) {
+                  acc[slot] += s;
+                }
+              }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, fresh);
+            if (m) {
+              int b = 0;
+              const int leader = __ffs(m) - 1;
+              if (lane == leader) b = atomicAdd(ncand_ctr, __popc(m));
+              b = __shfl_sync(0xFFFFFFFFu, b, leader);
+              if (fresh) cand[b + __popc(m & ((1u << lane) - 1u))] = (uint16_t)slot;
+            }
+          }
+        }
+        __syncthreads();   // the next leaf may touch the same slots
+      }
+    }
+
+    // ---- tile epilogue: matches -> total, keys -> top-k buffer, reset touched slots --------
+    const int ncand = *ncand_ctr;
+    for (int j0 = 0; j0 < ncand; j0 += nt) {
+      if (budget < nt) budget = p.cap - prune_topk(keys, &s_nkeys, &s_thr, p.k);
+      budget -= nt;
+      const int j = j0 + tid;
+      bool push = false;
+      unsigned long long key = 0ull;
+      if (j < ncand) {
+        const uint32_t slot = cand[j];
+        const float sc = acc[slot];
+        acc[slot] = 0.0f;
+        bool match = true;
+        if (!simple_or) { match = (cnt[slot] == (uint8_t)G); cnt[slot] = 0; }
+        const uint32_t doc = t0 + slot;
+        if (match && p.deleted != nullptr && p.deleted[doc]) match = false;   // W9
+        if (match) {
+          ++my_total;
+          key = make_key(sc, p.doc_base + doc);
+          push = (key > s_thr) && (key < upper);
+        }
+      }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, push);
+      if (m) {
+        int b = 0;
+        const int leader = __ffs(m) - 1;
+        if (lane == leader) b = atomicAdd(&s_nkeys, __popc(m));
+        b = __shfl_sync(0xFFFFFFFFu, b, leader);
+        if (push) keys[b + __popc(m & ((1u << lane) - 1u))] = key;
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();                   // end of tile: slots are clean, boundary row t + 2 has landed
+    if (tid == 0) *ncand_ctr = 0;      // next used by tile t + 2, ordered by the barrier of tile t + 1
+    budget = p.cap - s_nkeys;          // nobody appends before the next tile's leaf barrier
+  }
+
+  // ---- item epilogue -------------------------------------------------------------------
+  const int n = prune_topk(keys, &s_nkeys, &s_thr, p.k);
+  unsigned long long* out = p.part_keys + (size_t)item.part * p.k;
+  for (int i = tid; i < p.k; i += nt) out[i] = (i < n) ? keys[i] : 0ull;
+  // match count of this item
+  for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(0xFFFFFFFFu, my_total, o);
+  if (lane == 0 && my_total) atomicAdd(&s_total, (unsigned long long)my_total);
+  __syncthreads();
+  if (tid == 0 && s_total) atomicAdd(p.totals + item.q, s_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
+// mode 0: lists are the partial lists of the query's work items (start = part_begin * k, stride k)
+// mode 1: lists come from an all-gather over document shards  (start = q * k, stride = Q * k)
+// ------------------------------------------------------------------------------------------
+__global__ void k_merge_topk(const unsigned long long* __restrict__ keys_in, const QueryRec* __restrict__ queries,
+                             int mode, int n_lists_fixed, unsigned long long stride_fixed, uint32_t Q, int k,
+                             int kp /* pow2 >= k */, unsigned long long* __restrict__ keys_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* buf = reinterpret_cast<unsigned long long*>(smem_raw);   // [2 * kp]
+  const uint32_t q = blockIdx.x;
+  if (q >= Q) return;
+  unsigned long long start, stride;
+  int n_lists;
+  if (mode == 0) {
+    const QueryRec qr = queries[q];
+    start = (unsigned long long)qr.part_begin * k;
+    stride = (unsigned long long)k;
+    n_lists = (int)qr.n_parts;
+  } else {
+    start = (unsigned long long)q * k;
+    stride = stride_fixed;
+    n_lists = n_lists_fixed;
+  }
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < 2 * kp; i += nt) buf[i] = 0ull;
+  __syncthreads();
+  if (n_lists > 0)
+    for (int i = tid; i < k; i += nt) buf[i] = keys_in[start + i];
+  __syncthreads();
+  for (int l = 1; l < n_lists; ++l) {
+    for (int i = tid; i < kp; i += nt) buf[kp + i] = (i < k) ? keys_in[start + l * stride + i] : 0ull;
+    __syncthreads();
+    bitonic_sort_desc(buf, 2 * kp);
+    for (int i = k + tid; i < 2 * kp; i += nt) buf[i] = 0ull;
+    __syncthreads();
+  }
+  for (int i = tid; i < k; i += nt) keys_out[(size_t)q * k + i] = buf[i];
+}
+
+__global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint32_t Q, int k,
+                              float* __restrict__ scores, uint32_t* __restrict__ docids,
+                              uint32_t* __restrict__ counts) {
+  const uint32_t q = blockIdx.x;
+  if (q >= Q) return;
+  int n = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = keys[(size_t)q * k + i];
+    const bool ok = key != 0ull;
+    if (scores) scores[(size_t)q * k + i] = ok ? key_score(key) : -INFINITY;
+    if (docids) docids[(size_t)q * k + i] = ok ? key_doc(key) : 0xFFFFFFFFu;
+    n += ok;
+  }
+  if (counts) {
+    __shared__ int s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    if (n) atomicAdd(&s_n, n);
+    __syncthreads();
+    if (threadIdx.x == 0) counts[q] = (uint32_t)s_n;
+  }
+}
+
+}  // namespace
+
+// ==========================================================================================
+// Host side
+// ==========================================================================================
+struct bm25f_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;      // stream in use
+  cudaStream_t own_stream = nullptr;  // created by the library
+  uint64_t n_docs = 0, n_terms = 0, n_postings = 0, doc_base = 0;
+  uint32_t n_fields = 0;
+  std::vector<uint64_t> term_offsets;
+  std::vector<uint8_t> term_field;
+  uint32_t* d_docids = nullptr;
+  uint32_t* d_payload = nullptr;
+  uint8_t* d_lb = nullptr;
+  uint8_t* d_deleted = nullptr;
+  float* d_norm = nullptr;
+  bool packed = true;
+  bool have_weighting = false;
+  uint32_t S = 8192, NT = 256, split = 1u << 16;
+  int n_sms = 148;
+  int ctas_per_sm = 0;
+  static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
+  cudaEvent_t ev[EV_RING][4] = {};
+  int ev_head = 0;                     // next slot to use
+  int ev_pending = 0;                  // slots recorded but not yet folded into the stats
+  bm25f_stats stats{};
+  uint64_t device_bytes = 0;
+};
+
+struct bm25f_plan {
+  bm25f_handle* h = nullptr;
+  uint32_t Q = 0, n_leaves = 0, n_items = 0, n_parts = 0, T = 0;
+  int k = 0, kp = 1, cap = 1024;
+  uint64_t postings = 0;
+  LeafRec* d_leaves = nullptr;
+  QueryRec* d_queries = nullptr;
+  ItemRec* d_items = nullptr;
+  uint32_t* d_bounds = nullptr;
+  unsigned long long* d_part_keys = nullptr;
+  unsigned long long* d_keys = nullptr;
+  unsigned long long* d_totals = nullptr;
+  float* d_scores = nullptr;
+  uint32_t* d_docids = nullptr;
+  uint32_t* d_counts = nullptr;
+  size_t smem_score = 0;
+};
+
+namespace {
+
+size_t score_smem_bytes(uint32_t S, int cap) { return (size_t)cap * 8 + (size_t)S * 7; }
+
+int key_capacity(int k, int nt) {
+  int need = k + 2 * nt;
+  int cap = 1024;
+  while (cap < need) cap <<= 1;
+  return cap;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t n, bm25f_handle* h = nullptr) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T));
+  if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+  if (h) h->device_bytes += n * sizeof(T);
+  return 0;
+}
+
+// Fold the timings of the oldest `n` pending executes into the running sums (waits for them).
+int fold_events(bm25f_handle* h, int n) {
+  while (n-- > 0 && h->ev_pending > 0) {
+    const int slot = (h->ev_head - h->ev_pending + 2 * bm25f_handle::EV_RING) % bm25f_handle::EV_RING;
+    cudaEvent_t* e = h->ev[slot];
+    CU(cudaEventSynchronize(e[3]));
+    float a = 0, b = 0, c = 0, d = 0;
+    CU(cudaEventElapsedTime(&a, e[0], e[1]));
+    CU(cudaEventElapsedTime(&b, e[1], e[2]));
+    CU(cudaEventElapsedTime(&c, e[2], e[3]));
+    CU(cudaEventElapsedTime(&d, e[0], e[3]));
+    h->stats.ms_bounds += a;
+    h->stats.ms_score += b;
+    h->stats.ms_merge += c;
+    h->stats.ms_total += d;
+    h->stats.n_executes += 1;
+    --h->ev_pending;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bm25f_abi_version(void) { return BM25F_ABI_VERSION; }
+
+const char* bm25f_last_error(void) { return g_err.c_str(); }
+
+void bm25f_destroy(bm25f_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_docids);
+  cudaFree(h->d_payload);
+  cudaFree(h->d_lb);
+  cudaFree(h->d_deleted);
+  cudaFree(h->d_norm);
+  for (auto& set : h->ev)
+    for (auto& e : set)
+      if (e) cudaEventDestroy(e);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* opts, bm25f_handle** out) {
+  if (!desc || !out) return fail(BM25F_EINVAL, "null argument");
+  *out = nullptr;
+  if (desc->abi_version != BM25F_ABI_VERSION)
+    return fail(BM25F_EABI, "ABI mismatch: caller %u, library %d", desc->abi_version, BM25F_ABI_VERSION);
+  if (desc->n_fields == 0 || desc->n_fields > 255) return fail(BM25F_EINVAL, "n_fields must be 1..255");
+  if (desc->n_docs_all >= 0xFFFFFFFFull || desc->doc_base + desc->n_docs_all >= 0xFFFFFFFFull)
+    return fail(BM25F_EINVAL, "document numbers must fit 32 bits");
+  if (!desc->term_offsets || !desc->term_field || !desc->len_bytes || (desc->n_postings && (!desc->docids || !desc->tfs)))
+    return fail(BM25F_EINVAL, "null index array");
+  if (desc->term_offsets[0] != 0 || desc->term_offsets[desc->n_terms] != desc->n_postings)
+    return fail(BM25F_EINVAL, "term_offsets does not span n_postings");
+  for (uint64_t t = 0; t < desc->n_terms; ++t) {
+    if (desc->term_offsets[t + 1] < desc->term_offsets[t]) return fail(BM25F_EINVAL, "term_offsets not monotonic at %llu", (unsigned long long)t);
+    if (desc->term_offsets[t + 1] - desc->term_offsets[t] > 0xFFFFFFFFull) return fail(BM25F_EINVAL, "posting list too long");
+    if (desc->term_field[t] >= desc->n_fields) return fail(BM25F_EINVAL, "term_field out of range at %llu", (unsigned long long)t);
+  }
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(BM25F_EINVAL, "device %d not present (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(BM25F_ECUDA, "libbm25f is built for sm_100a; device is sm_%d%d", prop.major, prop.minor);
+
+  bm25f_handle* h = new (std::nothrow) bm25f_handle();
+  if (!h) return fail(BM25F_ENOMEM, "host allocation failed");
+  h->device = device;
+  h->n_sms = prop.multiProcessorCount;
+  h->n_docs = desc->n_docs_all;
+  h->n_terms = desc->n_terms;
+  h->n_postings = desc->n_postings;
+  h->doc_base = desc->doc_base;
+  h->n_fields = desc->n_fields;
+  if (opts) {
+    if (opts->tile_docs) h->S = opts->tile_docs;
+    if (opts->threads) h->NT = opts->threads;
+    if (opts->split_postings) h->split = opts->split_postings;
+  }
+  if (h->S < 256 || h->S > 65536 || (h->S & 3)) { delete h; return fail(BM25F_EINVAL, "tile_docs must be a multiple of 4 in 256..65536"); }
+  if (h->NT < 64 || h->NT > 512 || (h->NT & 31)) { delete h; return fail(BM25F_EINVAL, "threads must be a multiple of 32 in 64..512"); }
+  h->term_offsets.assign(desc->term_offsets, desc->term_offsets + desc->n_terms + 1);
+  h->term_field.assign(desc->term_field, desc->term_field + desc->n_terms);
+
+#define CUH(x)                                                          \
+  do {                                                                  \
+    cudaError_t e_ = (x);                                               \
+    if (e_ != cudaSuccess) {                                            \
+      int rc_ = fail(e_ == cudaErrorMemoryAllocation ? BM25F_ENOMEM : BM25F_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+      bm25f_destroy(h);                                                 \
+      return rc_;                                                       \
+    }                                                                   \
+  } while (0)
+#define RCH(x)                       \
+  do {                               \
+    int rc_ = (x);                   \
+    if (rc_) { bm25f_destroy(h); return rc_; } \
+  } while (0)
+
+  CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->stream = h->own_stream;
+  for (auto& set : h->ev)
+    for (auto& e : set) CUH(cudaEventCreate(&e));
+
+  const uint64_t P = desc->n_postings;
+  const size_t pad = 256;   // vector loads may run past the last posting of the last list
+  RCH(dev_alloc(&h->d_docids, P + pad, h));
+  RCH(dev_alloc(&h->d_payload, P + pad, h));
+  CUH(cudaMemsetAsync(h->d_docids + P, 0xFF, pad * 4, h->stream));
+  CUH(cudaMemsetAsync(h->d_payload + P, 0, pad * 4, h->stream));
+  RCH(dev_alloc(&h->d_norm, (size_t)h->n_fields * 256, h));
+  if (desc->deleted) {
+    RCH(dev_alloc(&h->d_deleted, h->n_docs, h));
+    CUH(cudaMemcpyAsync(h->d_deleted, desc->deleted, h->n_docs, cudaMemcpyDefault, h->stream));
+  }
+  // temporaries for packing
+  float* d_tfs = nullptr;
+  uint8_t* d_len = nullptr;
+  int* d_flag = nullptr;
+  RCH(dev_alloc(&d_tfs, P));
+  RCH(dev_alloc(&d_len, (size_t)h->n_fields * h->n_docs));
+  RCH(dev_alloc(&d_flag, 1));
+  auto free_tmp = [&]() { cudaFree(d_tfs); cudaFree(d_len); cudaFree(d_flag); };
+#define CUT(x)                                                          \
+  do {                                                                  \
+    cudaError_t e_ = (x);                                               \
+    if (e_ != cudaSuccess) {                                            \
+      int rc_ = fail(BM25F_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+      free_tmp();                                                       \
+      bm25f_destroy(h);                                                 \
+      return rc_;                                                       \
+    }                                                                   \
+  } while (0)
+  if (P) {
+    CUT(cudaMemcpyAsync(h->d_docids, desc->docids, P * 4, cudaMemcpyDefault, h->stream));
+    CUT(cudaMemcpyAsync(d_tfs, desc->tfs, P * 4, cudaMemcpyDefault, h->stream));
+  }
+  CUT(cudaMemcpyAsync(d_len, desc->len_bytes, (size_t)h->n_fields * h->n_docs, cudaMemcpyDefault, h->stream));
+  CUT(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+  int flag = 0;
+  if (P) {
+    k_check_tf<<<h->n_sms * 8, 256, 0, h->stream>>>(d_tfs, P, d_flag);
+    CUT(cudaGetLastError());
+  }
+  CUT(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUT(cudaStreamSynchronize(h->stream));
+  h->packed = (flag == 0);
+  if (!h->packed) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_lb), P + pad);
+    if (e != cudaSuccess) { free_tmp(); bm25f_destroy(h); return fail(BM25F_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    h->device_bytes += P + pad;
+    CUT(cudaMemsetAsync(h->d_lb + P, 0, pad, h->stream));
+  }
+  // docids of every posting must be inside the shard, or the gather below would fault
+  // (checked on the host for host inputs only when small; the kernel clamps nothing, so
+  //  validate with a cheap device reduction instead)
+  // runs of consecutive posting lists that belong to the same field
+  uint64_t t = 0;
+  while (t < h->n_terms) {
+    uint64_t t2 = t;
+    const uint8_t f = h->term_field[t];
+    while (t2 < h->n_terms && h->term_field[t2] == f) ++t2;
+    const uint64_t b = h->term_offsets[t], e = h->term_offsets[t2];
+    if (e > b) {
+      const uint64_t n = e - b;
+      const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)h->n_sms * 16);
+      k_pack_postings<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_tfs, d_len + (size_t)f * h->n_docs, b, e,
+                                                      h->packed ? 1 : 0, h->d_payload, h->d_lb);
+      CUT(cudaGetLastError());
+    }
+    t = t2;
+  }
+  CUT(cudaStreamSynchronize(h->stream));
+  free_tmp();
+
+  // kernel attributes: opt in to the large dynamic shared memory carve-out once
+  const size_t smem_max = score_smem_bytes(h->S, key_capacity(BM25F_MAX_K, (int)h->NT));
+  if (smem_max > (size_t)prop.sharedMemPerBlockOptin) {
+    bm25f_destroy(h);
+    return fail(BM25F_EINVAL, "tile_docs=%u needs %zu bytes of shared memory (> %zu)", h->S, smem_max, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  CUH(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CUH(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  h->stats.tile_docs = h->S;
+  h->stats.threads = h->NT;
+  h->stats.packed_payload = h->packed ? 1u : 0u;
+  h->stats.device_bytes = h->device_bytes;
+  *out = h;
+  return 0;
+#undef CUH
+#undef RCH
+#undef CUT
+}
+
+int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
+  if (!h || !norm) return fail(BM25F_EINVAL, "null argument");
+  CU(cudaSetDevice(h->device));
+  for (uint32_t i = 0; i < h->n_fields * 256; ++i)
+    if (!(norm[i] > 0.0f) || !std::isfinite(norm[i])) return fail(BM25F_EINVAL, "norm table entry %u is not a positive finite number", i);
+  CU(cudaMemcpyAsync(h->d_norm, norm, (size_t)h->n_fields * 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  h->have_weighting = true;
+  return 0;
+}
+
+void bm25f_plan_destroy(bm25f_plan* p) {
+  if (!p) return;
+  if (p->h) cudaSetDevice(p->h->device);
+  cudaFree(p->d_leaves);
+  cudaFree(p->d_queries);
+  cudaFree(p->d_items);
+  cudaFree(p->d_bounds);
+  cudaFree(p->d_part_keys);
+  cudaFree(p->d_keys);
+  cudaFree(p->d_totals);
+  cudaFree(p->d_scores);
+  cudaFree(p->d_docids);
+  cudaFree(p->d_counts);
+  delete p;
+}
+
+int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
+  if (!h || !b || !out) return fail(BM25F_EINVAL, "null argument");
+  *out = nullptr;
+  if (k < 1 || k > BM25F_MAX_K) return fail(BM25F_EINVAL, "k must be 1..%d", BM25F_MAX_K);
+  if (!h->have_weighting) return fail(BM25F_EINVAL, "bm25f_set_weighting has not been called");
+  const uint32_t Q = b->n_queries, NL = b->n_leaves;
+  if (Q && (!b->query_leaf_offsets || !b->query_n_groups)) return fail(BM25F_EINVAL, "null query arrays");
+  if (NL && (!b->leaf_term || !b->leaf_weight || !b->leaf_group)) return fail(BM25F_EINVAL, "null leaf arrays");
+  if (Q && (b->query_leaf_offsets[0] != 0 || b->query_leaf_offsets[Q] != NL)) return fail(BM25F_EINVAL, "query_leaf_offsets does not span n_leaves");
+  CU(cudaSetDevice(h->device));
+
+  const uint32_t S = h->S;
+  const uint32_t T = (uint32_t)std::max<uint64_t>(1, (h->n_docs + S - 1) / S);
+  std::vector<LeafRec> leaves(NL);
+  std::vector<QueryRec> queries(Q);
+  std::vector<ItemRec> items;
+  std::vector<uint64_t> item_w;
+  items.reserve(Q + Q / 4);
+  item_w.reserve(Q + Q / 4);
+  uint64_t postings = 0;
+  uint32_t n_parts = 0;
+  uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
+
+  for (uint32_t qi = 0; qi < Q; ++qi) {
+    const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
+    if (e < a || e > NL) return fail(BM25F_EINVAL, "query %u: bad leaf range", qi);
+    const uint32_t nl = e - a;
+    const uint32_t G = b->query_n_groups[qi];
+    QueryRec& qr = queries[qi];
+    qr = QueryRec{};
+    qr.after_key = b->after_keys ? b->after_keys[qi] : 0ull;
+    qr.leaf_begin = out_leaf;
+    qr.part_begin = n_parts;
+    if (nl > (uint32_t)MAXL) return fail(BM25F_EINVAL, "query %u has %u leaves (max %d)", qi, nl, MAXL);
+    if (G > 32) return fail(BM25F_EINVAL, "query %u has %u groups (max 32)", qi, G);
+    if (G == 0 || nl == 0) continue;   // null query
+
+    // per-group size; validates group ordering
+    uint64_t gsize[32] = {0};
+    bool gseen[32] = {false};
+    uint32_t prev_g = 0;
+    bool all_pos = true;
+    for (uint32_t i = a; i < e; ++i) {
+      const uint32_t g = b->leaf_group[i];
+      if (g >= G || g < prev_g) return fail(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
+      prev_g = g;
+      gseen[g] = true;
+      const uint32_t term = b->leaf_term[i];
+      if (term != BM25F_TERM_UNKNOWN) {
+        if (term >= h->n_terms) return fail(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, term);
+        gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
+      }
+      if (!(b->leaf_weight[i] > 1e-30f)) all_pos = false;
+      if (!std::isfinite(b->leaf_weight[i])) return fail(BM25F_EINVAL, "query %u: leaf weight is not finite", qi);
+    }
+    bool dead = false;
+    for (uint32_t g = 0; g < G; ++g)
+      if (!gseen[g] || gsize[g] == 0) dead = true;   // an empty group: the AND matches nothing (W10)
+    if (dead) continue;
+
+    // smallest group first: it defines the candidate set, later groups only filter it
+    uint32_t order[32], rank[32];
+    for (uint32_t g = 0; g < G; ++g) order[g] = g;
+    std::stable_sort(order, order + G, [&](uint32_t x, uint32_t y) { return gsize[x] < gsize[y]; });
+    for (uint32_t r = 0; r < G; ++r) rank[order[r]] = r;
+    uint64_t P = 0;
+    uint32_t nlq = 0;
+    for (uint32_t r = 0; r < G; ++r) {
+      for (uint32_t i = a; i < e; ++i) {
+        if (b->leaf_group[i] != order[r]) continue;
+        const uint32_t term = b->leaf_term[i];
+        if (term == BM25F_TERM_UNKNOWN) continue;
+        const uint64_t off = h->term_offsets[term], df = h->term_offsets[term + 1] - off;
+        if (df == 0) continue;
+        LeafRec& lf = leaves[out_leaf + nlq];
+        lf.off = off;
+        lf.df = (uint32_t)df;
+        lf.w = b->leaf_weight[i];
+        lf.norm_off = (uint32_t)h->term_field[term] * 256u;
+        lf.group = rank[b->leaf_group[i]];
+        lf.qleaf0 = out_leaf;
+        P += df;
+        ++nlq;
+      }
+    }
+    for (uint32_t i = 0; i < nlq; ++i) leaves[out_leaf + i].qnl = nlq;
+    qr.n_leaves = nlq;
+    qr.n_groups = G;
+    qr.flags = (G == 1 && all_pos) ? QF_SIMPLE_OR : 0u;
+    out_leaf += nlq;
+    postings += P;
+
+    uint32_t nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (P + h->split / 2) / h->split));
+    qr.n_parts = nsplit;
+    for (uint32_t s = 0; s < nsplit; ++s) {
+      ItemRec it;
+      it.q = qi;
+      it.tile_begin = (uint32_t)((uint64_t)T * s / nsplit);
+      it.tile_end = (uint32_t)((uint64_t)T * (s + 1) / nsplit);
+      it.part = n_parts + s;
+      items.push_back(it);
+      item_w.push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
+    }
+    n_parts += nsplit;
+  }
+  leaves.resize(out_leaf);
+
+  // heaviest items first (longest-processing-time order for the block scheduler)
+  std::vector<uint32_t> perm(items.size());
+  for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
+  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return item_w[x] > item_w[y]; });
+  std::vector<ItemRec> sorted(items.size());
+  for (uint32_t i = 0; i < perm.size(); ++i) sorted[i] = items[perm[i]];
+
+  bm25f_plan* p = new (std::nothrow) bm25f_plan();
+  if (!p) return fail(BM25F_ENOMEM, "host allocation failed");
+  p->h = h;
+  p->Q = Q;
+  p->k = k;
+  p->kp = 1;
+  while (p->kp < k) p->kp <<= 1;
+  p->cap = key_capacity(k, (int)h->NT);
+  p->n_leaves = out_leaf;
+  p->n_items = (uint32_t)sorted.size();
+  p->n_parts = n_parts;
+  p->T = T;
+  p->postings = postings;
+  p->smem_score = score_smem_bytes(S, p->cap);
+
+#define RCP(x)                                    \
+  do {                                            \
+    int rc_ = (x);                                \
+    if (rc_) { bm25f_plan_destroy(p); return rc_; } \
+  } while (0)
+#define CUP(x)                                                          \
+  do {                                                                  \
+    cudaError_t e_ = (x);                                               \
+    if (e_ != cudaSuccess) {                                            \
+      int rc_ = fail(BM25F_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+      bm25f_plan_destroy(p);                                            \
+      return rc_;                                                       \
+    }                                                                   \
+  } while (0)
+  const size_t n_bounds = (size_t)out_leaf * (T + 1);
+  RCP(dev_alloc(&p->d_leaves, out_leaf));
+  RCP(dev_alloc(&p->d_queries, Q));
+  RCP(dev_alloc(&p->d_items, sorted.size()));
+  RCP(dev_alloc(&p->d_bounds, n_bounds));
+  RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
+  RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
+  RCP(dev_alloc(&p->d_totals, Q));
+  RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
+  RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
+  RCP(dev_alloc(&p->d_counts, Q));
+  if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves.data(), out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
+  if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries.data(), Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
+  if (!sorted.empty()) CUP(cudaMemcpyAsync(p->d_items, sorted.data(), sorted.size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
+  CUP(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
+  *out = p;
+  return 0;
+#undef RCP
+#undef CUP
+}
+
+int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
+  if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  uint64_t launches = 0;
+  if (h->ev_pending == bm25f_handle::EV_RING) {
+    int rc = fold_events(h, 1);
+    if (rc) return rc;
+  }
+  cudaEvent_t* ev = h->ev[h->ev_head];
+  CU(cudaEventRecord(ev[0], st));
+  if (p->Q) CU(cudaMemsetAsync(p->d_totals, 0, (size_t)p->Q * 8, st));
+  const unsigned long long nb = (unsigned long long)p->n_leaves * (p->T + 1);
+  if (nb) {
+    k_tile_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(p->d_leaves, p->n_leaves, p->T, h->S, h->d_docids, p->d_bounds);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaEventRecord(ev[1], st));
+  if (p->n_items) {
+    ScoreParams sp;
+    sp.docids = h->d_docids;
+    sp.payload = h->d_payload;
+    sp.lb = h->d_lb;
+    sp.deleted = h->d_deleted;
+    sp.norm = h->d_norm;
+    sp.leaves = p->d_leaves;
+    sp.queries = p->d_queries;
+    sp.items = p->d_items;
+    sp.bounds = p->d_bounds;
+    sp.part_keys = p->d_part_keys;
+    sp.totals = p->d_totals;
+    sp.S = h->S;
+    sp.T = p->T;
+    sp.n_docs = (uint32_t)h->n_docs;
+    sp.doc_base = (uint32_t)h->doc_base;
+    sp.k = p->k;
+    sp.cap = p->cap;
+    if (h->packed) k_score_topk<true><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
+    else k_score_topk<false><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
+    CU(cudaGetLastError());
+    ++launches;
+  }
+  CU(cudaEventRecord(ev[2], st));
+  if (p->Q) {
+    k_merge_topk<<<p->Q, 128, (size_t)2 * p->kp * 8, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->kp, p->d_keys);
+    CU(cudaGetLastError());
+    k_decode_keys<<<p->Q, 64, 0, st>>>(p->d_keys, p->Q, p->k, p->d_scores, p->d_docids, p->d_counts);
+    CU(cudaGetLastError());
+    launches += 2;
+  }
+  CU(cudaEventRecord(ev[3], st));
+  h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
+  ++h->ev_pending;
+  h->stats.postings_touched = p->postings;
+  h->stats.n_items = p->n_items;
+  h->stats.n_launches = launches;
+  if (h->ctas_per_sm == 0) {
+    int nb_ = 0;
+    if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<true>, (int)h->NT, p->smem_score);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<false>, (int)h->NT, p->smem_score);
+    h->ctas_per_sm = nb_;
+    h->stats.ctas_per_sm = (uint32_t)nb_;
+  }
+  return 0;
+}
+
+int bm25f_set_stream(bm25f_handle* h, void* stream) {
+  if (!h) return fail(BM25F_EINVAL, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  h->stream = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  return 0;
+}
+
+int bm25f_synchronize(bm25f_handle* h) {
+  if (!h) return fail(BM25F_EINVAL, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  return fold_events(h, h->ev_pending);
+}
+
+int bm25f_fetch(bm25f_handle* h, bm25f_plan* p, float* out_scores, uint32_t* out_docids, uint32_t* out_counts,
+                uint64_t* out_totals) {
+  if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t)p->Q * p->k;
+  if (out_scores && n) CU(cudaMemcpyAsync(out_scores, p->d_scores, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_docids && n) CU(cudaMemcpyAsync(out_docids, p->d_docids, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_counts && p->Q) CU(cudaMemcpyAsync(out_counts, p->d_counts, (size_t)p->Q * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_totals && p->Q) CU(cudaMemcpyAsync(out_totals, p->d_totals, (size_t)p->Q * 8, cudaMemcpyDeviceToHost, h->stream));
+  return bm25f_synchronize(h);
+}
+
+int bm25f_plan_device_results(bm25f_plan* p, uint64_t** d_keys, uint64_t** d_totals) {
+  if (!p) return fail(BM25F_EINVAL, "null plan");
+  if (d_keys) *d_keys = reinterpret_cast<uint64_t*>(p->d_keys);
+  if (d_totals) *d_totals = reinterpret_cast<uint64_t*>(p->d_totals);
+  return 0;
+}
+
+int bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* b, int k, float* out_scores, uint32_t* out_docids,
+                       uint32_t* out_counts, uint64_t* out_totals) {
+  bm25f_plan* p = nullptr;
+  int rc = bm25f_prepare(h, b, k, &p);
+  if (rc) return rc;
+  rc = bm25f_execute(h, p);
+  if (!rc) rc = bm25f_fetch(h, p, out_scores, out_docids, out_counts, out_totals);
+  bm25f_plan_destroy(p);
+  return rc;
+}
+
+int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
+                     uint64_t* d_out_keys, void* stream) {
+  if (!h || !d_keys || !d_out_keys) return fail(BM25F_EINVAL, "null argument");
+  if (k < 1 || k > BM25F_MAX_K || n_lists < 1) return fail(BM25F_EINVAL, "bad k or n_lists");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  int kp = 1;
+  while (kp < k) kp <<= 1;
+  if (n_queries) {
+    k_merge_topk<<<n_queries, 128, (size_t)2 * kp * 8, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), nullptr, 1, n_lists,
+                                                             (unsigned long long)n_queries * k, n_queries, k, kp,
+                                                             reinterpret_cast<unsigned long long*>(d_out_keys));
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+int bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_queries, int k, float* d_scores,
+                      uint32_t* d_docids, uint32_t* d_counts, void* stream) {
+  if (!h || !d_keys) return fail(BM25F_EINVAL, "null argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  if (n_queries) {
+    k_decode_keys<<<n_queries, 64, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), n_queries, k, d_scores, d_docids, d_counts);
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+int bm25f_get_stats(bm25f_handle* h, bm25f_stats* out) {
+  if (!h || !out) return fail(BM25F_EINVAL, "null argument");
+  *out = h->stats;
+  return 0;
+}
+
+int bm25f_reset_stats(bm25f_handle* h) {
+  if (!h) return fail(BM25F_EINVAL, "null handle");
+  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = 0.0f;
+  h->stats.n_executes = 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+"""Document-sharded search across the GPUs of one box (SURVEY.md §8 e).
+
+One process per GPU (``torch.distributed``, backend ``nccl``).  Rank ``g`` holds the
+contiguous document range ``[g*N/G, (g+1)*N/G)`` as its own CSR with local docids and
+``doc_base`` set to the range start — the exact analogue of a Whoosh segment with a doc
+offset (W8).  Replicated on every rank: the term dictionary, the corpus-wide ``df`` /
+``doc_count_all`` / field totals (so idf and avgfl are global) and the query batch.
+
+Per batch the path has ONE exchange step: every rank scores its shard and produces, per
+query, a local top-k as 64-bit W11 keys over *global* docnums and a local match count;
+then ``all_gather`` of the ``Q*k`` keys and ``all_reduce(sum)`` of the ``Q`` totals, and the
+merge kernel (``bm25f_merge_keys``) selects the top-k of the ``G*k`` candidates per query on
+every rank.  PyTorch supplies the NCCL plumbing and the receive buffers; scoring, top-k and
+the merge are the library's own kernels.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _ffi
+from .searching import Searcher
+
+
+class _RawCuda:
+    """Zero-copy view of library-owned device memory for ``torch.as_tensor``."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+def device_view(ptr: int, n: int, device: int) -> torch.Tensor:
+    """int64 tensor aliasing ``n`` 64-bit words at device pointer ``ptr``."""
+    return torch.as_tensor(_RawCuda(ptr, n, "<i8"), device="cuda:%d" % device)
+
+
+def merge_keys_host(gathered: np.ndarray, k: int) -> np.ndarray:
+    """Host restatement of the merge kernel for CPU (gloo) tests: ``gathered`` is
+    ``[G, Q, k]`` uint64 keys (0 = empty); returns ``[Q, k]`` with the k largest per query."""
+    G, Q, _ = gathered.shape
+    allk = np.transpose(gathered, (1, 0, 2)).reshape(Q, G * k)
+    allk = np.sort(allk.astype(np.uint64), axis=1)[:, ::-1]      # descending = W11 order
+    return np.ascontiguousarray(allk[:, :k])
+
+
+def decode_keys_host(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """``(scores f32, docids u32, counts)`` from uint64 keys (host mirror of ``bm25f_decode_keys``)."""
+    u = (keys >> np.uint64(32)).astype(np.uint32)
+    pos = (u & np.uint32(0x80000000)) != 0
+    bits = np.where(pos, u & np.uint32(0x7FFFFFFF), ~u)
+    scores = bits.astype(np.uint32).view(np.float32).copy()
+    docids = (np.uint64(0xFFFFFFFF) - (keys & np.uint64(0xFFFFFFFF))).astype(np.uint32)
+    valid = keys != 0
+    scores[~valid] = -np.inf
+    docids[~valid] = 0xFFFFFFFF
+    return scores, docids, valid.sum(axis=-1).astype(np.uint32)
+
+
+class ShardedSearcher:
+    """Rank-local searcher over one document shard plus the cross-GPU merge."""
+
+    def __init__(self, full_ix, rank: Optional[int] = None, world: Optional[int] = None, device: Optional[int] = None,
+                 weighting=None, group=None, shard_ix=None, **engine_opts):
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.device = torch.cuda.current_device() if device is None else device
+        self.group = group
+        if shard_ix is None:
+            shard_ix = full_ix if self.world == 1 else full_ix.shard(self.rank, self.world)
+        self.shard_ix = shard_ix
+        # corpus-wide statistics come from ``full_ix`` (only its df / totals / dictionary are used)
+        self.local = Searcher(self.shard_ix, weighting=weighting, device=self.device, stats_ix=full_ix, **engine_opts)
+        self.engine = self.local.engine
+        self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._bufs = {}
+
+    def pack(self, queries, after_keys=None):
+        return self.local.pack(queries, after_keys)
+
+    def _buffers(self, Q: int, k: int):
+        key = (Q, k)
+        b = self._bufs.get(key)
+        if b is None:
+            dev = "cuda:%d" % self.device
+            b = dict(gathered=torch.empty(self.world * Q * k, dtype=torch.int64, device=dev),
+                     merged=torch.empty(Q * k, dtype=torch.int64, device=dev),
+                     totals=torch.empty(Q, dtype=torch.int64, device=dev),
+                     scores=torch.empty(Q * k, dtype=torch.float32, device=dev),
+                     docids=torch.empty(Q * k, dtype=torch.int32, device=dev),
+                     counts=torch.empty(Q, dtype=torch.int32, device=dev))
+            self._bufs[key] = b
+        return b
+
+    def run_plan(self, plan: _ffi.Plan):
+        """Execute a prepared plan on this shard, exchange, merge.  Everything is enqueued on
+        torch's current stream; returns the device buffers (merged keys, totals, decoded)."""
+        Q, k = plan.n_queries, plan.k
+        b = self._buffers(Q, k)
+        plan.execute()
+        d_keys, d_totals = plan.device_results()
+        local_keys = device_view(d_keys, Q * k, self.device)
+        local_totals = device_view(d_totals, Q, self.device)
+        if self.world > 1:
+            dist.all_gather_into_tensor(b["gathered"], local_keys, group=self.group)
+            b["totals"].copy_(local_totals)
+            dist.all_reduce(b["totals"], op=dist.ReduceOp.SUM, group=self.group)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.engine.merge_keys(b["gathered"].data_ptr(), self.world, Q, k, b["merged"].data_ptr(), stream)
+        else:
+            b["merged"].copy_(local_keys)
+            b["totals"].copy_(local_totals)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.engine.decode_keys(b["merged"].data_ptr(), Q, k, b["scores"].data_ptr(), b["docids"].data_ptr(),
+                                b["counts"].data_ptr(), stream)
+        return b
+
+    def search_packed(self, batch: _ffi.PackedBatch, k: int):
+        """Host buffers in, host buffers out: ``(scores, docids, counts, totals)`` of the whole corpus."""
+        plan = self.engine.prepare(batch, k)
+        try:
+            b = self.run_plan(plan)
+            Q = batch.n_queries
+            scores = b["scores"].cpu().numpy().reshape(Q, k)
+            docids = b["docids"].cpu().numpy().view(np.uint32).reshape(Q, k)
+            counts = b["counts"].cpu().numpy().view(np.uint32)
+            totals = b["totals"].cpu().numpy().view(np.uint64)
+        finally:
+            plan.close()
+        return scores, docids, counts, totals

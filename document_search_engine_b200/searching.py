@@ -1,0 +1,357 @@
+"""``Searcher`` / ``Results`` / ``ResultsPage`` / ``Hit`` with the Whoosh contract the
+reference's front ends consume (b).
+
+Call sites served (reference file:line):
+
+* ``with ix.searcher(weighting=weighting) as searcher``            my_flask.py:184
+* ``searcher.search_page(qp, pagenum=..., pagelen=...)``            my_flask.py:208, :211
+* ``searcher.search(qp, limit=MAXIMUM_SAME_SESSION_HITS + 1)``      my_flask.py:304
+* ``results.scored_length()``, ``results[0]['session']``, iteration  my_flask.py:306, :315
+* ``page.total / .offset / .pagelen / .pagenum / len(page)``        my_flask.py:212, :287-293
+* ``hit.docnum``, ``hit['field']``, ``hit.results.q``, ``hit.searcher``  my_flask.py:326-380
+* ``searcher.ixreader.frequency('exact', word)``                    my_flask.py:254
+* ``searcher.stored_fields(docnum)``                                my_whoosh.py:131
+
+New: ``search_batch(queries, limit)`` — the batched entry the GPU wants.  Scoring and
+top-k always run on the GPU through ``libbm25f``; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import time
+from math import ceil, log
+from typing import Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi
+from .query import Query, UnsupportedQuery, lower
+from .scoring import BM25F, instantiate
+
+#: bound on the per-call tile-boundary table (bytes); larger batches are split
+BOUNDS_BYTES_PER_CALL = 1 << 30
+DEFAULT_TILE_DOCS = 8192
+
+
+def make_keys(scores: np.ndarray, docids: np.ndarray) -> np.ndarray:
+    """The engine's 64-bit W11 ordering key (score desc, docnum asc), host version."""
+    u = np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    neg = (u & np.uint64(0x80000000)) != 0
+    u = np.where(neg, (~u) & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+    return (u << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - docids.astype(np.uint64))
+
+
+class Hit:
+    def __init__(self, results: "Results", docnum: int, pos: int, score: float):
+        self.results = results
+        self.searcher = results.searcher
+        self.docnum = docnum
+        self.pos = self.rank = pos
+        self.score = score
+        self._fields = None
+
+    def fields(self):
+        if self._fields is None:
+            self._fields = self.searcher.stored_fields(self.docnum)
+        return self._fields
+
+    def __getitem__(self, name):
+        return self.fields()[name]
+
+    def __contains__(self, name):
+        return name in self.fields()
+
+    def get(self, name, default=None):
+        return self.fields().get(name, default)
+
+    def keys(self):
+        return self.fields().keys()
+
+    def __iter__(self):
+        return iter(self.fields())
+
+    def __len__(self):
+        return len(self.fields())
+
+    def __repr__(self):
+        return "<Hit %r>" % (dict(self.fields()),)
+
+    def highlights(self, fieldname, text=None, top=3, minscore=1):
+        raise NotImplementedError("highlighting is outside the scoring path (SURVEY.md §2: out of scope)")
+
+
+class Results:
+    """Scored top-N plus the exact match count (``len(results)``, W13)."""
+
+    def __init__(self, searcher: "Searcher", q: Query, top_n, total: int, runtime: float = 0.0):
+        self.searcher = searcher
+        self.q = q
+        self.top_n = list(top_n)             # [(score, docnum)] in W11 order
+        self._total = int(total)
+        self.runtime = runtime
+        # settable presentation hooks the reference assigns (my_flask.py:349-352)
+        self.fragmenter = None
+        self.order = None
+        self.scorer = None
+        self.formatter = None
+
+    def __len__(self):
+        return self._total
+
+    def __repr__(self):
+        return "<Top %s Results for %r runtime=%s>" % (len(self.top_n), self.q, self.runtime)
+
+    def scored_length(self):
+        return len(self.top_n)
+
+    def has_exact_length(self):
+        return True
+
+    def estimated_length(self):
+        return self._total
+
+    def estimated_min_length(self):
+        return self._total
+
+    def is_empty(self):
+        return self._total == 0
+
+    def score(self, n):
+        return self.top_n[n][0]
+
+    def docnum(self, n):
+        return self.top_n[n][1]
+
+    def docs(self):
+        return set(d for _, d in self.top_n)
+
+    def fields(self, n):
+        return self.searcher.stored_fields(self.top_n[n][1])
+
+    def __getitem__(self, n):
+        if isinstance(n, slice):
+            start, stop, step = n.indices(len(self.top_n))
+            return [Hit(self, self.top_n[i][1], i, self.top_n[i][0]) for i in range(start, stop, step)]
+        if n < 0:
+            n += len(self.top_n)
+        if n >= len(self.top_n) or n < 0:
+            raise IndexError("results[%r]: Results only has %s hits" % (n, len(self.top_n)))
+        return Hit(self, self.top_n[n][1], n, self.top_n[n][0])
+
+    def __iter__(self):
+        for i in range(len(self.top_n)):
+            yield Hit(self, self.top_n[i][1], i, self.top_n[i][0])
+
+
+class ResultsPage:
+    """W13: a page view over ``search(q, limit=pagenum * pagelen)``."""
+
+    def __init__(self, results: Results, pagenum: int, pagelen: int = 10):
+        self.results = results
+        self.total = len(results)
+        if pagenum < 1:
+            raise ValueError("pagenum must be >= 1")
+        self.pagecount = int(ceil(self.total / pagelen))
+        self.pagenum = min(self.pagecount, pagenum)
+        offset = (self.pagenum - 1) * pagelen
+        if (offset + pagelen) > self.total:
+            pagelen = self.total - offset
+        self.offset = offset
+        self.pagelen = pagelen
+
+    def __getitem__(self, n):
+        offset = self.offset
+        if isinstance(n, slice):
+            start, stop, step = n.indices(self.pagelen)
+            return self.results.__getitem__(slice(start + offset, stop + offset, step))
+        return self.results.__getitem__(n + offset)
+
+    def __iter__(self):
+        return iter(self.results[self.offset:self.offset + self.pagelen])
+
+    def __len__(self):
+        return self.total          # the reference relies on this (my_flask.py:212)
+
+    def scored_length(self):
+        return self.results.scored_length()
+
+    def score(self, n):
+        return self.results.score(n + self.offset)
+
+    def docnum(self, n):
+        return self.results.docnum(n + self.offset)
+
+    def is_last_page(self):
+        return self.pagecount == 0 or self.pagenum == self.pagecount
+
+
+class Searcher:
+    """Whoosh-shaped searcher over a ``FlatIndex`` whose postings live in HBM."""
+
+    def __init__(self, ix, weighting=None, device: int = 0, tile_docs: int = 0, threads: int = 0,
+                 split_postings: int = 0, stats_ix=None):
+        self.ix = ix
+        #: index the corpus statistics come from (the whole corpus when ``ix`` is a shard, W8)
+        self.stats_ix = stats_ix or ix
+        self.weighting = instantiate(weighting)
+        if not isinstance(self.weighting, BM25F):
+            raise NotImplementedError("only BM25F weightings run on the GPU path")
+        self.device = device
+        self.ixreader = self.stats_ix.reader()
+        key = (device, tile_docs, threads, split_postings)
+        eng = ix._engine_cache.get(key)
+        if eng is None:
+            eng = _ffi.Engine(ix, device=device, tile_docs=tile_docs, threads=threads,
+                              split_postings=split_postings)
+            ix._engine_cache[key] = eng
+        self.engine = eng
+        wkey = self.weighting.key() + (self.stats_ix.doc_count_all(),)
+        if eng._weighting_key != wkey:
+            eng.set_weighting(self.weighting.norm_tables(self.stats_ix), key=wkey)
+        self._idf_cache = {}
+        self.closed = False
+
+    # -- context manager / lifetime (my_flask.py:184) ---------------------------
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def close(self):
+        self.closed = True       # the uploaded index stays cached on the FlatIndex
+
+    # -- statistics ---------------------------------------------------------------
+    def doc_count_all(self):
+        return self.stats_ix.doc_count_all()
+
+    def doc_count(self):
+        return self.stats_ix.doc_count()
+
+    def doc_frequency(self, fieldname, text):
+        tid = self.stats_ix.term_id(fieldname, text)
+        return 0 if tid < 0 else int(self.stats_ix.df[tid])
+
+    def idf(self, fieldname, text):
+        k = (fieldname, text)
+        v = self._idf_cache.get(k)
+        if v is None:
+            v = self.weighting.idf(self, fieldname, text)
+            self._idf_cache[k] = v
+        return v
+
+    def avg_field_length(self, fieldname):
+        return self.stats_ix.avg_field_length(fieldname)
+
+    def stored_fields(self, docnum):
+        return self.stats_ix.stored_fields(docnum)
+
+    def reader(self):
+        return self.ixreader
+
+    def get_parent(self):
+        return self
+
+    # -- lowering -------------------------------------------------------------------
+    def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
+        """Lower query trees to the ``bm25f_query_batch`` layout.  Leaf weights
+        ``idf * (K1 + 1) * boost`` are evaluated in float64 and rounded once."""
+        offs = [0]
+        ngroups: List[int] = []
+        terms: List[int] = []
+        weights: List[float] = []
+        groups: List[int] = []
+        k1p = self.weighting.K1 + 1.0
+        ix = self.ix
+        for q in queries:
+            leaves, g, kind = lower(q)
+            if kind == "every":
+                raise UnsupportedQuery("Every() is not served by the GPU path yet (SURVEY.md §8 f3)")
+            if kind == "null":
+                ngroups.append(0)
+                offs.append(len(terms))
+                continue
+            if len(leaves) > _ffi.MAX_LEAVES_PER_QUERY:
+                raise UnsupportedQuery("more than %d leaves in one query" % _ffi.MAX_LEAVES_PER_QUERY)
+            if g > 32:
+                raise UnsupportedQuery("more than 32 AND-groups in one query")
+            for lf in leaves:
+                tid = ix.term_id(lf.fieldname, lf.text)
+                terms.append(_ffi.TERM_UNKNOWN if tid < 0 else tid)
+                weights.append(self.idf(lf.fieldname, lf.text) * k1p * lf.boost)
+                groups.append(lf.group)
+            ngroups.append(g)
+            offs.append(len(terms))
+        return _ffi.PackedBatch(offs, ngroups, terms, np.asarray(weights, dtype=np.float64), groups, after_keys)
+
+    # -- searching ----------------------------------------------------------------
+    def _run_packed(self, batch: _ffi.PackedBatch, k: int):
+        """Run a packed batch, splitting it so the boundary table stays bounded."""
+        T = max(1, -(-self.ix.n_docs_all // (self.engine.stats()["tile_docs"] or DEFAULT_TILE_DOCS)))
+        max_leaves = max(_ffi.MAX_LEAVES_PER_QUERY, BOUNDS_BYTES_PER_CALL // (4 * (T + 1)))
+        if batch.n_leaves <= max_leaves:
+            return self.engine.search_batch(batch, k)
+        outs = []
+        a = 0
+        offs = batch.query_leaf_offsets
+        while a < batch.n_queries:
+            b = int(np.searchsorted(offs, offs[a] + max_leaves, side="right")) - 1
+            b = min(max(b, a + 1), batch.n_queries)
+            outs.append(self.engine.search_batch(batch.slice(a, b), k))
+            a = b
+        return tuple(np.concatenate([o[i] for o in outs]) for i in range(4))
+
+    def search_packed(self, batch: _ffi.PackedBatch, limit: int = 10):
+        """``(scores [Q,k] f32, docids [Q,k] u32, counts [Q], totals [Q])`` for a packed batch."""
+        if limit < 1 or limit > _ffi.MAX_K:
+            raise ValueError("limit must be 1..%d for search_packed" % _ffi.MAX_K)
+        return self._run_packed(batch, limit)
+
+    def search_batch(self, queries: Sequence[Query], limit: Optional[int] = 10) -> List[Results]:
+        """Batched ``search``: one GPU pass for all queries (several when ``limit`` is
+        ``None`` or exceeds the kernel's top-k capacity: the next pass collects only hits
+        ordered strictly after the last one already returned)."""
+        if self.weighting.use_final:
+            raise NotImplementedError(
+                "weightings with use_final=True (DescDateBM25F/AscDateBM25F, my_whoosh.py:127-154) apply "
+                "final() to every match before top-k (W14); the device path for it is SURVEY.md §8 f1")
+        t_start = time.perf_counter()
+        queries = list(queries)
+        nq = len(queries)
+        want = [limit if limit is not None else None] * nq
+        tops: List[list] = [[] for _ in range(nq)]
+        totals = np.zeros(nq, dtype=np.uint64)
+        active = list(range(nq))
+        after = None
+        first = True
+        while active:
+            k = _ffi.MAX_K if limit is None else min(limit, _ffi.MAX_K)
+            batch = self.pack([queries[i] for i in active], after)
+            scores, docids, counts, tot = self._run_packed(batch, k)
+            nxt, nxt_after = [], []
+            for j, i in enumerate(active):
+                c = int(counts[j])
+                if first:
+                    totals[i] = tot[j]
+                tops[i].extend(zip(scores[j, :c].tolist(), docids[j, :c].tolist()))
+                need = int(totals[i]) if want[i] is None else min(want[i], int(totals[i]))
+                if c == k and len(tops[i]) < need:
+                    nxt.append(i)
+                    nxt_after.append(make_keys(scores[j, c - 1:c], docids[j, c - 1:c])[0])
+            if limit is not None:
+                for i in active:
+                    del tops[i][limit:]
+            active = nxt
+            after = np.asarray(nxt_after, dtype=np.uint64) if nxt else None
+            first = False
+        dt = time.perf_counter() - t_start
+        return [Results(self, queries[i], tops[i], int(totals[i]), runtime=dt) for i in range(nq)]
+
+    def search(self, q: Query, limit: Optional[int] = 10, **kwargs) -> Results:
+        if limit is not None and limit < 1:
+            raise ValueError("limit must be >= 1")
+        return self.search_batch([q], limit=limit)[0]
+
+    def search_page(self, q: Query, pagenum: int, pagelen: int = 10, **kwargs) -> ResultsPage:
+        if pagenum < 1:
+            raise ValueError("pagenum must be >= 1")
+        return ResultsPage(self.search(q, limit=pagenum * pagelen, **kwargs), pagenum, pagelen)

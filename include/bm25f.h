@@ -1,0 +1,162 @@
+/*
+ * bm25f.h — C ABI of libbm25f.so, the B200-native BM25F scoring + top-k engine.
+ *
+ * This is the drop-in boundary for one hot path of CodeOptimist/document-search-engine.
+ * The reference is pure Python on top of Whoosh 2.7.4 (reference requirements.txt:6); it
+ * has no FFI of its own, so the entry points below are what a ctypes binding for the
+ * scoring path replaces, call site by call site:
+ *
+ *   bm25f_create / bm25f_destroy
+ *       <- the index handle the front ends keep for the life of the process:
+ *          `ix = my_index.get_idx('index')`            reference my_flask.py:549, cli.py:25
+ *          (open at my_index.py:226-234).  create uploads the flattened index to HBM once.
+ *   bm25f_set_weighting
+ *       <- `ix.searcher(weighting=BM25F | AscDateBM25F | DescDateBM25F)`
+ *                                                      reference my_flask.py:183-184
+ *          (B, K1, per-field B and the corpus avgfl are folded into per-field norm tables).
+ *   bm25f_search_batch  (= bm25f_prepare + bm25f_execute + bm25f_fetch)
+ *       <- `searcher.search_page(qp, pagenum, pagelen)` reference my_flask.py:208, :211
+ *          `searcher.search(qp, limit=3)`               reference my_flask.py:304
+ *          `ix.searcher().search(Every('session'), limit=None)`   reference cli.py:9
+ *          i.e. Whoosh Searcher.search -> matcher tree -> BM25FScorer -> TopCollector.
+ *   bm25f_merge_keys / bm25f_decode_keys
+ *       <- Whoosh's multi-segment collection (global docnum = segment offset + local docnum,
+ *          one collector over all segments); here: merge of per-GPU local top-k lists
+ *          after the NCCL all-gather.
+ *   bm25f_get_stats
+ *       <- `Results.runtime` (Whoosh records wall time per search; the reference never reads it).
+ *
+ * Conventions: every function returns 0 on success or a negative BM25F_E* code; the message
+ * is available from bm25f_last_error() (thread-local).  No exceptions or abort() cross this
+ * boundary.  A handle is not thread-safe: one in-flight call per handle.  The caller owns all
+ * host buffers; the library copies what it needs and owns all device memory until destroy.
+ * Pointers in bm25f_index_desc may be host or device pointers (the copy uses UVA);
+ * term_offsets and term_field must be host pointers.
+ */
+#ifndef BM25F_H_
+#define BM25F_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BM25F_ABI_VERSION 1
+
+#define BM25F_OK          0
+#define BM25F_EINVAL     -1   /* bad argument */
+#define BM25F_ECUDA      -2   /* CUDA runtime error */
+#define BM25F_ENCCL      -3   /* reserved: collective error (collectives run in the host layer) */
+#define BM25F_ENOMEM     -4   /* out of (device or host) memory */
+#define BM25F_EABI       -5   /* ABI version mismatch */
+
+#define BM25F_MAX_LEAVES_PER_QUERY 64
+#define BM25F_MAX_K               1024
+#define BM25F_TERM_UNKNOWN 0xFFFFFFFFu  /* leaf_term value for a term/field not in the index (empty matcher) */
+
+typedef struct bm25f_handle bm25f_handle;
+typedef struct bm25f_plan bm25f_plan;
+
+/* Flattened index of one document shard (SURVEY.md §8 b). */
+typedef struct {
+  uint32_t abi_version;          /* must be BM25F_ABI_VERSION */
+  uint32_t n_fields;
+  uint64_t n_docs_all;           /* documents in this shard, deleted ones included */
+  uint64_t n_terms;              /* posting lists; a "term" is a (field, text) pair */
+  uint64_t n_postings;
+  uint64_t doc_base;             /* global docnum of local document 0 (Whoosh segment offset) */
+  const uint64_t* term_offsets;  /* [n_terms + 1] CSR row pointers (host) */
+  const uint8_t*  term_field;    /* [n_terms] field index of every posting list (host) */
+  const uint32_t* docids;        /* [n_postings] local docids, ascending inside a term */
+  const float*    tfs;           /* [n_postings] posting weights (term count x field boost) */
+  const uint8_t*  len_bytes;     /* [n_fields * n_docs_all] quantised field lengths */
+  const uint8_t*  deleted;       /* [n_docs_all] 1 = deleted, or NULL */
+} bm25f_index_desc;
+
+/* Engine options; zero means "library default". */
+typedef struct {
+  uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
+  uint32_t threads;              /* threads per CTA of the scoring kernel */
+  uint32_t split_postings;       /* target postings per work item */
+  uint32_t reserved[5];
+} bm25f_options;
+
+/* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves
+ * (an OR query is the one-group case).  Leaves of a query are contiguous and sorted by group. */
+typedef struct {
+  uint32_t n_queries;
+  uint32_t n_leaves;
+  const uint32_t* query_leaf_offsets;  /* [n_queries + 1] */
+  const uint8_t*  query_n_groups;      /* [n_queries]; 0 = null query (matches nothing) */
+  const uint32_t* leaf_term;           /* [n_leaves] posting-list id or BM25F_TERM_UNKNOWN */
+  const float*    leaf_weight;         /* [n_leaves] idf * (K1 + 1) * boost, rounded from float64 */
+  const uint8_t*  leaf_group;          /* [n_leaves] group index inside the query */
+  const uint64_t* after_keys;          /* [n_queries] or NULL: only hits ordered strictly after this
+                                          key are collected (paging past BM25F_MAX_K); 0 = no bound */
+} bm25f_query_batch;
+
+typedef struct {
+  uint64_t postings_touched;     /* sum over leaves of live df, last execute */
+  uint64_t n_items;              /* work items of the last execute */
+  uint64_t n_launches;           /* kernels launched by the last execute */
+  uint64_t n_executes;           /* executes folded into the ms_* sums since the last reset */
+  float    ms_bounds;            /* summed device time of the tile-boundary kernel (CUDA events) */
+  float    ms_score;             /* summed device time of the scoring + top-k kernel */
+  float    ms_merge;             /* summed device time of the merge + decode kernels */
+  float    ms_total;             /* summed first-launch-to-last-kernel-end time */
+  uint32_t tile_docs;
+  uint32_t threads;
+  uint32_t ctas_per_sm;
+  uint32_t packed_payload;       /* 1: (tf,lb) packed in 32 bits; 0: float tf + length byte */
+  uint64_t device_bytes;         /* device memory held by the index */
+} bm25f_stats;
+
+int  bm25f_abi_version(void);
+const char* bm25f_last_error(void);
+
+int  bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* opts, bm25f_handle** out);
+void bm25f_destroy(bm25f_handle* h);
+
+/* norm: [n_fields * 256] float32, norm[f][b] = K1 * ((1 - B_f) + B_f * fl(b) / avgfl_f). */
+int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
+
+/* Host planning + upload of one batch.  The plan can be executed any number of times. */
+int  bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
+/* Launch the kernels of a plan on the handle's stream (asynchronous). */
+int  bm25f_execute(bm25f_handle* h, bm25f_plan* plan);
+/* Wait for the plan's kernels and copy the results to host buffers:
+ * out_scores/out_docids [n_queries * k] (unused slots: -inf / 0xFFFFFFFF),
+ * out_counts [n_queries] hits written, out_totals [n_queries] exact number of matching documents. */
+int  bm25f_fetch(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_t* out_docids,
+                 uint32_t* out_counts, uint64_t* out_totals);
+/* Device-resident results of a plan: keys [n_queries * k] (0 = empty slot), totals [n_queries]. */
+int  bm25f_plan_device_results(bm25f_plan* plan, uint64_t** d_keys, uint64_t** d_totals);
+int  bm25f_synchronize(bm25f_handle* h);
+/* Launch on the caller's stream (a cudaStream_t; e.g. the host framework's current stream) so the
+ * caller's events and collectives order with the library's kernels.  NULL restores the own stream. */
+int  bm25f_set_stream(bm25f_handle* h, void* stream);
+void bm25f_plan_destroy(bm25f_plan* plan);
+
+/* prepare + execute + fetch */
+int  bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* batch, int k, float* out_scores,
+                        uint32_t* out_docids, uint32_t* out_counts, uint64_t* out_totals);
+
+/* Merge n_lists device-resident top-k key lists per query (layout [n_lists][n_queries][k], as an
+ * all-gather of per-shard results produces) into d_out_keys [n_queries][k].  Runs on `stream`
+ * (a cudaStream_t, or NULL for the handle's stream). */
+int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
+                      uint64_t* d_out_keys, void* stream);
+/* Decode device keys to device arrays of scores / docids / counts (any may be NULL). */
+int  bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_queries, int k,
+                       float* d_scores, uint32_t* d_docids, uint32_t* d_counts, void* stream);
+
+/* Timings are folded in by bm25f_synchronize / bm25f_fetch. */
+int  bm25f_get_stats(bm25f_handle* h, bm25f_stats* out);
+int  bm25f_reset_stats(bm25f_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BM25F_H_ */

@@ -24,6 +24,7 @@ Queries are duck-typed on the class names ``Term`` / ``And`` / ``Or`` / ``Every`
 """
 from __future__ import annotations
 
+from bisect import bisect_left
 from heapq import heappush, heapreplace
 from math import log
 
@@ -221,9 +222,10 @@ class PostingMatcher:
         self._skip_deleted()
 
     def skip_to(self, d):
-        ids, n = self.ids, len(self.ids)
-        while self.i < n and ids[self.i] < d:
-            self.i += 1
+        # Whoosh skips whole posting blocks and bisects inside one; a bisect from the
+        # current position is the same O(log n) behaviour
+        if self.i < len(self.ids) and self.ids[self.i] < d:
+            self.i = bisect_left(self.ids, d, self.i + 1)
         self._skip_deleted()
 
     def score(self):

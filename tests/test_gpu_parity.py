@@ -1,0 +1,154 @@
+"""GPU parity tests proper: CUDA path (through the façade -> ctypes -> C ABI) vs the oracle."""
+import numpy as np
+import pytest
+
+from document_search_engine_b200 import And, BM25F, FlatIndex, Or, Term
+from document_search_engine_b200.corpus import (config_corpus, config_queries, make_corpus, make_queries,
+                                                 TITLE, BODY)
+from oracle.numpy_oracle import NumpyOracle
+from tests.parity import assert_batch_parity, assert_query_parity
+from tests.test_oracle_kat import kat1_index
+
+pytestmark = pytest.mark.gpu
+
+
+def test_kat1_gpu():
+    ix = kat1_index()
+    with ix.searcher(weighting=BM25F) as s:
+        r = s.search(Or([Term("f", "a"), Term("f", "b")]), limit=10)
+        assert len(r) == 3 and [h.docnum for h in r] == [2, 3, 0]
+        want = [3.1036244074953756, 2.1209246397136083, 1.5080645161290325]
+        assert [h.score for h in r] == pytest.approx(want, rel=1e-6)
+        r = s.search(And([Term("f", "a"), Term("f", "b")]), limit=10)
+        assert len(r) == 2 and [h.docnum for h in r] == [2, 3]
+        assert s.search(Term("f", "nope")).is_empty()
+        assert s.search(And([Term("f", "a"), Term("f", "nope")])).is_empty()
+        assert len(s.search(Or([Term("f", "a"), Term("f", "nope")]))) == 3
+
+
+def test_kat1_deleted_gpu():
+    ix = kat1_index(deleted=[2])
+    o = NumpyOracle(ix)
+    with ix.searcher() as s:
+        for q in (Or([Term("f", "a"), Term("f", "b")]), And([Term("f", "a"), Term("f", "b")]), Term("f", "a")):
+            r = s.search(q)
+            assert_query_parity(o, q, r.top_n, len(r), 10)
+
+
+@pytest.fixture(scope="module")
+def cfg1():
+    ix = config_corpus(1, device="cpu")
+    return ix, NumpyOracle(ix)
+
+
+@pytest.mark.parametrize("mode", ["and", "or", "mixed"])
+def test_config1(cfg1, mode):
+    ix, o = cfg1
+    qs = make_queries(1000, 50_000, 20261001, 2, 2 if mode == "and" else 4, mode)
+    with ix.searcher(weighting=BM25F) as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+def test_config1_variants_groups(cfg1):
+    ix, o = cfg1
+    qs = make_queries(300, 50_000, 20261003, 4, 4, "and", variants=True)
+    with ix.searcher() as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (65536, 0)])
+def test_tiling_and_splitting(cfg1, tile_docs, split):
+    """Tiny tiles and tiny work items: many tiles per query, many partial lists to merge."""
+    ix, o = cfg1
+    qs = make_queries(200, 50_000, 77, 2, 4, "mixed", skip_top=0)       # includes the densest terms
+    with ix.searcher(tile_docs=tile_docs, split_postings=split) as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+@pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])
+def test_limits(cfg1, k):
+    ix, o = cfg1
+    qs = make_queries(60, 50_000, 5, 2, 3, "or", skip_top=0)
+    with ix.searcher() as s:
+        res = s.search_batch(qs.queries, limit=k)
+    assert_batch_parity(o, qs.queries, res, k)
+
+
+def test_limit_none_and_paging_past_kernel_k(cfg1):
+    ix, o = cfg1
+    qs = make_queries(6, 50_000, 9, 2, 3, "or", skip_top=0)            # thousands of matches each
+    with ix.searcher() as s:
+        res = s.search_batch(qs.queries, limit=None)
+        assert_batch_parity(o, qs.queries, res, None)
+        res = s.search_batch(qs.queries, limit=2500)
+        assert_batch_parity(o, qs.queries, res, 2500)
+        page = s.search_page(qs.queries[0], 3, 10)
+        top, total = o.search(qs.queries[0], limit=30)
+        assert page.total == total and len(page) == total and page.offset == 20 and page.pagelen == 10
+        assert [h.docnum for h in page] == [d for _, d in top[20:30]]
+
+
+def test_two_fields_boosts_per_field_B():
+    ix = make_corpus(3000, 2000, 123, (TITLE, BODY), device="cpu")
+    qs = make_queries(300, 2000, 321, 1, 3, "mixed", fields=("title", "body"), field_boosts=(2.0, 1.0), skip_top=0)
+    w = BM25F(B=0.6, K1=1.5, title_B=0.2)
+    o = NumpyOracle(ix, B=0.6, K1=1.5, field_B={"title": 0.2})
+    with ix.searcher(weighting=w, tile_docs=512) as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+def test_deleted_zero_bytes_and_ties():
+    ix = make_corpus(5000, 300, 99, device="cpu")
+    rng = np.random.default_rng(0)
+    ix.deleted = (rng.random(ix.n_docs_all) < 0.2).astype(np.uint8)
+    ix.len_bytes[0, rng.random(ix.n_docs_all) < 0.1] = 0            # W5: scored with fl = 1
+    ix.tfs[:] = 1.0                                                  # many exact score ties
+    o = NumpyOracle(ix)
+    qs = make_queries(200, 300, 11, 1, 4, "mixed", skip_top=0)
+    with ix.searcher(tile_docs=1024) as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+def test_float_weights_use_unpacked_payload():
+    ix = make_corpus(2000, 500, 5, device="cpu")
+    ix.tfs *= 1.5                                                    # non-integral posting weights (field boost)
+    o = NumpyOracle(ix)
+    qs = make_queries(100, 500, 3, 1, 3, "mixed", skip_top=0)
+    with ix.searcher() as s:
+        assert s.engine.stats()["packed_payload"] == 0
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+
+
+def test_leaf_boosts_zero_and_negative(cfg1):
+    ix, o = cfg1
+    qs = [Or([Term("body", 60, boost=0.0), Term("body", 70)]),
+          Or([Term("body", 60, boost=-1.0), Term("body", 70, boost=0.5)]),
+          And([Term("body", 55, boost=3.0), Term("body", 60)]),
+          Term("body", 52)]
+    with ix.searcher() as s:
+        res = s.search_batch(qs, limit=10)
+    assert_batch_parity(o, qs, res, 10)
+
+
+def test_sharded_equals_whole(cfg1):
+    """W8: shards with global statistics give the same scores; merged lists equal the whole."""
+    ix, o = cfg1
+    qs = make_queries(100, 50_000, 4, 2, 3, "mixed")
+    from document_search_engine_b200.searching import Searcher
+    tops = [[] for _ in qs.queries]
+    totals = [0] * len(qs.queries)
+    for g in range(3):
+        sh = ix.shard(g, 3)
+        s = Searcher(sh, stats_ix=ix)
+        for i, r in enumerate(s.search_batch(qs.queries, limit=10)):
+            tops[i].extend(r.top_n)
+            totals[i] += len(r)
+    for i, q in enumerate(qs.queries):
+        merged = sorted(tops[i], key=lambda t: (-t[0], t[1]))[:10]
+        assert_query_parity(o, q, merged, totals[i], 10, ctx="query %d" % i)
