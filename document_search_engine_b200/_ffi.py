@@ -88,7 +88,7 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bm25f_plan_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.bm25f_synchronize.argtypes = [vp]
-    lib.bm25f_set_stream.argtypes = [vp, vp]
+    lib.bm25f_set_stream.argtypes = [vp, vp, i32]
     lib.bm25f_plan_destroy.argtypes = [vp]
     lib.bm25f_plan_destroy.restype = None
     lib.bm25f_search_batch.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, vp, vp, vp, vp]
@@ -226,20 +226,24 @@ class Engine:
                                                      _ptr(counts), _ptr(totals)))
         return scores, docids, counts, totals
 
-    def merge_keys(self, d_keys: int, n_lists: int, n_queries: int, k: int, d_out: int, stream: int = 0):
-        _check(self.lib, self.lib.bm25f_merge_keys(self._h, d_keys, n_lists, n_queries, k, d_out, stream or None))
+    def merge_keys(self, d_keys: int, n_lists: int, n_queries: int, k: int, d_out: int):
+        """Runs on the handle's stream (see ``set_stream``)."""
+        _check(self.lib, self.lib.bm25f_merge_keys(self._h, d_keys, n_lists, n_queries, k, d_out, None))
 
-    def decode_keys(self, d_keys: int, n_queries: int, k: int, d_scores: int, d_docids: int, d_counts: int,
-                    stream: int = 0):
+    def decode_keys(self, d_keys: int, n_queries: int, k: int, d_scores: int, d_docids: int, d_counts: int):
         _check(self.lib, self.lib.bm25f_decode_keys(self._h, d_keys, n_queries, k, d_scores or None,
-                                                    d_docids or None, d_counts or None, stream or None))
+                                                    d_docids or None, d_counts or None, None))
 
     def synchronize(self):
         _check(self.lib, self.lib.bm25f_synchronize(self._h))
 
-    def set_stream(self, stream: int = 0):
-        """Launch on the given ``cudaStream_t`` (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
-        _check(self.lib, self.lib.bm25f_set_stream(self._h, stream or None))
+    def set_stream(self, stream: Optional[int]):
+        """Launch on the given ``cudaStream_t`` (e.g. ``torch.cuda.current_stream().cuda_stream``;
+        0 is the legacy default stream).  ``None`` restores the library's own stream."""
+        if stream is None:
+            _check(self.lib, self.lib.bm25f_set_stream(self._h, None, 1))
+        else:
+            _check(self.lib, self.lib.bm25f_set_stream(self._h, C.c_void_p(stream), 0))
 
     def stats(self) -> dict:
         s = Stats()

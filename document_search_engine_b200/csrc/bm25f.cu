@@ -367,7 +367,13 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
     // ---- tile epilogue: matches -> total, keys -> top-k buffer, reset touched slots --------
     const int ncand = *ncand_ctr;
     for (int j0 = 0; j0 < ncand; j0 += nt) {
-      if (budget < nt) budget = p.cap - prune_topk(keys, &s_nkeys, &s_thr, p.k);
+      if (budget < nt) {               // the bound is conservative: look at the real count first
+        __syncthreads();
+        int n = s_nkeys;
+        __syncthreads();
+        if (p.cap - n < nt) n = prune_topk(keys, &s_nkeys, &s_thr, p.k);
+        budget = p.cap - n;
+      }
       budget -= nt;
       const int j = j0 + tid;
       bool push = false;
@@ -1001,11 +1007,12 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   return 0;
 }
 
-int bm25f_set_stream(bm25f_handle* h, void* stream) {
+int bm25f_set_stream(bm25f_handle* h, void* stream, int use_own) {
   if (!h) return fail(BM25F_EINVAL, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
-  h->stream = stream ? static_cast<cudaStream_t>(stream) : h->own_stream;
+  // a NULL `stream` is a valid handle: the legacy default stream
+  h->stream = use_own ? h->own_stream : static_cast<cudaStream_t>(stream);
   return 0;
 }
 

@@ -108,14 +108,12 @@ class ShardedSearcher:
             dist.all_gather_into_tensor(b["gathered"], local_keys, group=self.group)
             b["totals"].copy_(local_totals)
             dist.all_reduce(b["totals"], op=dist.ReduceOp.SUM, group=self.group)
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            self.engine.merge_keys(b["gathered"].data_ptr(), self.world, Q, k, b["merged"].data_ptr(), stream)
+            self.engine.merge_keys(b["gathered"].data_ptr(), self.world, Q, k, b["merged"].data_ptr())
         else:
             b["merged"].copy_(local_keys)
             b["totals"].copy_(local_totals)
-        stream = torch.cuda.current_stream(self.device).cuda_stream
         self.engine.decode_keys(b["merged"].data_ptr(), Q, k, b["scores"].data_ptr(), b["docids"].data_ptr(),
-                                b["counts"].data_ptr(), stream)
+                                b["counts"].data_ptr())
         return b
 
     def search_packed(self, batch: _ffi.PackedBatch, k: int):

@@ -135,8 +135,9 @@ int  bm25f_fetch(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_t*
 int  bm25f_plan_device_results(bm25f_plan* plan, uint64_t** d_keys, uint64_t** d_totals);
 int  bm25f_synchronize(bm25f_handle* h);
 /* Launch on the caller's stream (a cudaStream_t; e.g. the host framework's current stream) so the
- * caller's events and collectives order with the library's kernels.  NULL restores the own stream. */
-int  bm25f_set_stream(bm25f_handle* h, void* stream);
+ * caller's events and collectives order with the library's kernels.  NULL is the legacy default
+ * stream.  use_own != 0 restores the library's own non-blocking stream. */
+int  bm25f_set_stream(bm25f_handle* h, void* stream, int use_own);
 void bm25f_plan_destroy(bm25f_plan* plan);
 
 /* prepare + execute + fetch */
@@ -145,7 +146,7 @@ int  bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* batch, int k, 
 
 /* Merge n_lists device-resident top-k key lists per query (layout [n_lists][n_queries][k], as an
  * all-gather of per-shard results produces) into d_out_keys [n_queries][k].  Runs on `stream`
- * (a cudaStream_t, or NULL for the handle's stream). */
+ * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
 /* Decode device keys to device arrays of scores / docids / counts (any may be NULL). */

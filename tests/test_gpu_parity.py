@@ -58,7 +58,7 @@ def test_config1_variants_groups(cfg1):
     assert_batch_parity(o, qs.queries, res, 10)
 
 
-@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (65536, 0)])
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (28672, 1 << 20)])
 def test_tiling_and_splitting(cfg1, tile_docs, split):
     """Tiny tiles and tiny work items: many tiles per query, many partial lists to merge."""
     ix, o = cfg1
