@@ -172,12 +172,23 @@ __global__ void k_tile_bounds(const LeafRec* __restrict__ leaves, uint32_t n_lea
 }
 
 // ------------------------------------------------------------------------------------------
-// Shared-memory bitonic sort (descending) of n = 2^m keys by all threads of the CTA
+// A "team" is the set of threads that cooperate on one work item: the whole CTA (barrier 0) in
+// k_score_topk, the consumer warps (named barrier 1) in k_score_pipe.
 // ------------------------------------------------------------------------------------------
-__device__ void bitonic_sort_desc(unsigned long long* a, int n) {
+struct Team {
+  int tid;   // rank inside the team
+  int nt;    // team size (multiple of 32)
+  int bar;   // hardware barrier id
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nt) : "memory");
+  }
+};
+
+// Shared-memory bitonic sort (descending) of n = 2^m keys by all threads of the team
+__device__ void bitonic_sort_desc(unsigned long long* a, int n, const Team& tm) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = tm.tid; i < n; i += tm.nt) {
         int x = i ^ j;
         if (x > i) {
           unsigned long long ai = a[i], ax = a[x];
@@ -185,7 +196,7 @@ __device__ void bitonic_sort_desc(unsigned long long* a, int n) {
           if (desc ? (ai < ax) : (ai > ax)) { a[i] = ax; a[x] = ai; }
         }
       }
-      __syncthreads();
+      tm.sync();
     }
   }
 }
@@ -197,17 +208,17 @@ __device__ __forceinline__ int next_pow2(int v) {
 }
 
 // Keep the k largest keys of keys[0..*nkeys) (sorted descending), update the admission threshold.
-// Must be called by all threads; contains barriers.  Returns the new key count (uniform).
-__device__ int prune_topk(unsigned long long* keys, int* nkeys, unsigned long long* thr, int k) {
-  __syncthreads();
+// Must be called by all threads of the team; contains barriers.  Returns the new count (uniform).
+__device__ int prune_topk(unsigned long long* keys, int* nkeys, unsigned long long* thr, int k, const Team& tm) {
+  tm.sync();
   const int n = *nkeys;
   if (n > 1) {
     const int np = next_pow2(n);
-    for (int i = n + threadIdx.x; i < np; i += blockDim.x) keys[i] = 0ull;
-    __syncthreads();
-    bitonic_sort_desc(keys, np);
-    if (threadIdx.x == 0 && n >= k) { *nkeys = k; *thr = keys[k - 1]; }
-    __syncthreads();
+    for (int i = n + tm.tid; i < np; i += tm.nt) keys[i] = 0ull;
+    tm.sync();
+    bitonic_sort_desc(keys, np, tm);
+    if (tm.tid == 0 && n >= k) { *nkeys = k; *thr = keys[k - 1]; }
+    tm.sync();
   }
   return min(n, k);
 }
@@ -259,6 +270,7 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
   const int warp = tid >> 5;
   const int nwarps = nt >> 5;
   const uint32_t S = p.S;
+  const Team tm{tid, nt, 0};
 
   // carve shared memory
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
         __syncthreads();
         int n = s_nkeys;
         __syncthreads();
-        if (p.cap - n < nt) n = prune_topk(keys, &s_nkeys, &s_thr, p.k);
+        if (p.cap - n < nt) n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
         budget = p.cap - n;
       }
       budget -= nt;
@@ -408,13 +420,319 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
   }
 
   // ---- item epilogue -------------------------------------------------------------------
-  const int n = prune_topk(keys, &s_nkeys, &s_thr, p.k);
+  const int n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
   unsigned long long* out = p.part_keys + (size_t)item.part * p.k;
   for (int i = tid; i < p.k; i += nt) out[i] = (i < n) ? keys[i] : 0ull;
   // match count of this item
   for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(0xFFFFFFFFu, my_total, o);
   if (lane == 0 && my_total) atomicAdd(&s_total, (unsigned long long)my_total);
   __syncthreads();
+  if (tid == 0 && s_total) atomicAdd(p.totals + item.q, s_total);
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy (TMA) primitives, sm_90+ PTX
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// The hot kernel, pipelined.  Same algorithm and data structures as k_score_topk, but DRAM
+// latency is decoupled from the per-leaf accumulate phases: the last warp of the CTA is a
+// PRODUCER that walks the item's static (tile, leaf, chunk) schedule ahead of the consumers and
+// stages posting chunks (docids + payload) into a ring of shared-memory stages with 1-D bulk
+// copies (cp.async.bulk, completion on an mbarrier per stage).  The CONSUMER warps wait on the
+// stage's "full" barrier, accumulate one posting per lane from shared memory, release the stage
+// on its "empty" barrier, and synchronise among themselves (named barrier 1) only where the
+// algorithm needs it: between two leaves of a tile and around the tile epilogue.
+// ------------------------------------------------------------------------------------------
+constexpr int PIPE_MAX_STAGES = 8;
+constexpr int PIPE_BROWS = 4;          // boundary rows kept by the producer
+constexpr uint32_t SF_LEAF_END = 1u, SF_TILE_END = 2u, SF_END = 4u;
+
+struct StageMeta {
+  uint32_t t0;      // first document of the tile
+  uint32_t n;       // postings staged (multiple of 16, includes alignment padding)
+  uint32_t vbeg;    // valid range inside the stage
+  uint32_t vend;
+  uint32_t leaf;
+  uint32_t flags;
+};
+
+struct PipeParams {
+  ScoreParams sp;
+  uint32_t chunk;       // postings per stage (multiple of 16)
+  uint32_t stages;      // ring depth (<= PIPE_MAX_STAGES)
+  uint32_t nf_smem;     // fields whose norm table is copied to shared memory (0: read from global)
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ScoreParams& p = pp.sp;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int NC = (int)blockDim.x - 32;          // consumer threads
+  const int producer_warp = NC >> 5;
+  const uint32_t S = p.S, CH = pp.chunk, NS = pp.stages;
+
+  // carve shared memory
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw);
+  float* acc = reinterpret_cast<float*>(keys + p.cap);
+  uint16_t* cand = reinterpret_cast<uint16_t*>(acc + S);
+  uint8_t* cnt = reinterpret_cast<uint8_t*>(cand + S);
+  uint32_t* sdoc = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)p.cap * 8 + (size_t)S * 7 + 15) & ~(size_t)15));
+  uint32_t* spay = sdoc + (size_t)NS * CH;
+  uint8_t* slb = reinterpret_cast<uint8_t*>(spay + (size_t)NS * CH);
+  float* snorm = reinterpret_cast<float*>(slb + (PACKED ? 0 : (size_t)NS * CH));
+  __shared__ LeafRec s_leaf[MAXL];
+  __shared__ uint32_t s_brow[PIPE_BROWS][MAXL];
+  __shared__ StageMeta s_meta[PIPE_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long s_full[PIPE_MAX_STAGES];
+  __shared__ __align__(8) unsigned long long s_empty[PIPE_MAX_STAGES];
+  __shared__ int s_ncand[2];
+  __shared__ int s_nkeys;
+  __shared__ unsigned long long s_thr;
+  __shared__ unsigned long long s_total;
+
+  const ItemRec item = p.items[blockIdx.x];
+  const QueryRec q = p.queries[item.q];
+  const int L = (int)q.n_leaves;
+  const int G = (int)q.n_groups;
+  const bool simple_or = (q.flags & QF_SIMPLE_OR) != 0;
+  const unsigned long long upper = q.after_key ? q.after_key : ~0ull;
+  const uint32_t* qbounds = p.bounds + (size_t)q.leaf_begin * (p.T + 1);
+
+  for (int i = tid; i < L; i += blockDim.x) s_leaf[i] = p.leaves[q.leaf_begin + i];
+  for (uint32_t i = tid; i < S; i += blockDim.x) { acc[i] = 0.0f; cnt[i] = 0; }
+  for (uint32_t i = tid; i < pp.nf_smem * 256u; i += blockDim.x) snorm[i] = p.norm[i];
+  if (tid == 0) {
+    s_ncand[0] = 0; s_ncand[1] = 0; s_nkeys = 0; s_thr = 0ull; s_total = 0ull;
+    for (uint32_t i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], (uint32_t)producer_warp); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == producer_warp) {
+    // =============================== PRODUCER ===============================================
+    // boundary rows tile_begin .. tile_begin + PIPE_BROWS - 1
+    for (int r = 0; r < PIPE_BROWS; ++r) {
+      const uint32_t row = item.tile_begin + r;
+      if (row <= p.T)
+        for (int l = lane; l < L; l += 32) s_brow[row % PIPE_BROWS][l] = qbounds[(size_t)row * L + l];
+    }
+    __syncwarp();
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t t = item.tile_begin; t < item.tile_end; ++t) {
+      if (t > item.tile_begin) {
+        // rows t and t + 1 are needed: at most the two youngest prefetch groups may be pending
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        __syncwarp();
+      }
+      const uint32_t* blo = s_brow[t % PIPE_BROWS];
+      const uint32_t* bhi = s_brow[(t + 1) % PIPE_BROWS];
+      if (lane == 0) {
+        // which leaves have postings in this tile; an AND with an empty group skips the tile
+        int last = -1;
+        bool skip = false;
+        uint32_t cur_g = 0;
+        bool g_has = false;
+        for (int l = 0; l < L; ++l) {
+          const uint32_t g = s_leaf[l].group;
+          if (g != cur_g) { if (!g_has) skip = true; cur_g = g; g_has = false; }
+          if (blo[l] < bhi[l]) { last = l; g_has = true; }
+        }
+        if (!g_has) skip = true;
+        if (simple_or) skip = (last < 0);
+        if (!skip) {
+          for (int l = 0; l <= last; ++l) {
+            const uint32_t lo = blo[l], hi = bhi[l];
+            if (lo >= hi) continue;
+            const unsigned long long a = s_leaf[l].off + lo, b = s_leaf[l].off + hi;
+            for (unsigned long long c0 = a & ~15ull; c0 < b; c0 += CH) {
+              unsigned long long rem = ((b - c0) + 15ull) & ~15ull;
+              const uint32_t n = (uint32_t)(rem < CH ? rem : CH);
+              mbar_wait(&s_empty[stage], phase ^ 1u);
+              StageMeta m;
+              m.t0 = t * S;
+              m.n = n;
+              m.vbeg = (uint32_t)(a > c0 ? a - c0 : 0);
+              m.vend = (uint32_t)(b < c0 + n ? b - c0 : n);
+              m.leaf = (uint32_t)l;
+              const bool last_chunk = (c0 + CH >= b);
+              m.flags = (last_chunk ? SF_LEAF_END : 0u) | ((last_chunk && l == last) ? SF_TILE_END : 0u);
+              s_meta[stage] = m;
+              mbar_arrive_expect_tx(&s_full[stage], n * (PACKED ? 8u : 9u));
+              bulk_g2s(sdoc + (size_t)stage * CH, p.docids + c0, n * 4u, &s_full[stage]);
+              bulk_g2s(spay + (size_t)stage * CH, p.payload + c0, n * 4u, &s_full[stage]);
+              if (!PACKED) bulk_g2s(slb + (size_t)stage * CH, p.lb + c0, n, &s_full[stage]);
+              if (++stage == NS) { stage = 0; phase ^= 1u; }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // prefetch row t + PIPE_BROWS into the slot row t occupied (only this warp reads the ring)
+      const uint32_t row = t + PIPE_BROWS;
+      if (row <= p.T)
+        for (int l = lane; l < L; l += 32) cp_async4(&s_brow[row % PIPE_BROWS][l], qbounds + (size_t)row * L + l);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    if (lane == 0) {
+      mbar_wait(&s_empty[stage], phase ^ 1u);
+      StageMeta m = {0u, 0u, 0u, 0u, 0u, SF_END};
+      s_meta[stage] = m;
+      mbar_arrive(&s_full[stage]);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    return;
+  }
+
+  // ================================= CONSUMERS ================================================
+  const Team tm{tid, NC, 1};
+  unsigned int my_total = 0;
+  int budget = p.cap;
+  uint32_t stage = 0, phase = 0, seq = 0;
+  for (;;) {
+    mbar_wait(&s_full[stage], phase);
+    const StageMeta m = s_meta[stage];
+    if (m.flags & SF_END) break;
+    {
+      const LeafRec lf = s_leaf[m.leaf];
+      const float w = lf.w;
+      const uint32_t g = lf.group;
+      const float* __restrict__ nrm = (pp.nf_smem ? snorm : p.norm) + lf.norm_off;
+      const uint32_t* __restrict__ sd = sdoc + (size_t)stage * CH;
+      const uint32_t* __restrict__ spl = spay + (size_t)stage * CH;
+      const uint8_t* __restrict__ sl = slb + (size_t)stage * CH;
+      int* ncand_ctr = &s_ncand[seq & 1u];
+      for (uint32_t i0 = (uint32_t)(warp * 32); i0 < m.n; i0 += (uint32_t)NC) {
+        const uint32_t i = i0 + lane;
+        const bool valid = (i >= m.vbeg) && (i < m.vend);
+        bool fresh = false;
+        uint32_t slot = 0;
+        if (valid) {
+          slot = sd[i] - m.t0;
+          const uint32_t pl = spl[i];
+          float tf;
+          uint32_t lb;
+          if (PACKED) { tf = (float)(pl >> 8); lb = pl & 255u; }
+          else { tf = __uint_as_float(pl); lb = sl[i]; }
+          const float s = __fdividef(w * tf, tf + nrm[lb]);
+          if (simple_or) {
+            const float old = acc[slot];
+            acc[slot] = old + s;
+            fresh = (old == 0.0f);
+          } else {
+            const uint32_t c = cnt[slot];
+            if (c == g) {
+              cnt[slot] = (uint8_t)(g + 1);
+              acc[slot] += s;
+              fresh = (g == 0);
+            } else if (c == g + 1) {
+              acc[slot] += s;
+            }
+          }
+        }
+        const unsigned mk = __ballot_sync(0xFFFFFFFFu, fresh);
+        if (mk) {
+          int b = 0;
+          const int leader = __ffs(mk) - 1;
+          if (lane == leader) b = atomicAdd(ncand_ctr, __popc(mk));
+          b = __shfl_sync(0xFFFFFFFFu, b, leader);
+          if (fresh) cand[b + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)slot;
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);       // this warp no longer reads the stage
+    if (++stage == NS) { stage = 0; phase ^= 1u; }
+    if (m.flags & SF_LEAF_END) tm.sync();               // the next leaf may touch the same slots
+    if (m.flags & SF_TILE_END) {
+      // ---- tile epilogue: matches -> total, keys -> top-k buffer, reset touched slots ----------
+      int* ncand_ctr = &s_ncand[seq & 1u];
+      const int ncand = *ncand_ctr;
+      for (int j0 = 0; j0 < ncand; j0 += NC) {
+        if (budget < NC) {
+          tm.sync();
+          int n = s_nkeys;
+          tm.sync();
+          if (p.cap - n < NC) n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
+          budget = p.cap - n;
+        }
+        budget -= NC;
+        const int j = j0 + tid;
+        bool push = false;
+        unsigned long long key = 0ull;
+        if (j < ncand) {
+          const uint32_t slot = cand[j];
+          const float sc = acc[slot];
+          acc[slot] = 0.0f;
+          bool match = true;
+          if (!simple_or) { match = (cnt[slot] == (uint8_t)G); cnt[slot] = 0; }
+          const uint32_t doc = m.t0 + slot;
+          if (match && p.deleted != nullptr && p.deleted[doc]) match = false;   // W9
+          if (match) {
+            ++my_total;
+            key = make_key(sc, p.doc_base + doc);
+            push = (key > s_thr) && (key < upper);
+          }
+        }
+        const unsigned mk = __ballot_sync(0xFFFFFFFFu, push);
+        if (mk) {
+          int b = 0;
+          const int leader = __ffs(mk) - 1;
+          if (lane == leader) b = atomicAdd(&s_nkeys, __popc(mk));
+          b = __shfl_sync(0xFFFFFFFFu, b, leader);
+          if (push) keys[b + __popc(mk & ((1u << lane) - 1u))] = key;
+        }
+      }
+      tm.sync();                          // end of tile: slots are clean
+      if (tid == 0) *ncand_ctr = 0;       // next used two tiles later, ordered by the next tile's barrier
+      budget = p.cap - s_nkeys;
+      ++seq;
+    }
+  }
+
+  // ---- item epilogue (consumers only; the producer warp has exited) ---------------------------
+  const int n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
+  unsigned long long* out = p.part_keys + (size_t)item.part * p.k;
+  for (int i = tid; i < p.k; i += NC) out[i] = (i < n) ? keys[i] : 0ull;
+  for (int o = 16; o > 0; o >>= 1) my_total += __shfl_down_sync(0xFFFFFFFFu, my_total, o);
+  if (lane == 0 && my_total) atomicAdd(&s_total, (unsigned long long)my_total);
+  tm.sync();
   if (tid == 0 && s_total) atomicAdd(p.totals + item.q, s_total);
 }
 
@@ -451,7 +769,7 @@ __global__ void k_merge_topk(const unsigned long long* __restrict__ keys_in, con
   for (int l = 1; l < n_lists; ++l) {
     for (int i = tid; i < kp; i += nt) buf[kp + i] = (i < k) ? keys_in[start + l * stride + i] : 0ull;
     __syncthreads();
-    bitonic_sort_desc(buf, 2 * kp);
+    bitonic_sort_desc(buf, 2 * kp, Team{tid, nt, 0});
     for (int i = k + tid; i < 2 * kp; i += nt) buf[i] = 0ull;
     __syncthreads();
   }
@@ -502,6 +820,9 @@ struct bm25f_handle {
   bool packed = true;
   bool have_weighting = false;
   uint32_t S = 8192, NT = 256, split = 1u << 16;
+  uint32_t variant = 0;               // 0: k_score_pipe (bulk-copy pipeline), 1: k_score_topk (direct loads)
+  uint32_t chunk = 512, stages = 4;   // pipeline geometry
+  uint32_t nf_smem = 0;
   int n_sms = 148;
   int ctas_per_sm = 0;
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
@@ -534,11 +855,20 @@ namespace {
 
 size_t score_smem_bytes(uint32_t S, int cap) { return (size_t)cap * 8 + (size_t)S * 7; }
 
+size_t pipe_smem_bytes(const bm25f_handle* h, int cap);
+
 int key_capacity(int k, int nt) {
   int need = k + 2 * nt;
   int cap = 1024;
   while (cap < need) cap <<= 1;
   return cap;
+}
+
+size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
+  size_t b = (score_smem_bytes(h->S, cap) + 15) & ~(size_t)15;
+  b += (size_t)h->stages * h->chunk * (h->packed ? 8 : 9);
+  b += (size_t)h->nf_smem * 256 * sizeof(float);
+  return b;
 }
 
 template <typename T>
@@ -633,7 +963,14 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->tile_docs) h->S = opts->tile_docs;
     if (opts->threads) h->NT = opts->threads;
     if (opts->split_postings) h->split = opts->split_postings;
+    if (opts->variant) h->variant = opts->variant - 1;
+    if (opts->chunk_postings) h->chunk = opts->chunk_postings;
+    if (opts->stages) h->stages = opts->stages;
   }
+  if (h->variant > 1) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (default), 1 (pipelined) or 2 (direct loads)"); }
+  if (h->chunk < 64 || (h->chunk & 15) || h->chunk > 8192) { delete h; return fail(BM25F_EINVAL, "chunk_postings must be a multiple of 16 in 64..8192"); }
+  if (h->stages < 2 || h->stages > (uint32_t)PIPE_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "stages must be 2..%d", PIPE_MAX_STAGES); }
+  h->nf_smem = desc->n_fields <= 4 ? desc->n_fields : 0;
   if (h->S < 256 || h->S > 65536 || (h->S & 3)) { delete h; return fail(BM25F_EINVAL, "tile_docs must be a multiple of 4 in 256..65536"); }
   if (h->NT < 64 || h->NT > 512 || (h->NT & 31)) { delete h; return fail(BM25F_EINVAL, "threads must be a multiple of 32 in 64..512"); }
   h->term_offsets.assign(desc->term_offsets, desc->term_offsets + desc->n_terms + 1);
@@ -731,13 +1068,16 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   free_tmp();
 
   // kernel attributes: opt in to the large dynamic shared memory carve-out once
-  const size_t smem_max = score_smem_bytes(h->S, key_capacity(BM25F_MAX_K, (int)h->NT));
+  const int cap_max = key_capacity(BM25F_MAX_K, (int)h->NT);
+  const size_t smem_max = h->variant == 0 ? pipe_smem_bytes(h, cap_max) : score_smem_bytes(h->S, cap_max);
   if (smem_max > (size_t)prop.sharedMemPerBlockOptin) {
     bm25f_destroy(h);
     return fail(BM25F_EINVAL, "tile_docs=%u needs %zu bytes of shared memory (> %zu)", h->S, smem_max, (size_t)prop.sharedMemPerBlockOptin);
   }
   CUH(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   CUH(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CUH(cudaFuncSetAttribute(k_score_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  CUH(cudaFuncSetAttribute(k_score_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
   h->stats.tile_docs = h->S;
   h->stats.threads = h->NT;
   h->stats.packed_payload = h->packed ? 1u : 0u;
@@ -903,7 +1243,7 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
-  p->smem_score = score_smem_bytes(S, p->cap);
+  p->smem_score = h->variant == 0 ? pipe_smem_bytes(h, p->cap) : score_smem_bytes(S, p->cap);
 
 #define RCP(x)                                    \
   do {                                            \
@@ -978,8 +1318,18 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.doc_base = (uint32_t)h->doc_base;
     sp.k = p->k;
     sp.cap = p->cap;
-    if (h->packed) k_score_topk<true><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
-    else k_score_topk<false><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
+    if (h->variant == 0) {
+      PipeParams pp;
+      pp.sp = sp;
+      pp.chunk = h->chunk;
+      pp.stages = h->stages;
+      pp.nf_smem = h->nf_smem;
+      if (h->packed) k_score_pipe<true><<<p->n_items, h->NT + 32, p->smem_score, st>>>(pp);
+      else k_score_pipe<false><<<p->n_items, h->NT + 32, p->smem_score, st>>>(pp);
+    } else {
+      if (h->packed) k_score_topk<true><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
+      else k_score_topk<false><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
+    }
     CU(cudaGetLastError());
     ++launches;
   }
@@ -999,8 +1349,13 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
-    if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<true>, (int)h->NT, p->smem_score);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<false>, (int)h->NT, p->smem_score);
+    if (h->variant == 0) {
+      if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);
+    } else {
+      if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<true>, (int)h->NT, p->smem_score);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_topk<false>, (int)h->NT, p->smem_score);
+    }
     h->ctas_per_sm = nb_;
     h->stats.ctas_per_sm = (uint32_t)nb_;
   }

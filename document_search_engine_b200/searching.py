@@ -188,7 +188,8 @@ class Searcher:
     """Whoosh-shaped searcher over a ``FlatIndex`` whose postings live in HBM."""
 
     def __init__(self, ix, weighting=None, device: int = 0, tile_docs: int = 0, threads: int = 0,
-                 split_postings: int = 0, stats_ix=None):
+                 split_postings: int = 0, stats_ix=None, variant: int = 0, chunk_postings: int = 0,
+                 stages: int = 0):
         self.ix = ix
         #: index the corpus statistics come from (the whole corpus when ``ix`` is a shard, W8)
         self.stats_ix = stats_ix or ix
@@ -197,11 +198,12 @@ class Searcher:
             raise NotImplementedError("only BM25F weightings run on the GPU path")
         self.device = device
         self.ixreader = self.stats_ix.reader()
-        key = (device, tile_docs, threads, split_postings)
+        key = (device, tile_docs, threads, split_postings, variant, chunk_postings, stages)
         eng = ix._engine_cache.get(key)
         if eng is None:
             eng = _ffi.Engine(ix, device=device, tile_docs=tile_docs, threads=threads,
-                              split_postings=split_postings)
+                              split_postings=split_postings, variant=variant,
+                              chunk_postings=chunk_postings, stages=stages)
             ix._engine_cache[key] = eng
         self.engine = eng
         wkey = self.weighting.key() + (self.stats_ix.doc_count_all(),)

@@ -80,7 +80,10 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t reserved[5];
+  uint32_t variant;              /* scoring kernel: 1 = bulk-copy pipeline (default), 2 = direct loads */
+  uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
+  uint32_t stages;               /* pipeline: ring depth (2..8) */
+  uint32_t reserved[2];
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

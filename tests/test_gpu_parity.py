@@ -41,11 +41,13 @@ def cfg1():
     return ix, NumpyOracle(ix)
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("mode", ["and", "or", "mixed"])
-def test_config1(cfg1, mode):
+def test_config1(cfg1, mode, variant):
+    """BASELINE configs[0] (and OR / mixed variations of it), both scoring kernels."""
     ix, o = cfg1
     qs = make_queries(1000, 50_000, 20261001, 2, 2 if mode == "and" else 4, mode)
-    with ix.searcher(weighting=BM25F) as s:
+    with ix.searcher(weighting=BM25F, variant=variant) as s:
         res = s.search_batch(qs.queries, limit=10)
     assert_batch_parity(o, qs.queries, res, 10)
 
@@ -58,12 +60,15 @@ def test_config1_variants_groups(cfg1):
     assert_batch_parity(o, qs.queries, res, 10)
 
 
-@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (28672, 1 << 20)])
-def test_tiling_and_splitting(cfg1, tile_docs, split):
-    """Tiny tiles and tiny work items: many tiles per query, many partial lists to merge."""
+@pytest.mark.parametrize("variant,chunk,stages", [(1, 64, 2), (1, 256, 8), (1, 2048, 3), (2, 0, 0)])
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (24576, 1 << 20)])
+def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
+    """Tiny tiles, tiny work items, tiny/huge pipeline stages: many tiles per query, chunks that
+    split posting sub-ranges, many partial lists to merge."""
     ix, o = cfg1
     qs = make_queries(200, 50_000, 77, 2, 4, "mixed", skip_top=0)       # includes the densest terms
-    with ix.searcher(tile_docs=tile_docs, split_postings=split) as s:
+    with ix.searcher(tile_docs=tile_docs, split_postings=split, variant=variant, chunk_postings=chunk,
+                     stages=stages) as s:
         res = s.search_batch(qs.queries, limit=10)
     assert_batch_parity(o, qs.queries, res, 10)
 
@@ -114,12 +119,13 @@ def test_deleted_zero_bytes_and_ties():
     assert_batch_parity(o, qs.queries, res, 10)
 
 
-def test_float_weights_use_unpacked_payload():
+@pytest.mark.parametrize("variant", [1, 2])
+def test_float_weights_use_unpacked_payload(variant):
     ix = make_corpus(2000, 500, 5, device="cpu")
     ix.tfs *= 1.5                                                    # non-integral posting weights (field boost)
     o = NumpyOracle(ix)
     qs = make_queries(100, 500, 3, 1, 3, "mixed", skip_top=0)
-    with ix.searcher() as s:
+    with ix.searcher(variant=variant, tile_docs=512) as s:
         assert s.engine.stats()["packed_payload"] == 0
         res = s.search_batch(qs.queries, limit=10)
     assert_batch_parity(o, qs.queries, res, 10)

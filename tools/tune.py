@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the hot path for several engine options on one GPU (development tool).
 
-Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split`` triple
+Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split[:variant:chunk:stages]`` tuple
 creates an engine, checks a query sample against the oracle, and times ``execute`` with the
 library's CUDA events.  Prints one JSON line per configuration.
 """
@@ -48,9 +48,11 @@ def main():
             qsets[m] = make_queries(nq, c["vocab"], 20261000 + args.config, c["min_terms"], c["max_terms"], m).queries
     k = c["k"]
     for opt in args.opts:
-        S, NT, split = (int(x) for x in opt.split(":"))
+        f = [int(x) for x in opt.split(":")] + [0] * 6
+        S, NT, split, variant, chunk, stages = f[:6]
         ix._engine_cache.clear()
-        s = Searcher(ix, weighting=BM25F, tile_docs=S, threads=NT, split_postings=split)
+        s = Searcher(ix, weighting=BM25F, tile_docs=S, threads=NT, split_postings=split, variant=variant,
+                     chunk_postings=chunk, stages=stages)
         eng = s.engine
         for m, queries in qsets.items():
             batch = s.pack(queries)
