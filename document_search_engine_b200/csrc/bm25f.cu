@@ -125,16 +125,19 @@ __global__ void k_check_tf(const float* __restrict__ tfs, unsigned long long n, 
   if (bad) atomicOr(flag, 1);
 }
 
-// payload[i] = (tf << 8) | len_byte[field][docid]   (packed)   or float bits of tf + separate byte
+// payload[i] = (tf << 8) | len_byte[field][docid]   (packed)   or float bits of tf + separate byte;
+// postings of deleted documents get tf = 0, which the scoring kernels skip
 __global__ void k_pack_postings(const uint32_t* __restrict__ docids, const float* __restrict__ tfs,
-                                const uint8_t* __restrict__ len_bytes_field, unsigned long long begin,
-                                unsigned long long end, int packed, uint32_t* __restrict__ payload,
-                                uint8_t* __restrict__ lb_out) {
+                                const uint8_t* __restrict__ len_bytes_field, const uint8_t* __restrict__ deleted,
+                                unsigned long long begin, unsigned long long end, int packed,
+                                uint32_t* __restrict__ payload, uint8_t* __restrict__ lb_out) {
   unsigned long long i = begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (; i < end; i += stride) {
-    uint32_t lb = len_bytes_field[docids[i]];
+    const uint32_t d = docids[i];
+    uint32_t lb = len_bytes_field[d];
     float t = tfs[i];
+    if (deleted != nullptr && deleted[d]) t = 0.0f;   // W9: the kernels skip tf == 0
     if (packed) {
       payload[i] = ((uint32_t)t << 8) | lb;
     } else {
@@ -347,7 +350,9 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
               if (PACKED) { tf = (float)(pl[e] >> 8); lb = pl[e] & 255u; }
               else { tf = __uint_as_float(pl[e]); lb = (lbs >> (8 * e)) & 255u; }
               const float s = __fdividef(w * tf, tf + __ldg(nrm + lb));
-              if (simple_or) {
+              if (!(tf > 0.0f)) {
+                // tf == 0 marks a posting of a deleted document (W9): not a match
+              } else if (simple_or) {
                 const float old = acc[slot];
                 acc[slot] = old + s;
                 fresh = (old == 0.0f);
@@ -397,7 +402,6 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
         bool match = true;
         if (!simple_or) { match = (cnt[slot] == (uint8_t)G); cnt[slot] = 0; }
         const uint32_t doc = t0 + slot;
-        if (match && p.deleted != nullptr && p.deleted[doc]) match = false;   // W9
         if (match) {
           ++my_total;
           key = make_key(sc, p.doc_base + doc);
@@ -479,14 +483,17 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // ------------------------------------------------------------------------------------------
 constexpr int PIPE_MAX_STAGES = 8;
 constexpr int PIPE_BROWS = 4;          // boundary rows kept by the producer
-constexpr uint32_t SF_LEAF_END = 1u, SF_TILE_END = 2u, SF_END = 4u;
+constexpr int HOTCAP = 512;            // per-tile list of documents whose score crossed the threshold
+constexpr uint32_t SF_LEAF_END = 1u, SF_TILE_END = 2u, SF_END = 4u, SF_LAST_GROUP = 8u;
 
-struct StageMeta {
-  uint32_t t0;      // first document of the tile
-  uint32_t n;       // postings staged (multiple of 16, includes alignment padding)
-  uint32_t vbeg;    // valid range inside the stage
+struct __align__(16) StageMeta {   // 32 B: two 128-bit shared loads
+  uint32_t t0;        // first document of the tile
+  uint32_t n;         // postings staged (multiple of 16, includes alignment padding)
+  uint32_t vbeg;      // valid range inside the stage
   uint32_t vend;
-  uint32_t leaf;
+  float w;            // leaf weight
+  uint32_t norm_off;  // field * 256
+  uint32_t group;     // leaf's group rank
   uint32_t flags;
 };
 
@@ -495,8 +502,17 @@ struct PipeParams {
   uint32_t chunk;       // postings per stage (multiple of 16)
   uint32_t stages;      // ring depth (<= PIPE_MAX_STAGES)
   uint32_t nf_smem;     // fields whose norm table is copied to shared memory (0: read from global)
+  uint32_t prune_at;    // sort + cut the key buffer when it holds this many keys
 };
 
+// Requires every leaf weight > 0 (scores only grow while a tile is accumulated); batches with a
+// non-positive weight are routed to k_score_topk by the host.
+//
+// Matches are COUNTED while accumulating (a slot's first hit for OR, the hit that completes the
+// last group for AND), so the tile epilogue does no per-candidate work beyond clearing the touched
+// slots.  A document is offered to the top-k buffer only if its running score crosses the current
+// k-th best score ("hot"); until k hits exist the threshold is the smallest positive float, every
+// match is hot, the hot list overflows and the epilogue falls back to walking all candidates.
 template <bool PACKED>
 __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -517,14 +533,17 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   uint32_t* spay = sdoc + (size_t)NS * CH;
   uint8_t* slb = reinterpret_cast<uint8_t*>(spay + (size_t)NS * CH);
   float* snorm = reinterpret_cast<float*>(slb + (PACKED ? 0 : (size_t)NS * CH));
+  uint16_t* hot = reinterpret_cast<uint16_t*>(snorm + (size_t)pp.nf_smem * 256);
   __shared__ LeafRec s_leaf[MAXL];
   __shared__ uint32_t s_brow[PIPE_BROWS][MAXL];
   __shared__ StageMeta s_meta[PIPE_MAX_STAGES];
   __shared__ __align__(8) unsigned long long s_full[PIPE_MAX_STAGES];
   __shared__ __align__(8) unsigned long long s_empty[PIPE_MAX_STAGES];
   __shared__ int s_ncand[2];
+  __shared__ int s_nhot[2];
   __shared__ int s_nkeys;
   __shared__ unsigned long long s_thr;
+  __shared__ float s_thr_score;
   __shared__ unsigned long long s_total;
 
   const ItemRec item = p.items[blockIdx.x];
@@ -539,7 +558,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   for (uint32_t i = tid; i < S; i += blockDim.x) { acc[i] = 0.0f; cnt[i] = 0; }
   for (uint32_t i = tid; i < pp.nf_smem * 256u; i += blockDim.x) snorm[i] = p.norm[i];
   if (tid == 0) {
-    s_ncand[0] = 0; s_ncand[1] = 0; s_nkeys = 0; s_thr = 0ull; s_total = 0ull;
+    s_ncand[0] = 0; s_ncand[1] = 0; s_nhot[0] = 0; s_nhot[1] = 0; s_nkeys = 0; s_thr = 0ull; s_total = 0ull;
+    s_thr_score = 1.17549435e-38f;    // FLT_MIN: every first hit crosses it
     for (uint32_t i = 0; i < NS; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], (uint32_t)producer_warp); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -547,7 +567,6 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
 
   if (warp == producer_warp) {
     // =============================== PRODUCER ===============================================
-    // boundary rows tile_begin .. tile_begin + PIPE_BROWS - 1
     for (int r = 0; r < PIPE_BROWS; ++r) {
       const uint32_t row = item.tile_begin + r;
       if (row <= p.T)
@@ -580,7 +599,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
           for (int l = 0; l <= last; ++l) {
             const uint32_t lo = blo[l], hi = bhi[l];
             if (lo >= hi) continue;
-            const unsigned long long a = s_leaf[l].off + lo, b = s_leaf[l].off + hi;
+            const LeafRec lf = s_leaf[l];
+            const unsigned long long a = lf.off + lo, b = lf.off + hi;
             for (unsigned long long c0 = a & ~15ull; c0 < b; c0 += CH) {
               unsigned long long rem = ((b - c0) + 15ull) & ~15ull;
               const uint32_t n = (uint32_t)(rem < CH ? rem : CH);
@@ -590,9 +610,12 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
               m.n = n;
               m.vbeg = (uint32_t)(a > c0 ? a - c0 : 0);
               m.vend = (uint32_t)(b < c0 + n ? b - c0 : n);
-              m.leaf = (uint32_t)l;
+              m.w = lf.w;
+              m.norm_off = lf.norm_off;
+              m.group = lf.group;
               const bool last_chunk = (c0 + CH >= b);
-              m.flags = (last_chunk ? SF_LEAF_END : 0u) | ((last_chunk && l == last) ? SF_TILE_END : 0u);
+              m.flags = (last_chunk ? SF_LEAF_END : 0u) | ((last_chunk && l == last) ? SF_TILE_END : 0u) |
+                        ((int)lf.group == G - 1 ? SF_LAST_GROUP : 0u);
               s_meta[stage] = m;
               mbar_arrive_expect_tx(&s_full[stage], n * (PACKED ? 8u : 9u));
               bulk_g2s(sdoc + (size_t)stage * CH, p.docids + c0, n * 4u, &s_full[stage]);
@@ -604,7 +627,6 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
         }
       }
       __syncwarp();
-      // prefetch row t + PIPE_BROWS into the slot row t occupied (only this warp reads the ring)
       const uint32_t row = t + PIPE_BROWS;
       if (row <= p.T)
         for (int l = lane; l < L; l += 32) cp_async4(&s_brow[row % PIPE_BROWS][l], qbounds + (size_t)row * L + l);
@@ -612,7 +634,7 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
     }
     if (lane == 0) {
       mbar_wait(&s_empty[stage], phase ^ 1u);
-      StageMeta m = {0u, 0u, 0u, 0u, 0u, SF_END};
+      StageMeta m = {0u, 0u, 0u, 0u, 0.0f, 0u, 0u, SF_END};
       s_meta[stage] = m;
       mbar_arrive(&s_full[stage]);
     }
@@ -623,56 +645,100 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   // ================================= CONSUMERS ================================================
   const Team tm{tid, NC, 1};
   unsigned int my_total = 0;
-  int budget = p.cap;
   uint32_t stage = 0, phase = 0, seq = 0;
   for (;;) {
     mbar_wait(&s_full[stage], phase);
     const StageMeta m = s_meta[stage];
     if (m.flags & SF_END) break;
     {
-      const LeafRec lf = s_leaf[m.leaf];
-      const float w = lf.w;
-      const uint32_t g = lf.group;
-      const float* __restrict__ nrm = (pp.nf_smem ? snorm : p.norm) + lf.norm_off;
+      const float w = m.w;
+      const float thr_s = s_thr_score;
+      const float* __restrict__ nrm = (pp.nf_smem ? snorm : p.norm) + m.norm_off;
       const uint32_t* __restrict__ sd = sdoc + (size_t)stage * CH;
       const uint32_t* __restrict__ spl = spay + (size_t)stage * CH;
       const uint8_t* __restrict__ sl = slb + (size_t)stage * CH;
       int* ncand_ctr = &s_ncand[seq & 1u];
-      for (uint32_t i0 = (uint32_t)(warp * 32); i0 < m.n; i0 += (uint32_t)NC) {
-        const uint32_t i = i0 + lane;
-        const bool valid = (i >= m.vbeg) && (i < m.vend);
-        bool fresh = false;
-        uint32_t slot = 0;
-        if (valid) {
-          slot = sd[i] - m.t0;
-          const uint32_t pl = spl[i];
-          float tf;
-          uint32_t lb;
-          if (PACKED) { tf = (float)(pl >> 8); lb = pl & 255u; }
-          else { tf = __uint_as_float(pl); lb = sl[i]; }
-          const float s = __fdividef(w * tf, tf + nrm[lb]);
-          if (simple_or) {
-            const float old = acc[slot];
-            acc[slot] = old + s;
-            fresh = (old == 0.0f);
-          } else {
-            const uint32_t c = cnt[slot];
-            if (c == g) {
-              cnt[slot] = (uint8_t)(g + 1);
-              acc[slot] += s;
-              fresh = (g == 0);
-            } else if (c == g + 1) {
-              acc[slot] += s;
+      int* nhot_ctr = &s_nhot[seq & 1u];
+      if (simple_or) {
+        for (uint32_t i0 = (uint32_t)(warp * 32); i0 < m.n; i0 += (uint32_t)NC) {
+          const uint32_t i = i0 + lane;
+          bool fresh = false;
+          uint32_t slot = 0;
+          if (i >= m.vbeg && i < m.vend) {
+            const uint32_t pl = spl[i];
+            float tf;
+            uint32_t lb;
+            if (PACKED) { tf = (float)(pl >> 8); lb = pl & 255u; }
+            else { tf = __uint_as_float(pl); lb = sl[i]; }
+            if (tf > 0.0f) {                                    // tf == 0 marks a deleted document (W9)
+              slot = sd[i] - m.t0;
+              const float s = __fdividef(w * tf, tf + nrm[lb]);
+              const float old = acc[slot];
+              const float nw = old + s;
+              acc[slot] = nw;
+              fresh = (old == 0.0f);
+              if (nw >= thr_s && old < thr_s) {
+                const int h = atomicAdd(nhot_ctr, 1);
+                if (h < HOTCAP) hot[h] = (uint16_t)slot;
+              }
             }
           }
+          const unsigned mk = __ballot_sync(0xFFFFFFFFu, fresh);
+          if (mk) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(ncand_ctr, __popc(mk));
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (fresh) cand[b + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)slot;
+            if (lane == 0) my_total += __popc(mk);              // a first hit is a match (OR)
+          }
         }
-        const unsigned mk = __ballot_sync(0xFFFFFFFFu, fresh);
-        if (mk) {
-          int b = 0;
-          const int leader = __ffs(mk) - 1;
-          if (lane == leader) b = atomicAdd(ncand_ctr, __popc(mk));
-          b = __shfl_sync(0xFFFFFFFFu, b, leader);
-          if (fresh) cand[b + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)slot;
+      } else {
+        const uint32_t g = m.group;
+        const bool last_group = (m.flags & SF_LAST_GROUP) != 0;
+        for (uint32_t i0 = (uint32_t)(warp * 32); i0 < m.n; i0 += (uint32_t)NC) {
+          const uint32_t i = i0 + lane;
+          bool fresh = false, matched = false;
+          uint32_t slot = 0;
+          if (i >= m.vbeg && i < m.vend) {
+            slot = sd[i] - m.t0;
+            const uint32_t c = cnt[slot];
+            if (c == g || c == g + 1) {                         // alive: earlier groups all matched
+              const uint32_t pl = spl[i];
+              float tf;
+              uint32_t lb;
+              if (PACKED) { tf = (float)(pl >> 8); lb = pl & 255u; }
+              else { tf = __uint_as_float(pl); lb = sl[i]; }
+              if (tf > 0.0f) {
+                const float s = __fdividef(w * tf, tf + nrm[lb]);
+                const float old = acc[slot];
+                const float nw = old + s;
+                acc[slot] = nw;
+                bool crossing = (nw >= thr_s);
+                if (c == g) {
+                  cnt[slot] = (uint8_t)(g + 1);
+                  fresh = (g == 0);
+                  matched = last_group;                         // this hit completes the last group
+                } else {
+                  crossing = crossing && (old < thr_s);
+                }
+                if (last_group && crossing) {
+                  const int h = atomicAdd(nhot_ctr, 1);
+                  if (h < HOTCAP) hot[h] = (uint16_t)slot;
+                }
+              }
+            }
+          }
+          const unsigned mk = __ballot_sync(0xFFFFFFFFu, fresh);
+          if (mk) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(ncand_ctr, __popc(mk));
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (fresh) cand[b + __popc(mk & ((1u << lane) - 1u))] = (uint16_t)slot;
+          }
+          if (last_group) {
+            const unsigned mm = __ballot_sync(0xFFFFFFFFu, matched);
+            if (lane == 0) my_total += __popc(mm);
+          }
         }
       }
     }
@@ -681,47 +747,71 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
     if (++stage == NS) { stage = 0; phase ^= 1u; }
     if (m.flags & SF_LEAF_END) tm.sync();               // the next leaf may touch the same slots
     if (m.flags & SF_TILE_END) {
-      // ---- tile epilogue: matches -> total, keys -> top-k buffer, reset touched slots ----------
+      // ---- tile epilogue ----------------------------------------------------------------------
       int* ncand_ctr = &s_ncand[seq & 1u];
+      int* nhot_ctr = &s_nhot[seq & 1u];
       const int ncand = *ncand_ctr;
-      for (int j0 = 0; j0 < ncand; j0 += NC) {
-        if (budget < NC) {
-          tm.sync();
-          int n = s_nkeys;
-          tm.sync();
-          if (p.cap - n < NC) n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
-          budget = p.cap - n;
-        }
-        budget -= NC;
-        const int j = j0 + tid;
-        bool push = false;
-        unsigned long long key = 0ull;
-        if (j < ncand) {
-          const uint32_t slot = cand[j];
-          const float sc = acc[slot];
-          acc[slot] = 0.0f;
-          bool match = true;
-          if (!simple_or) { match = (cnt[slot] == (uint8_t)G); cnt[slot] = 0; }
-          const uint32_t doc = m.t0 + slot;
-          if (match && p.deleted != nullptr && p.deleted[doc]) match = false;   // W9
-          if (match) {
-            ++my_total;
-            key = make_key(sc, p.doc_base + doc);
-            push = (key > s_thr) && (key < upper);
+      const int nhot = *nhot_ctr;
+      if (nhot > HOTCAP) {
+        // no (tight) threshold yet: walk every candidate, as k_score_topk does
+        int budget = p.cap - s_nkeys;
+        tm.sync();
+        for (int j0 = 0; j0 < ncand; j0 += NC) {
+          if (budget < NC) {
+            tm.sync();
+            int n = s_nkeys;
+            tm.sync();
+            if (p.cap - n < NC) n = prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
+            budget = p.cap - n;
+          }
+          budget -= NC;
+          const int j = j0 + tid;
+          bool push = false;
+          unsigned long long key = 0ull;
+          if (j < ncand) {
+            const uint32_t slot = cand[j];
+            const float sc = acc[slot];
+            acc[slot] = 0.0f;
+            bool match = true;
+            if (!simple_or) { match = (cnt[slot] == (uint8_t)G); cnt[slot] = 0; }
+            if (match) {
+              key = make_key(sc, p.doc_base + m.t0 + slot);
+              push = (key > s_thr) && (key < upper);
+            }
+          }
+          const unsigned mk = __ballot_sync(0xFFFFFFFFu, push);
+          if (mk) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&s_nkeys, __popc(mk));
+            b = __shfl_sync(0xFFFFFFFFu, b, 0);
+            if (push) keys[b + __popc(mk & ((1u << lane) - 1u))] = key;
           }
         }
-        const unsigned mk = __ballot_sync(0xFFFFFFFFu, push);
-        if (mk) {
-          int b = 0;
-          const int leader = __ffs(mk) - 1;
-          if (lane == leader) b = atomicAdd(&s_nkeys, __popc(mk));
-          b = __shfl_sync(0xFFFFFFFFu, b, leader);
-          if (push) keys[b + __popc(mk & ((1u << lane) - 1u))] = key;
+      } else {
+        if (nhot > 0) {
+          // the buffer always has room for HOTCAP more keys here (see the prune rule below)
+          for (int j = tid; j < nhot; j += NC) {
+            const uint32_t slot = hot[j];
+            const unsigned long long key = make_key(acc[slot], p.doc_base + m.t0 + slot);
+            if (key > s_thr && key < upper) keys[atomicAdd(&s_nkeys, 1)] = key;
+          }
+          tm.sync();                      // scores are read before the slots are cleared
+        }
+        if (simple_or) {
+          for (int j = tid; j < ncand; j += NC) acc[cand[j]] = 0.0f;
+        } else {
+          for (int j = tid; j < ncand; j += NC) { const uint32_t slot = cand[j]; acc[slot] = 0.0f; cnt[slot] = 0; }
         }
       }
       tm.sync();                          // end of tile: slots are clean
-      if (tid == 0) *ncand_ctr = 0;       // next used two tiles later, ordered by the next tile's barrier
-      budget = p.cap - s_nkeys;
+      if (tid == 0) { *ncand_ctr = 0; *nhot_ctr = 0; }    // next used two tiles later
+      // keep the threshold tight and the buffer small: sort + cut when enough keys piled up
+      const int nk = s_nkeys;
+      if (nk >= p.k && (nk >= (int)pp.prune_at || s_thr == 0ull)) {
+        prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
+        if (tid == 0) s_thr_score = key_score(s_thr);
+        tm.sync();                        // one threshold per tile for everybody (no double "crossing")
+      }
       ++seq;
     }
   }
@@ -849,6 +939,7 @@ struct bm25f_plan {
   uint32_t* d_docids = nullptr;
   uint32_t* d_counts = nullptr;
   size_t smem_score = 0;
+  bool simple_kernel = false;   // k_score_topk instead of k_score_pipe (option, or a non-positive leaf weight)
 };
 
 namespace {
@@ -868,7 +959,18 @@ size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
   size_t b = (score_smem_bytes(h->S, cap) + 15) & ~(size_t)15;
   b += (size_t)h->stages * h->chunk * (h->packed ? 8 : 9);
   b += (size_t)h->nf_smem * 256 * sizeof(float);
+  b += (size_t)HOTCAP * sizeof(uint16_t);
   return b;
+}
+
+int pipe_prune_at(int k) { return std::max(2 * k, 256); }
+
+// room for a full hot list on top of an unpruned buffer, and for the walk-all-candidates path
+int pipe_key_capacity(int k, int nc) {
+  int need = std::max(pipe_prune_at(k) + HOTCAP, k + 2 * nc);
+  int cap = 1024;
+  while (cap < need) cap <<= 1;
+  return cap;
 }
 
 template <typename T>
@@ -1058,7 +1160,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (e > b) {
       const uint64_t n = e - b;
       const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)h->n_sms * 16);
-      k_pack_postings<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_tfs, d_len + (size_t)f * h->n_docs, b, e,
+      k_pack_postings<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_tfs, d_len + (size_t)f * h->n_docs, h->d_deleted, b, e,
                                                       h->packed ? 1 : 0, h->d_payload, h->d_lb);
       CUT(cudaGetLastError());
     }
@@ -1069,15 +1171,19 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
 
   // kernel attributes: opt in to the large dynamic shared memory carve-out once
   const int cap_max = key_capacity(BM25F_MAX_K, (int)h->NT);
-  const size_t smem_max = h->variant == 0 ? pipe_smem_bytes(h, cap_max) : score_smem_bytes(h->S, cap_max);
+  const size_t smem_max = std::max(pipe_smem_bytes(h, pipe_key_capacity(BM25F_MAX_K, (int)h->NT)),
+                                   score_smem_bytes(h->S, cap_max));
   if (smem_max > (size_t)prop.sharedMemPerBlockOptin) {
     bm25f_destroy(h);
     return fail(BM25F_EINVAL, "tile_docs=%u needs %zu bytes of shared memory (> %zu)", h->S, smem_max, (size_t)prop.sharedMemPerBlockOptin);
   }
-  CUH(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CUH(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CUH(cudaFuncSetAttribute(k_score_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
-  CUH(cudaFuncSetAttribute(k_score_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+  // The attribute is per-function state shared by every handle in the process: always opt in to
+  // the device maximum so that engines with different tile sizes can coexist.
+  const int optin = (int)prop.sharedMemPerBlockOptin;
+  CUH(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUH(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUH(cudaFuncSetAttribute(k_score_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  CUH(cudaFuncSetAttribute(k_score_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
   h->stats.tile_docs = h->S;
   h->stats.threads = h->NT;
   h->stats.packed_payload = h->packed ? 1u : 0u;
@@ -1137,6 +1243,7 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   item_w.reserve(Q + Q / 4);
   uint64_t postings = 0;
   uint32_t n_parts = 0;
+  bool any_nonpos = false;
   uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
 
   for (uint32_t qi = 0; qi < Q; ++qi) {
@@ -1205,6 +1312,7 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     qr.n_leaves = nlq;
     qr.n_groups = G;
     qr.flags = (G == 1 && all_pos) ? QF_SIMPLE_OR : 0u;
+    if (!all_pos) any_nonpos = true;
     out_leaf += nlq;
     postings += P;
 
@@ -1237,13 +1345,14 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   p->k = k;
   p->kp = 1;
   while (p->kp < k) p->kp <<= 1;
-  p->cap = key_capacity(k, (int)h->NT);
+  p->simple_kernel = (h->variant != 0) || any_nonpos;
+  p->cap = p->simple_kernel ? key_capacity(k, (int)h->NT) : pipe_key_capacity(k, (int)h->NT);
   p->n_leaves = out_leaf;
   p->n_items = (uint32_t)sorted.size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
-  p->smem_score = h->variant == 0 ? pipe_smem_bytes(h, p->cap) : score_smem_bytes(S, p->cap);
+  p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
 
 #define RCP(x)                                    \
   do {                                            \
@@ -1318,12 +1427,13 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.doc_base = (uint32_t)h->doc_base;
     sp.k = p->k;
     sp.cap = p->cap;
-    if (h->variant == 0) {
+    if (!p->simple_kernel) {
       PipeParams pp;
       pp.sp = sp;
       pp.chunk = h->chunk;
       pp.stages = h->stages;
       pp.nf_smem = h->nf_smem;
+      pp.prune_at = (uint32_t)pipe_prune_at(p->k);
       if (h->packed) k_score_pipe<true><<<p->n_items, h->NT + 32, p->smem_score, st>>>(pp);
       else k_score_pipe<false><<<p->n_items, h->NT + 32, p->smem_score, st>>>(pp);
     } else {
