@@ -1180,10 +1180,20 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // The attribute is per-function state shared by every handle in the process: always opt in to
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
-  CUH(cudaFuncSetAttribute(k_score_topk<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUH(cudaFuncSetAttribute(k_score_topk<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUH(cudaFuncSetAttribute(k_score_pipe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
-  CUH(cudaFuncSetAttribute(k_score_pipe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin));
+  {
+    const void* fns[4] = {(const void*)k_score_topk<true>, (const void*)k_score_topk<false>,
+                          (const void*)k_score_pipe<true>, (const void*)k_score_pipe<false>};
+    for (const void* fn : fns) {
+      cudaFuncAttributes fa;
+      CUH(cudaFuncGetAttributes(&fa, fn));
+      CUH(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+      if (smem_max + fa.sharedSizeBytes > (size_t)optin) {
+        bm25f_destroy(h);
+        return fail(BM25F_EINVAL, "tile_docs=%u needs %zu bytes of shared memory (> %d)", h->S,
+                    smem_max + fa.sharedSizeBytes, optin);
+      }
+    }
+  }
   h->stats.tile_docs = h->S;
   h->stats.threads = h->NT;
   h->stats.packed_payload = h->packed ? 1u : 0u;
