@@ -262,6 +262,7 @@ struct ScoreParams {
   uint32_t doc_base;
   int k;
   int cap;                      // key buffer capacity (power of two)
+  unsigned long long* prof;     // BM25F_PROFILE builds: 16 cycle counters, else null
 };
 
 template <bool PACKED>
@@ -481,7 +482,19 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // on its "empty" barrier, and synchronise among themselves (named barrier 1) only where the
 // algorithm needs it: between two leaves of a tile and around the tile epilogue.
 // ------------------------------------------------------------------------------------------
-constexpr int PIPE_MAX_STAGES = 8;
+#ifdef BM25F_PROFILE
+#define PROF_DECL long long pt_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long pt0_ = 0
+#define PROF_T0() pt0_ = clock64()
+#define PROF_ADD(i) do { long long n_ = clock64(); pt_[i] += n_ - pt0_; pt0_ = n_; } while (0)
+#define PROF_FLUSH(base, on) do { if (on && p.prof) for (int i_ = 0; i_ < 8; ++i_) atomicAdd(p.prof + (base) + i_, (unsigned long long)pt_[i_]); } while (0)
+#else
+#define PROF_DECL
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_FLUSH(base, on)
+#endif
+
+constexpr int PIPE_MAX_STAGES = 32;
 constexpr int PIPE_BROWS = 4;          // boundary rows kept by the producer
 constexpr int HOTCAP = 512;            // per-tile list of documents whose score crossed the threshold
 constexpr uint32_t SF_LEAF_END = 1u, SF_TILE_END = 2u, SF_END = 4u, SF_LAST_GROUP = 8u;
@@ -573,6 +586,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
         for (int l = lane; l < L; l += 32) s_brow[row % PIPE_BROWS][l] = qbounds[(size_t)row * L + l];
     }
     __syncwarp();
+    PROF_DECL;
+    PROF_T0();
     uint32_t stage = 0, phase = 0;
     for (uint32_t t = item.tile_begin; t < item.tile_end; ++t) {
       if (t > item.tile_begin) {
@@ -580,6 +595,7 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
         asm volatile("cp.async.wait_group 2;" ::: "memory");
         __syncwarp();
       }
+      PROF_ADD(0);                        // [8] producer: boundary rows
       const uint32_t* blo = s_brow[t % PIPE_BROWS];
       const uint32_t* bhi = s_brow[(t + 1) % PIPE_BROWS];
       if (lane == 0) {
@@ -604,7 +620,9 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
             for (unsigned long long c0 = a & ~15ull; c0 < b; c0 += CH) {
               unsigned long long rem = ((b - c0) + 15ull) & ~15ull;
               const uint32_t n = (uint32_t)(rem < CH ? rem : CH);
+              PROF_ADD(1);                // [9] producer: schedule arithmetic
               mbar_wait(&s_empty[stage], phase ^ 1u);
+              PROF_ADD(2);                // [10] producer: wait for a free stage
               StageMeta m;
               m.t0 = t * S;
               m.n = n;
@@ -622,6 +640,7 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
               bulk_g2s(spay + (size_t)stage * CH, p.payload + c0, n * 4u, &s_full[stage]);
               if (!PACKED) bulk_g2s(slb + (size_t)stage * CH, p.lb + c0, n, &s_full[stage]);
               if (++stage == NS) { stage = 0; phase ^= 1u; }
+              PROF_ADD(3);                // [11] producer: meta + issue
             }
           }
         }
@@ -639,6 +658,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
       mbar_arrive(&s_full[stage]);
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    PROF_ADD(4);
+    PROF_FLUSH(8, lane == 0);
     return;
   }
 
@@ -646,8 +667,11 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   const Team tm{tid, NC, 1};
   unsigned int my_total = 0;
   uint32_t stage = 0, phase = 0, seq = 0;
+  PROF_DECL;
+  PROF_T0();
   for (;;) {
     mbar_wait(&s_full[stage], phase);
+    PROF_ADD(0);                          // [0] consumer: wait for a full stage
     const StageMeta m = s_meta[stage];
     if (m.flags & SF_END) break;
     {
@@ -745,7 +769,9 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
     __syncwarp();
     if (lane == 0) mbar_arrive(&s_empty[stage]);       // this warp no longer reads the stage
     if (++stage == NS) { stage = 0; phase ^= 1u; }
+    PROF_ADD(1);                                        // [1] consumer: accumulate
     if (m.flags & SF_LEAF_END) tm.sync();               // the next leaf may touch the same slots
+    PROF_ADD(2);                                        // [2] consumer: leaf barrier
     if (m.flags & SF_TILE_END) {
       // ---- tile epilogue ----------------------------------------------------------------------
       int* ncand_ctr = &s_ncand[seq & 1u];
@@ -811,8 +837,10 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
         prune_topk(keys, &s_nkeys, &s_thr, p.k, tm);
         if (tid == 0) s_thr_score = key_score(s_thr);
         tm.sync();                        // one threshold per tile for everybody (no double "crossing")
+        PROF_ADD(4);                      // [4] consumer: prune
       }
       ++seq;
+      PROF_ADD(3);                        // [3] consumer: tile epilogue
     }
   }
 
@@ -824,6 +852,221 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
   if (lane == 0 && my_total) atomicAdd(&s_total, (unsigned long long)my_total);
   tm.sync();
   if (tid == 0 && s_total) atomicAdd(p.totals + item.q, s_total);
+  PROF_ADD(5);                            // [5] consumer: item epilogue
+  PROF_FLUSH(0, tid == 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// The hot kernel, warp-stream form (default for k <= 32, <= 8 leaves per query, packed payload).
+//
+// Every WARP is an independent stream: it owns one work item = (query, document range) and
+// sweeps that range in sub-tiles of SW documents with warp-private state, so there are no CTA
+// barriers, no shared-memory atomics and 24-32 independent latency chains per SM.
+//
+//  * slots[SW] in shared memory, 8 bytes each: {generation << 8 | groups_matched, score f32}.
+//    A slot whose generation differs from the current sub-tile's is empty: nothing is ever
+//    zeroed and no list of touched slots is kept.
+//  * per leaf a WINDOW of 32 consecutive postings lives in registers (lane i holds posting
+//    base + i: coalesced 128-byte loads of docids and payload); the next window is loaded when
+//    the current one becomes active and lines further ahead are prefetched into L2, so a
+//    sub-tile only ever waits on registers.  Lists are sorted by docid, hence the lanes whose
+//    posting falls in the current sub-tile form one contiguous run.
+//  * matches are counted while accumulating (first hit of a slot for OR; the hit that completes
+//    the last group for AND).
+//  * top-k: lane i of the warp holds the i-th best 64-bit key.  A document is examined only when
+//    its running score crosses the k-th best score ("hot"); such documents are rare once k hits
+//    exist.  Until then every match is hot, the small hot list overflows and the warp scans its
+//    slots once.
+// ------------------------------------------------------------------------------------------
+constexpr int WARP_HOT = 64;            // hot-list entries per warp
+constexpr int WARP_PF_WINDOWS = 8;      // L2 prefetch distance, in 32-posting windows
+
+struct WarpParams {
+  ScoreParams sp;
+  uint32_t SW;            // documents per sub-tile (slots per warp)
+  uint32_t n_items;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// insert `key` into the warp's sorted top list (lane i = i-th best); all lanes call this
+__device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsigned long long key, int lane) {
+  const int pos = __popc(__ballot_sync(0xFFFFFFFFu, mine > key));
+  const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, mine, 1);
+  if (lane > pos) mine = up;
+  if (lane == pos) mine = key;
+}
+
+template <int LMAX>
+__global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ScoreParams& p = wp.sp;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const uint32_t SW = wp.SW;
+  const uint32_t item_idx = blockIdx.x * nwarps + warp;
+  if (item_idx >= wp.n_items) return;
+
+  uint2* slots = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * SW;
+  uint16_t* hot = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)nwarps * SW) + warp * WARP_HOT;
+  __shared__ LeafRec s_leaf[8][LMAX];
+
+  const ItemRec item = p.items[item_idx];
+  const QueryRec q = p.queries[item.q];
+  const int L = (int)q.n_leaves;
+  const uint32_t G = q.n_groups;
+  const bool simple_or = (q.flags & QF_SIMPLE_OR) != 0;
+  const unsigned long long upper = q.after_key ? q.after_key : ~0ull;
+  const uint32_t* qbounds = p.bounds + (size_t)q.leaf_begin * (p.T + 1);
+  const float* __restrict__ nrm_base = p.norm;
+
+  if (lane < L) s_leaf[warp][lane] = p.leaves[q.leaf_begin + lane];
+  for (uint32_t i = lane; i < SW; i += 32) slots[i] = make_uint2(0u, 0u);
+  __syncwarp();
+
+  // ---- per-leaf stream state (registers; all loops over leaves are fully unrolled) ----------
+  uint32_t cd[LMAX], cp[LMAX], nd[LMAX], np[LMAX];   // current / next window: docid, payload
+  uint32_t pos[LMAX], cons[LMAX], lend[LMAX];        // window start, lanes consumed, end (list-relative)
+  float lw[LMAX];
+#pragma unroll
+  for (int l = 0; l < LMAX; ++l) {
+    cd[l] = nd[l] = 0xFFFFFFFFu;
+    cp[l] = np[l] = 0u;
+    pos[l] = cons[l] = lend[l] = 0u;
+    lw[l] = 0.0f;
+    if (l < L) {
+      const LeafRec lf = s_leaf[warp][l];
+      pos[l] = qbounds[(size_t)item.tile_begin * L + l];
+      lend[l] = qbounds[(size_t)item.tile_end * L + l];
+      lw[l] = lf.w;
+      const uint32_t* dd = p.docids + lf.off;
+      const uint32_t* pd = p.payload + lf.off;
+      const uint32_t i0 = pos[l] + lane, i1 = i0 + 32;
+      if (i0 < lend[l]) { cd[l] = __ldg(dd + i0); cp[l] = __ldg(pd + i0); }
+      if (i1 < lend[l]) { nd[l] = __ldg(dd + i1); np[l] = __ldg(pd + i1); }
+    }
+  }
+
+  unsigned long long top = 0ull;            // lane i: i-th best key of this item so far
+  unsigned long long thr_key = 0ull;
+  float thr_s = 1.17549435e-38f;            // FLT_MIN until k hits exist: every first hit is hot
+  unsigned int tot = 0;
+  uint32_t gen = 0;
+  const uint32_t d_lo = item.tile_begin * p.S;
+  const uint32_t d_hi = min(item.tile_end * p.S, p.n_docs);
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (uint32_t sub_lo = d_lo; sub_lo < d_hi; sub_lo += SW) {
+    const uint32_t sub_hi = min(sub_lo + SW, d_hi);
+    ++gen;
+    int nhot = 0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+      if (l < L) {
+        for (;;) {
+          const bool act = (lane >= (int)cons[l]) && (cd[l] < sub_hi);
+          const unsigned mk = __ballot_sync(0xFFFFFFFFu, act);
+          if (mk == 0u) break;
+          bool ishot = false;
+          uint32_t slot = 0;
+          if (act) {
+            const uint32_t pl = cp[l];
+            if (pl >= 256u) {                                   // tf == 0 marks a deleted document (W9)
+              slot = cd[l] - sub_lo;
+              const float tf = (float)(pl >> 8);
+              const LeafRec& lf = s_leaf[warp][l];
+              const float s = __fdividef(lw[l] * tf, tf + __ldg(nrm_base + lf.norm_off + (pl & 255u)));
+              const uint2 v = slots[slot];
+              const bool live = (v.x >> 8) == gen;
+              const float old = live ? __uint_as_float(v.y) : 0.0f;
+              if (simple_or) {
+                const float nw = old + s;
+                slots[slot] = make_uint2((gen << 8) | 1u, __float_as_uint(nw));
+                tot += live ? 0u : 1u;                          // first hit of the slot: a match
+                ishot = (nw >= thr_s) && (old < thr_s);
+              } else {
+                const uint32_t g = lf.group;
+                const uint32_t c = live ? (v.x & 255u) : 0u;
+                if (c == g || c == g + 1u) {                    // alive: all earlier groups matched
+                  const float nw = old + s;
+                  slots[slot] = make_uint2((gen << 8) | (g + 1u), __float_as_uint(nw));
+                  if (g + 1u == G) {                            // last group
+                    if (c == g) { ++tot; ishot = (nw >= thr_s); }   // this hit completes the match
+                    else ishot = (nw >= thr_s) && (old < thr_s);
+                  }
+                }
+              }
+            }
+          }
+          const unsigned hk = __ballot_sync(0xFFFFFFFFu, ishot);
+          if (hk) {
+            const int at = nhot + __popc(hk & lt_mask);
+            if (ishot && at < WARP_HOT) hot[at] = (uint16_t)slot;
+            nhot += __popc(hk);
+          }
+          cons[l] += (uint32_t)__popc(mk);
+          if (cons[l] < 32u) break;
+          // window exhausted: rotate, fetch the window after next, prefetch further ahead
+          cd[l] = nd[l];
+          cp[l] = np[l];
+          pos[l] += 32u;
+          cons[l] = 0u;
+          const LeafRec& lf = s_leaf[warp][l];
+          const uint32_t* dd = p.docids + lf.off;
+          const uint32_t* pd = p.payload + lf.off;
+          const uint32_t i1 = pos[l] + 32u + lane;
+          nd[l] = 0xFFFFFFFFu;
+          np[l] = 0u;
+          if (i1 < lend[l]) { nd[l] = __ldg(dd + i1); np[l] = __ldg(pd + i1); }
+          const uint32_t ipf = pos[l] + 32u * WARP_PF_WINDOWS;
+          if (lane < 2 && ipf < lend[l]) prefetch_l2(lane == 0 ? (const void*)(dd + ipf) : (const void*)(pd + ipf));
+        }
+      }
+    }
+    // ---- sub-tile epilogue: only documents that crossed the threshold are looked at ----------
+    if (nhot > 0) {
+      __syncwarp();
+      const bool overflow = nhot > WARP_HOT;
+      const int n = overflow ? (int)(sub_hi - sub_lo) : nhot;
+      for (int j0 = 0; j0 < n; j0 += 32) {
+        const int j = j0 + lane;
+        bool push = false;
+        unsigned long long key = 0ull;
+        if (j < n) {
+          const uint32_t slot = overflow ? (uint32_t)j : (uint32_t)hot[j];
+          const uint2 v = slots[slot];
+          bool ok = (v.x >> 8) == gen;
+          if (!simple_or) ok = ok && ((v.x & 255u) == G);
+          const float sc = __uint_as_float(v.y);
+          if (ok && sc >= thr_s) {
+            key = make_key(sc, p.doc_base + sub_lo + slot);
+            push = (key > thr_key) && (key < upper);
+          }
+        }
+        unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
+        while (pm) {
+          const int src = __ffs(pm) - 1;
+          pm &= pm - 1u;
+          const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
+          if (bk > thr_key) {
+            warp_topk_insert(top, bk, lane);
+            thr_key = __shfl_sync(0xFFFFFFFFu, top, p.k - 1);
+          }
+        }
+      }
+      if (thr_key != 0ull) thr_s = key_score(thr_key);
+      __syncwarp();
+    }
+  }
+
+  // ---- item epilogue -----------------------------------------------------------------------
+  unsigned long long* out = p.part_keys + (size_t)item.part * p.k;
+  if (lane < p.k) out[lane] = top;
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
+  if (lane == 0 && tot) atomicAdd(p.totals + item.q, (unsigned long long)tot);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -910,7 +1153,8 @@ struct bm25f_handle {
   bool packed = true;
   bool have_weighting = false;
   uint32_t S = 8192, NT = 256, split = 1u << 16;
-  uint32_t variant = 0;               // 0: k_score_pipe (bulk-copy pipeline), 1: k_score_topk (direct loads)
+  uint32_t variant = 0;               // 0: auto (warp streams where eligible, else pipeline), 1: pipeline, 2: direct loads, 3: warp streams
+  uint32_t SW = 1024, wsplit = 1u << 15;   // warp-stream kernel: docs per sub-tile, target work per item
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
   uint32_t nf_smem = 0;
   int n_sms = 148;
@@ -921,11 +1165,15 @@ struct bm25f_handle {
   int ev_pending = 0;                  // slots recorded but not yet folded into the stats
   bm25f_stats stats{};
   uint64_t device_bytes = 0;
+  unsigned long long* d_prof = nullptr;   // BM25F_PROFILE builds only
 };
 
 struct bm25f_plan {
   bm25f_handle* h = nullptr;
   uint32_t Q = 0, n_leaves = 0, n_items = 0, n_parts = 0, T = 0;
+  uint32_t n_w4 = 0, n_w8 = 0;            // warp-stream items (<= 4 / <= 8 leaves); the rest are CTA items
+  ItemRec* d_items_w4 = nullptr;
+  ItemRec* d_items_w8 = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
   LeafRec* d_leaves = nullptr;
@@ -1020,6 +1268,7 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_lb);
   cudaFree(h->d_deleted);
   cudaFree(h->d_norm);
+  cudaFree(h->d_prof);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
@@ -1065,11 +1314,14 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->tile_docs) h->S = opts->tile_docs;
     if (opts->threads) h->NT = opts->threads;
     if (opts->split_postings) h->split = opts->split_postings;
-    if (opts->variant) h->variant = opts->variant - 1;
+    if (opts->variant) h->variant = opts->variant;
+    if (opts->subtile_docs) h->SW = opts->subtile_docs;
+    if (opts->warp_split) h->wsplit = opts->warp_split;
     if (opts->chunk_postings) h->chunk = opts->chunk_postings;
     if (opts->stages) h->stages = opts->stages;
   }
-  if (h->variant > 1) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (default), 1 (pipelined) or 2 (direct loads)"); }
+  if (h->variant > 3) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads) or 3 (warp streams)"); }
+  if (h->SW < 128 || h->SW > 8192 || (h->SW & 31)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 32 in 128..8192"); }
   if (h->chunk < 64 || (h->chunk & 15) || h->chunk > 8192) { delete h; return fail(BM25F_EINVAL, "chunk_postings must be a multiple of 16 in 64..8192"); }
   if (h->stages < 2 || h->stages > (uint32_t)PIPE_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "stages must be 2..%d", PIPE_MAX_STAGES); }
   h->nf_smem = desc->n_fields <= 4 ? desc->n_fields : 0;
@@ -1181,6 +1433,12 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
+    const void* wfns[2] = {(const void*)k_score_warp<4>, (const void*)k_score_warp<8>};
+    for (const void* fn : wfns) {
+      cudaFuncAttributes fa;
+      CUH(cudaFuncGetAttributes(&fa, fn));
+      CUH(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes));
+    }
     const void* fns[4] = {(const void*)k_score_topk<true>, (const void*)k_score_topk<false>,
                           (const void*)k_score_pipe<true>, (const void*)k_score_pipe<false>};
     for (const void* fn : fns) {
@@ -1194,6 +1452,10 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
       }
     }
   }
+#ifdef BM25F_PROFILE
+  CUH(cudaMalloc(reinterpret_cast<void**>(&h->d_prof), 16 * sizeof(unsigned long long)));
+  CUH(cudaMemset(h->d_prof, 0, 16 * sizeof(unsigned long long)));
+#endif
   h->stats.tile_docs = h->S;
   h->stats.threads = h->NT;
   h->stats.packed_payload = h->packed ? 1u : 0u;
@@ -1222,6 +1484,8 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_leaves);
   cudaFree(p->d_queries);
   cudaFree(p->d_items);
+  cudaFree(p->d_items_w4);
+  cudaFree(p->d_items_w8);
   cudaFree(p->d_bounds);
   cudaFree(p->d_part_keys);
   cudaFree(p->d_keys);
@@ -1247,10 +1511,8 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   const uint32_t T = (uint32_t)std::max<uint64_t>(1, (h->n_docs + S - 1) / S);
   std::vector<LeafRec> leaves(NL);
   std::vector<QueryRec> queries(Q);
-  std::vector<ItemRec> items;
-  std::vector<uint64_t> item_w;
-  items.reserve(Q + Q / 4);
-  item_w.reserve(Q + Q / 4);
+  std::vector<ItemRec> items[3];     // 0: warp streams, <= 4 leaves; 1: warp streams, <= 8; 2: CTA kernels
+  std::vector<uint64_t> item_w[3];
   uint64_t postings = 0;
   uint32_t n_parts = 0;
   bool any_nonpos = false;
@@ -1326,7 +1588,19 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     out_leaf += nlq;
     postings += P;
 
-    uint32_t nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (P + h->split / 2) / h->split));
+    // Route the query: warp-stream kernel when it is eligible (top list fits one warp, payload is
+    // packed, few enough leaves for register-resident windows), else the CTA-per-item kernels.
+    const bool warp_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && h->packed && nlq <= 8 && all_pos;
+    const int cls = warp_ok ? (nlq <= 4 ? 0 : 1) : 2;
+    uint32_t nsplit;
+    if (warp_ok) {
+      // cost model in posting-equivalents: every sub-tile costs a fixed amount even when empty
+      const uint64_t nsub = (h->n_docs + h->SW - 1) / h->SW;
+      const uint64_t work = P + 24ull * nsub * nlq / 3;
+      nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (work + h->wsplit / 2) / h->wsplit));
+    } else {
+      nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (P + h->split / 2) / h->split));
+    }
     qr.n_parts = nsplit;
     for (uint32_t s = 0; s < nsplit; ++s) {
       ItemRec it;
@@ -1334,19 +1608,22 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
       it.tile_begin = (uint32_t)((uint64_t)T * s / nsplit);
       it.tile_end = (uint32_t)((uint64_t)T * (s + 1) / nsplit);
       it.part = n_parts + s;
-      items.push_back(it);
-      item_w.push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
+      items[cls].push_back(it);
+      item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
     }
     n_parts += nsplit;
   }
   leaves.resize(out_leaf);
 
   // heaviest items first (longest-processing-time order for the block scheduler)
-  std::vector<uint32_t> perm(items.size());
-  for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
-  std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return item_w[x] > item_w[y]; });
-  std::vector<ItemRec> sorted(items.size());
-  for (uint32_t i = 0; i < perm.size(); ++i) sorted[i] = items[perm[i]];
+  std::vector<ItemRec> sorted[3];
+  for (int c = 0; c < 3; ++c) {
+    std::vector<uint32_t> perm(items[c].size());
+    for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return item_w[c][x] > item_w[c][y]; });
+    sorted[c].resize(perm.size());
+    for (uint32_t i = 0; i < perm.size(); ++i) sorted[c][i] = items[c][perm[i]];
+  }
 
   bm25f_plan* p = new (std::nothrow) bm25f_plan();
   if (!p) return fail(BM25F_ENOMEM, "host allocation failed");
@@ -1355,10 +1632,12 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   p->k = k;
   p->kp = 1;
   while (p->kp < k) p->kp <<= 1;
-  p->simple_kernel = (h->variant != 0) || any_nonpos;
+  p->simple_kernel = (h->variant == 2) || any_nonpos;
   p->cap = p->simple_kernel ? key_capacity(k, (int)h->NT) : pipe_key_capacity(k, (int)h->NT);
   p->n_leaves = out_leaf;
-  p->n_items = (uint32_t)sorted.size();
+  p->n_items = (uint32_t)sorted[2].size();
+  p->n_w4 = (uint32_t)sorted[0].size();
+  p->n_w8 = (uint32_t)sorted[1].size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
@@ -1381,7 +1660,9 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   const size_t n_bounds = (size_t)out_leaf * (T + 1);
   RCP(dev_alloc(&p->d_leaves, out_leaf));
   RCP(dev_alloc(&p->d_queries, Q));
-  RCP(dev_alloc(&p->d_items, sorted.size()));
+  RCP(dev_alloc(&p->d_items, sorted[2].size()));
+  RCP(dev_alloc(&p->d_items_w4, sorted[0].size()));
+  RCP(dev_alloc(&p->d_items_w8, sorted[1].size()));
   RCP(dev_alloc(&p->d_bounds, n_bounds));
   RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
   RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
@@ -1391,7 +1672,9 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   RCP(dev_alloc(&p->d_counts, Q));
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves.data(), out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries.data(), Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
-  if (!sorted.empty()) CUP(cudaMemcpyAsync(p->d_items, sorted.data(), sorted.size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
+  if (!sorted[2].empty()) CUP(cudaMemcpyAsync(p->d_items, sorted[2].data(), sorted[2].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
+  if (!sorted[0].empty()) CUP(cudaMemcpyAsync(p->d_items_w4, sorted[0].data(), sorted[0].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
+  if (!sorted[1].empty()) CUP(cudaMemcpyAsync(p->d_items_w8, sorted[1].data(), sorted[1].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
   CUP(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
   *out = p;
   return 0;
@@ -1418,7 +1701,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items) {
+  if (p->n_items || p->n_w4 || p->n_w8) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -1437,7 +1720,31 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.doc_base = (uint32_t)h->doc_base;
     sp.k = p->k;
     sp.cap = p->cap;
-    if (!p->simple_kernel) {
+    sp.prof = h->d_prof;
+    {
+      WarpParams wp;
+      wp.sp = sp;
+      wp.SW = h->SW;
+      const int nw = 8;
+      const size_t smem = (size_t)nw * h->SW * 8 + (size_t)nw * WARP_HOT * 2;
+      if (p->n_w4) {
+        wp.sp.items = p->d_items_w4;
+        wp.n_items = p->n_w4;
+        k_score_warp<4><<<(p->n_w4 + nw - 1) / nw, nw * 32, smem, st>>>(wp);
+        CU(cudaGetLastError());
+        ++launches;
+      }
+      if (p->n_w8) {
+        wp.sp.items = p->d_items_w8;
+        wp.n_items = p->n_w8;
+        k_score_warp<8><<<(p->n_w8 + nw - 1) / nw, nw * 32, smem, st>>>(wp);
+        CU(cudaGetLastError());
+        ++launches;
+      }
+    }
+    if (!p->n_items) {
+      // nothing for the CTA kernels
+    } else if (!p->simple_kernel) {
       PipeParams pp;
       pp.sp = sp;
       pp.chunk = h->chunk;
@@ -1450,8 +1757,10 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       if (h->packed) k_score_topk<true><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
       else k_score_topk<false><<<p->n_items, h->NT, p->smem_score, st>>>(sp);
     }
-    CU(cudaGetLastError());
-    ++launches;
+    if (p->n_items) {
+      CU(cudaGetLastError());
+      ++launches;
+    }
   }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q) {
@@ -1465,11 +1774,13 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
   h->stats.postings_touched = p->postings;
-  h->stats.n_items = p->n_items;
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
-    if (h->variant == 0) {
+    if (p->n_w4 || p->n_w8) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_warp<4>, 256, (size_t)8 * h->SW * 8 + 8 * WARP_HOT * 2);
+    } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);
     } else {
@@ -1565,6 +1876,19 @@ int bm25f_get_stats(bm25f_handle* h, bm25f_stats* out) {
 
 int bm25f_reset_stats(bm25f_handle* h) {
   if (!h) return fail(BM25F_EINVAL, "null handle");
+#ifdef BM25F_PROFILE
+  {
+    unsigned long long v[16];
+    cudaMemcpy(v, h->d_prof, sizeof v, cudaMemcpyDeviceToHost);
+    static const char* names[16] = {"c.wait_full", "c.accumulate", "c.leaf_barrier", "c.tile_epilogue", "c.prune",
+                                    "c.item_epilogue", "c6", "c7", "p.bound_rows", "p.schedule", "p.wait_empty",
+                                    "p.issue", "p.tail", "p13", "p14", "p15"};
+    fprintf(stderr, "[bm25f profile] cycles summed over CTAs (consumer thread 0 / producer lane 0):\n");
+    for (int i = 0; i < 16; ++i)
+      if (v[i]) fprintf(stderr, "  %-16s %14llu\n", names[i], v[i]);
+    cudaMemset(h->d_prof, 0, sizeof v);
+  }
+#endif
   h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = 0.0f;
   h->stats.n_executes = 0;
   return 0;

@@ -80,10 +80,13 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 1 = bulk-copy pipeline (default), 2 = direct loads */
+  uint32_t variant;              /* scoring kernel: 0 = auto (warp streams where eligible: k <= 32, <= 8 leaves,
+                                    integral weights; else the bulk-copy pipeline), 1 = bulk-copy pipeline,
+                                    2 = direct loads, 3 = same as 0 */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
-  uint32_t stages;               /* pipeline: ring depth (2..8) */
-  uint32_t reserved[2];
+  uint32_t stages;               /* pipeline: ring depth (2..32) */
+  uint32_t subtile_docs;         /* warp streams: documents per warp-private sub-tile (multiple of 32) */
+  uint32_t warp_split;           /* warp streams: target work (posting-equivalents) per warp item */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

@@ -41,7 +41,7 @@ def cfg1():
     return ix, NumpyOracle(ix)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 @pytest.mark.parametrize("mode", ["and", "or", "mixed"])
 def test_config1(cfg1, mode, variant):
     """BASELINE configs[0] (and OR / mixed variations of it), both scoring kernels."""
@@ -61,7 +61,7 @@ def test_config1_variants_groups(cfg1):
 
 
 @pytest.mark.parametrize("variant,chunk,stages", [(1, 64, 2), (1, 256, 8), (1, 2048, 3), (2, 0, 0)])
-@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (24576, 1 << 20)])
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (20480, 1 << 20)])
 def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
     """Tiny tiles, tiny work items, tiny/huge pipeline stages: many tiles per query, chunks that
     split posting sub-ranges, many partial lists to merge."""
@@ -71,6 +71,23 @@ def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
                      stages=stages) as s:
         res = s.search_batch(qs.queries, limit=10)
     assert_batch_parity(o, qs.queries, res, 10)
+
+
+@pytest.mark.parametrize("subtile,wsplit", [(128, 2048), (512, 0), (1024, 1 << 14), (4096, 1 << 20)])
+@pytest.mark.parametrize("mode", ["mixed", "variants"])
+def test_warp_streams(cfg1, subtile, wsplit, mode):
+    """Warp-stream kernel: sub-tile sizes, many small items per query, 8-leaf AND-of-OR queries."""
+    ix, o = cfg1
+    if mode == "variants":
+        qs = make_queries(150, 50_000, 31, 4, 4, "and", variants=True, skip_top=0)
+    else:
+        qs = make_queries(300, 50_000, 78, 1, 4, "mixed", skip_top=0)
+    with ix.searcher(variant=3, subtile_docs=subtile, warp_split=wsplit, tile_docs=1024) as s:
+        res = s.search_batch(qs.queries, limit=10)
+    assert_batch_parity(o, qs.queries, res, 10)
+    with ix.searcher(variant=3, subtile_docs=subtile, warp_split=wsplit, tile_docs=1024) as s:
+        res = s.search_batch(qs.queries[:60], limit=32)
+    assert_batch_parity(o, qs.queries[:60], res, 32)
 
 
 @pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])

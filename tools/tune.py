@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the hot path for several engine options on one GPU (development tool).
 
-Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split[:variant:chunk:stages]`` tuple
+Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split[:variant:chunk:stages:subtile:warp_split]`` tuple
 creates an engine, checks a query sample against the oracle, and times ``execute`` with the
 library's CUDA events.  Prints one JSON line per configuration.
 """
@@ -48,11 +48,11 @@ def main():
             qsets[m] = make_queries(nq, c["vocab"], 20261000 + args.config, c["min_terms"], c["max_terms"], m).queries
     k = c["k"]
     for opt in args.opts:
-        f = [int(x) for x in opt.split(":")] + [0] * 6
-        S, NT, split, variant, chunk, stages = f[:6]
+        f = [int(x) for x in opt.split(":")] + [0] * 8
+        S, NT, split, variant, chunk, stages, sw, wsplit = f[:8]
         ix._engine_cache.clear()
         s = Searcher(ix, weighting=BM25F, tile_docs=S, threads=NT, split_postings=split, variant=variant,
-                     chunk_postings=chunk, stages=stages)
+                     chunk_postings=chunk, stages=stages, subtile_docs=sw, warp_split=wsplit)
         eng = s.engine
         for m, queries in qsets.items():
             batch = s.pack(queries)
@@ -79,6 +79,7 @@ def main():
                               "ms_merge": st["ms_merge"] / n, "algo_GBs": gbs, "frac_6547": gbs / 6547.2,
                               "items": st["n_items"], "ctas_per_sm": st["ctas_per_sm"],
                               "postings": st["postings_touched"]}), flush=True)
+            eng.reset_stats()      # a BM25F_PROFILE build prints its phase timers here
             plan.close()
         eng.close()
 
