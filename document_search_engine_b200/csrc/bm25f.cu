@@ -879,16 +879,32 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
 //    slots once.
 // ------------------------------------------------------------------------------------------
 constexpr int WARP_HOT = 64;            // hot-list entries per warp
-constexpr int WARP_PF_WINDOWS = 8;      // L2 prefetch distance, in 32-posting windows
+constexpr int WARP_PF_WINDOWS = 12;     // L2 prefetch distance, in 32-posting windows
+constexpr int WARP_NW = 8;              // warps (independent streams) per CTA
+constexpr int WARP_NF = 4;              // norm tables held in shared memory
 
 struct WarpParams {
   ScoreParams sp;
   uint32_t SW;            // documents per sub-tile (slots per warp)
   uint32_t n_items;
+  uint32_t n_fields;
 };
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
 }
 
 // insert `key` into the warp's sorted top list (lane i = i-th best); all lanes call this
@@ -899,20 +915,25 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
   if (lane == pos) mine = key;
 }
 
+// Requires: k <= 32, <= LMAX leaves, packed payload, positive leaf weights, < 2^32 postings.
 template <int LMAX>
-__global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(WARP_NW * 32) k_score_warp(WarpParams wp) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];   // norm tables must be 256-byte aligned
   const ScoreParams& p = wp.sp;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
   const uint32_t SW = wp.SW;
-  const uint32_t item_idx = blockIdx.x * nwarps + warp;
-  if (item_idx >= wp.n_items) return;
+  const uint32_t item_idx = blockIdx.x * WARP_NW + warp;
 
+  // shared memory: [WARP_NW][SW] slots (8 B) | [WARP_NW][WARP_HOT] hot (2 B) | [n_fields][256] norm
   uint2* slots = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * SW;
-  uint16_t* hot = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)nwarps * SW) + warp * WARP_HOT;
-  __shared__ LeafRec s_leaf[8][LMAX];
+  uint16_t* hot = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)WARP_NW * SW) + warp * WARP_HOT;
+  float* snorm = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)WARP_NW * SW) + WARP_NW * WARP_HOT);
+  __shared__ LeafRec s_leaf[WARP_NW][LMAX];
+
+  for (uint32_t i = threadIdx.x; i < wp.n_fields * 256u; i += blockDim.x) snorm[i] = p.norm[i];
+  __syncthreads();                       // the only CTA-wide barrier: norm tables are shared
+  if (item_idx >= wp.n_items) return;
 
   const ItemRec item = p.items[item_idx];
   const QueryRec q = p.queries[item.q];
@@ -921,32 +942,38 @@ __global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
   const bool simple_or = (q.flags & QF_SIMPLE_OR) != 0;
   const unsigned long long upper = q.after_key ? q.after_key : ~0ull;
   const uint32_t* qbounds = p.bounds + (size_t)q.leaf_begin * (p.T + 1);
-  const float* __restrict__ nrm_base = p.norm;
+  const uint32_t* __restrict__ docids = p.docids;
+  const uint32_t* __restrict__ payload = p.payload;
 
   if (lane < L) s_leaf[warp][lane] = p.leaves[q.leaf_begin + lane];
   for (uint32_t i = lane; i < SW; i += 32) slots[i] = make_uint2(0u, 0u);
   __syncwarp();
+  const uint32_t slots_addr = smem_u32(slots);
+  const uint32_t snorm_addr = smem_u32(snorm);
 
   // ---- per-leaf stream state (registers; all loops over leaves are fully unrolled) ----------
   uint32_t cd[LMAX], cp[LMAX], nd[LMAX], np[LMAX];   // current / next window: docid, payload
-  uint32_t pos[LMAX], cons[LMAX], lend[LMAX];        // window start, lanes consumed, end (list-relative)
+  uint32_t idx[LMAX];     // absolute posting index of this lane's element of the current window
+  uint32_t endx[LMAX];    // absolute end of the leaf's postings inside the item's document range
+  uint32_t cons[LMAX];    // lanes of the current window already consumed
+  uint32_t ngrp[LMAX];    // shared-memory address of the field's norm table | group rank (low 8 bits)
   float lw[LMAX];
 #pragma unroll
   for (int l = 0; l < LMAX; ++l) {
     cd[l] = nd[l] = 0xFFFFFFFFu;
     cp[l] = np[l] = 0u;
-    pos[l] = cons[l] = lend[l] = 0u;
+    idx[l] = endx[l] = cons[l] = ngrp[l] = 0u;
     lw[l] = 0.0f;
     if (l < L) {
       const LeafRec lf = s_leaf[warp][l];
-      pos[l] = qbounds[(size_t)item.tile_begin * L + l];
-      lend[l] = qbounds[(size_t)item.tile_end * L + l];
+      const uint32_t base = (uint32_t)lf.off;
+      idx[l] = base + qbounds[(size_t)item.tile_begin * L + l] + lane;
+      endx[l] = base + qbounds[(size_t)item.tile_end * L + l];
       lw[l] = lf.w;
-      const uint32_t* dd = p.docids + lf.off;
-      const uint32_t* pd = p.payload + lf.off;
-      const uint32_t i0 = pos[l] + lane, i1 = i0 + 32;
-      if (i0 < lend[l]) { cd[l] = __ldg(dd + i0); cp[l] = __ldg(pd + i0); }
-      if (i1 < lend[l]) { nd[l] = __ldg(dd + i1); np[l] = __ldg(pd + i1); }
+      ngrp[l] = (snorm_addr + lf.norm_off * 4u) | lf.group;     // table is 1 KB aligned inside a 16 B aligned base: keep group in a separate byte
+      const uint32_t i1 = idx[l] + 32u;
+      if (idx[l] < endx[l]) { cd[l] = __ldg(docids + idx[l]); cp[l] = __ldg(payload + idx[l]); }
+      if (i1 < endx[l]) { nd[l] = __ldg(docids + i1); np[l] = __ldg(payload + i1); }
     }
   }
 
@@ -962,6 +989,8 @@ __global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
   for (uint32_t sub_lo = d_lo; sub_lo < d_hi; sub_lo += SW) {
     const uint32_t sub_hi = min(sub_lo + SW, d_hi);
     ++gen;
+    const uint32_t gtag = gen << 8;
+    const uint32_t sbase = slots_addr - sub_lo * 8u;       // slot address = sbase + docid * 8
     int nhot = 0;
 #pragma unroll
     for (int l = 0; l < LMAX; ++l) {
@@ -971,28 +1000,30 @@ __global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
           const unsigned mk = __ballot_sync(0xFFFFFFFFu, act);
           if (mk == 0u) break;
           bool ishot = false;
-          uint32_t slot = 0;
+          uint32_t sa = 0;
           if (act) {
             const uint32_t pl = cp[l];
             if (pl >= 256u) {                                   // tf == 0 marks a deleted document (W9)
-              slot = cd[l] - sub_lo;
+              sa = sbase + cd[l] * 8u;
+              const uint2 v = lds_v2(sa);
               const float tf = (float)(pl >> 8);
-              const LeafRec& lf = s_leaf[warp][l];
-              const float s = __fdividef(lw[l] * tf, tf + __ldg(nrm_base + lf.norm_off + (pl & 255u)));
-              const uint2 v = slots[slot];
-              const bool live = (v.x >> 8) == gen;
-              const float old = live ? __uint_as_float(v.y) : 0.0f;
+              const float nrm = lds_f32((ngrp[l] & ~255u) + (pl & 255u) * 4u);
+              const float s = __fdividef(lw[l] * tf, tf + nrm);
               if (simple_or) {
+                const bool live = (v.x == (gtag | 1u));
+                const float old = live ? __uint_as_float(v.y) : 0.0f;
                 const float nw = old + s;
-                slots[slot] = make_uint2((gen << 8) | 1u, __float_as_uint(nw));
+                sts_v2(sa, gtag | 1u, __float_as_uint(nw));
                 tot += live ? 0u : 1u;                          // first hit of the slot: a match
                 ishot = (nw >= thr_s) && (old < thr_s);
               } else {
-                const uint32_t g = lf.group;
+                const uint32_t g = ngrp[l] & 255u;
+                const bool live = (v.x >> 8) == gen;
                 const uint32_t c = live ? (v.x & 255u) : 0u;
                 if (c == g || c == g + 1u) {                    // alive: all earlier groups matched
+                  const float old = live ? __uint_as_float(v.y) : 0.0f;
                   const float nw = old + s;
-                  slots[slot] = make_uint2((gen << 8) | (g + 1u), __float_as_uint(nw));
+                  sts_v2(sa, gtag | (g + 1u), __float_as_uint(nw));
                   if (g + 1u == G) {                            // last group
                     if (c == g) { ++tot; ishot = (nw >= thr_s); }   // this hit completes the match
                     else ishot = (nw >= thr_s) && (old < thr_s);
@@ -1004,25 +1035,24 @@ __global__ void __launch_bounds__(256) k_score_warp(WarpParams wp) {
           const unsigned hk = __ballot_sync(0xFFFFFFFFu, ishot);
           if (hk) {
             const int at = nhot + __popc(hk & lt_mask);
-            if (ishot && at < WARP_HOT) hot[at] = (uint16_t)slot;
+            if (ishot && at < WARP_HOT) hot[at] = (uint16_t)((sa - slots_addr) >> 3);
             nhot += __popc(hk);
           }
           cons[l] += (uint32_t)__popc(mk);
           if (cons[l] < 32u) break;
-          // window exhausted: rotate, fetch the window after next, prefetch further ahead
+          // window exhausted: rotate, fetch the window after next, now and then prefetch far ahead
           cd[l] = nd[l];
           cp[l] = np[l];
-          pos[l] += 32u;
+          idx[l] += 32u;
           cons[l] = 0u;
-          const LeafRec& lf = s_leaf[warp][l];
-          const uint32_t* dd = p.docids + lf.off;
-          const uint32_t* pd = p.payload + lf.off;
-          const uint32_t i1 = pos[l] + 32u + lane;
+          const uint32_t i1 = idx[l] + 32u;
           nd[l] = 0xFFFFFFFFu;
           np[l] = 0u;
-          if (i1 < lend[l]) { nd[l] = __ldg(dd + i1); np[l] = __ldg(pd + i1); }
-          const uint32_t ipf = pos[l] + 32u * WARP_PF_WINDOWS;
-          if (lane < 2 && ipf < lend[l]) prefetch_l2(lane == 0 ? (const void*)(dd + ipf) : (const void*)(pd + ipf));
+          if (i1 < endx[l]) { nd[l] = __ldg(docids + i1); np[l] = __ldg(payload + i1); }
+          if (((idx[l] - lane) & 127u) == 0u) {                 // every 4th window: 4 lines of each array
+            const uint32_t ipf = idx[l] - lane + 32u * WARP_PF_WINDOWS + (lane & 3) * 32u;
+            if (lane < 8 && ipf < endx[l]) prefetch_l2((lane < 4 ? docids : payload) + ipf);
+          }
         }
       }
     }
@@ -1209,6 +1239,10 @@ size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
   b += (size_t)h->nf_smem * 256 * sizeof(float);
   b += (size_t)HOTCAP * sizeof(uint16_t);
   return b;
+}
+
+size_t warp_smem_bytes(const bm25f_handle* h) {
+  return (size_t)WARP_NW * h->SW * 8 + (size_t)WARP_NW * WARP_HOT * 2 + (size_t)h->n_fields * 256 * sizeof(float);
 }
 
 int pipe_prune_at(int k) { return std::max(2 * k, 256); }
@@ -1590,7 +1624,8 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
 
     // Route the query: warp-stream kernel when it is eligible (top list fits one warp, payload is
     // packed, few enough leaves for register-resident windows), else the CTA-per-item kernels.
-    const bool warp_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && h->packed && nlq <= 8 && all_pos;
+    const bool warp_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && h->packed && nlq <= 8 && all_pos &&
+                         h->n_fields <= (uint32_t)WARP_NF && h->n_postings < 0xFFFF0000ull;
     const int cls = warp_ok ? (nlq <= 4 ? 0 : 1) : 2;
     uint32_t nsplit;
     if (warp_ok) {
@@ -1725,8 +1760,9 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       WarpParams wp;
       wp.sp = sp;
       wp.SW = h->SW;
-      const int nw = 8;
-      const size_t smem = (size_t)nw * h->SW * 8 + (size_t)nw * WARP_HOT * 2;
+      wp.n_fields = h->n_fields;
+      const int nw = WARP_NW;
+      const size_t smem = warp_smem_bytes(h);
       if (p->n_w4) {
         wp.sp.items = p->d_items_w4;
         wp.n_items = p->n_w4;
@@ -1779,7 +1815,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
     if (p->n_w4 || p->n_w8) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_warp<4>, 256, (size_t)8 * h->SW * 8 + 8 * WARP_HOT * 2);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_warp<4>, WARP_NW * 32, warp_smem_bytes(h));
     } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);

@@ -73,7 +73,7 @@ def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
     assert_batch_parity(o, qs.queries, res, 10)
 
 
-@pytest.mark.parametrize("subtile,wsplit", [(128, 2048), (512, 0), (1024, 1 << 14), (4096, 1 << 20)])
+@pytest.mark.parametrize("subtile,wsplit", [(128, 2048), (512, 0), (1024, 1 << 14), (2048, 1 << 20)])
 @pytest.mark.parametrize("mode", ["mixed", "variants"])
 def test_warp_streams(cfg1, subtile, wsplit, mode):
     """Warp-stream kernel: sub-tile sizes, many small items per query, 8-leaf AND-of-OR queries."""

@@ -49,7 +49,7 @@ src = open(os.path.join(root, "document_search_engine_b200/csrc/bm25f.cu")).read
 for b in blocks:
     if kern not in b["name"]:
         continue
-    fn = [k for k in funcs if kern in k and ("Lb1" in k) == ("1>" in b["name"] or "(bool)1" in b["name"])]
+    fn = [k for k in funcs if kern in k and len(funcs[k]) == len(b["rows"])]
     fn = fn[0] if fn else [k for k in funcs if kern in k][0]
     lines = funcs[fn]
     hdr = b["hdr"]
