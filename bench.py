@@ -364,7 +364,7 @@ def main():
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "kernel": "k_score_topk", "kernel_ms_per_step": ms_score,
+                            "kernel": "k_score_warp", "kernel_ms_per_step": ms_score,
                             "algorithmic_bytes_per_step": BYTES_PER_POSTING * st["postings_touched"],
                             "frac_of_nominal_8000": achieved / 8000.0},
                "kernel_ms": {"bounds": st["ms_bounds"] / max(1, st["n_executes"]), "score": ms_score,

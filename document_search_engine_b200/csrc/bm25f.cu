@@ -1196,6 +1196,11 @@ struct bm25f_handle {
   bm25f_stats stats{};
   uint64_t device_bytes = 0;
   unsigned long long* d_prof = nullptr;   // BM25F_PROFILE builds only
+  // grow-only workspaces reused by bm25f_search_batch (no cudaMalloc / cudaFree per call)
+  unsigned char* d_arena = nullptr;
+  size_t d_arena_cap = 0;
+  unsigned char* h_arena = nullptr;       // pinned
+  size_t h_arena_cap = 0;
 };
 
 struct bm25f_plan {
@@ -1217,6 +1222,7 @@ struct bm25f_plan {
   uint32_t* d_docids = nullptr;
   uint32_t* d_counts = nullptr;
   size_t smem_score = 0;
+  bool owns_memory = true;      // false: buffers live in the handle's arena (bm25f_search_batch)
   bool simple_kernel = false;   // k_score_topk instead of k_score_pipe (option, or a non-positive leaf weight)
 };
 
@@ -1303,6 +1309,8 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_deleted);
   cudaFree(h->d_norm);
   cudaFree(h->d_prof);
+  cudaFree(h->d_arena);
+  if (h->h_arena) cudaFreeHost(h->h_arena);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
@@ -1514,12 +1522,11 @@ int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
 
 void bm25f_plan_destroy(bm25f_plan* p) {
   if (!p) return;
+  if (!p->owns_memory) { delete p; return; }
   if (p->h) cudaSetDevice(p->h->device);
   cudaFree(p->d_leaves);
   cudaFree(p->d_queries);
   cudaFree(p->d_items);
-  cudaFree(p->d_items_w4);
-  cudaFree(p->d_items_w8);
   cudaFree(p->d_bounds);
   cudaFree(p->d_part_keys);
   cudaFree(p->d_keys);
@@ -1530,7 +1537,31 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   delete p;
 }
 
-int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
+}  // extern "C" (reopened below)
+
+namespace {
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) & ~(a - 1); }
+
+// order items heaviest-first (longest-processing-time order for the block scheduler) with an O(n)
+// bucket pass: exact order inside a quarter-octave of weight does not matter
+void order_items(const std::vector<ItemRec>& items, const std::vector<uint64_t>& w, ItemRec* out) {
+  constexpr int NB = 256;
+  uint32_t count[NB + 1] = {0};
+  auto bucket = [](uint64_t x) {
+    if (x < 4) return (int)x;
+    const int lg = 63 - __builtin_clzll(x);
+    return std::min(NB - 1, lg * 4 + (int)((x >> (lg - 2)) & 3));
+  };
+  for (uint64_t x : w) ++count[NB - 1 - bucket(x)];
+  uint32_t sum = 0;
+  for (int i = 0; i < NB; ++i) { const uint32_t c = count[i]; count[i] = sum; sum += c; }
+  for (size_t i = 0; i < items.size(); ++i) out[count[NB - 1 - bucket(w[i])]++] = items[i];
+}
+
+// Host planning + upload.  With use_arena the plan's buffers live in the handle's grow-only
+// workspaces (pinned host staging, one device arena): no allocation on the hot path.
+int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out, bool use_arena) {
   if (!h || !b || !out) return fail(BM25F_EINVAL, "null argument");
   *out = nullptr;
   if (k < 1 || k > BM25F_MAX_K) return fail(BM25F_EINVAL, "k must be 1..%d", BM25F_MAX_K);
@@ -1543,14 +1574,43 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
 
   const uint32_t S = h->S;
   const uint32_t T = (uint32_t)std::max<uint64_t>(1, (h->n_docs + S - 1) / S);
-  std::vector<LeafRec> leaves(NL);
-  std::vector<QueryRec> queries(Q);
+
+  // pinned staging for the leaf and query records (upper bounds known up front)
+  const size_t hl_bytes = align_up((size_t)NL * sizeof(LeafRec)), hq_bytes = align_up((size_t)Q * sizeof(QueryRec));
+  std::vector<LeafRec> own_leaves;
+  std::vector<QueryRec> own_queries;
+  LeafRec* leaves;
+  QueryRec* queries;
+  if (use_arena) {
+    // items are appended after planning; reserve generously (grown below if needed)
+    const size_t want = hl_bytes + hq_bytes;
+    if (h->h_arena_cap < want + (1u << 20)) {
+      if (h->h_arena) cudaFreeHost(h->h_arena);
+      h->h_arena = nullptr;
+      h->h_arena_cap = 0;
+      const size_t cap = align_up((want + (1u << 20)) * 2, 1u << 20);
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_arena), cap, cudaHostAllocDefault);
+      if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e));
+      h->h_arena_cap = cap;
+    }
+    leaves = reinterpret_cast<LeafRec*>(h->h_arena);
+    queries = reinterpret_cast<QueryRec*>(h->h_arena + hl_bytes);
+  } else {
+    own_leaves.resize(NL);
+    own_queries.resize(Q);
+    leaves = own_leaves.data();
+    queries = own_queries.data();
+  }
+
   std::vector<ItemRec> items[3];     // 0: warp streams, <= 4 leaves; 1: warp streams, <= 8; 2: CTA kernels
   std::vector<uint64_t> item_w[3];
+  items[0].reserve(Q * 2);
+  item_w[0].reserve(Q * 2);
   uint64_t postings = 0;
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
+  const uint64_t nsub = (h->n_docs + h->SW - 1) / h->SW;
 
   for (uint32_t qi = 0; qi < Q; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -1567,8 +1627,9 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     if (G == 0 || nl == 0) continue;   // null query
 
     // per-group size; validates group ordering
-    uint64_t gsize[32] = {0};
-    bool gseen[32] = {false};
+    uint64_t gsize[32];
+    bool gseen[32];
+    for (uint32_t g = 0; g < G; ++g) { gsize[g] = 0; gseen[g] = false; }
     uint32_t prev_g = 0;
     bool all_pos = true;
     for (uint32_t i = a; i < e; ++i) {
@@ -1592,7 +1653,7 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     // smallest group first: it defines the candidate set, later groups only filter it
     uint32_t order[32], rank[32];
     for (uint32_t g = 0; g < G; ++g) order[g] = g;
-    std::stable_sort(order, order + G, [&](uint32_t x, uint32_t y) { return gsize[x] < gsize[y]; });
+    if (G > 1) std::stable_sort(order, order + G, [&](uint32_t x, uint32_t y) { return gsize[x] < gsize[y]; });
     for (uint32_t r = 0; r < G; ++r) rank[order[r]] = r;
     uint64_t P = 0;
     uint32_t nlq = 0;
@@ -1630,7 +1691,6 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     uint32_t nsplit;
     if (warp_ok) {
       // cost model in posting-equivalents: every sub-tile costs a fixed amount even when empty
-      const uint64_t nsub = (h->n_docs + h->SW - 1) / h->SW;
       const uint64_t work = P + 24ull * nsub * nlq / 3;
       nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (work + h->wsplit / 2) / h->wsplit));
     } else {
@@ -1648,17 +1708,6 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     }
     n_parts += nsplit;
   }
-  leaves.resize(out_leaf);
-
-  // heaviest items first (longest-processing-time order for the block scheduler)
-  std::vector<ItemRec> sorted[3];
-  for (int c = 0; c < 3; ++c) {
-    std::vector<uint32_t> perm(items[c].size());
-    for (uint32_t i = 0; i < perm.size(); ++i) perm[i] = i;
-    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t x, uint32_t y) { return item_w[c][x] > item_w[c][y]; });
-    sorted[c].resize(perm.size());
-    for (uint32_t i = 0; i < perm.size(); ++i) sorted[c][i] = items[c][perm[i]];
-  }
 
   bm25f_plan* p = new (std::nothrow) bm25f_plan();
   if (!p) return fail(BM25F_ENOMEM, "host allocation failed");
@@ -1670,13 +1719,14 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   p->simple_kernel = (h->variant == 2) || any_nonpos;
   p->cap = p->simple_kernel ? key_capacity(k, (int)h->NT) : pipe_key_capacity(k, (int)h->NT);
   p->n_leaves = out_leaf;
-  p->n_items = (uint32_t)sorted[2].size();
-  p->n_w4 = (uint32_t)sorted[0].size();
-  p->n_w8 = (uint32_t)sorted[1].size();
+  p->n_items = (uint32_t)items[2].size();
+  p->n_w4 = (uint32_t)items[0].size();
+  p->n_w8 = (uint32_t)items[1].size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
+  p->owns_memory = !use_arena;
 
 #define RCP(x)                                    \
   do {                                            \
@@ -1693,28 +1743,94 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
     }                                                                   \
   } while (0)
   const size_t n_bounds = (size_t)out_leaf * (T + 1);
-  RCP(dev_alloc(&p->d_leaves, out_leaf));
-  RCP(dev_alloc(&p->d_queries, Q));
-  RCP(dev_alloc(&p->d_items, sorted[2].size()));
-  RCP(dev_alloc(&p->d_items_w4, sorted[0].size()));
-  RCP(dev_alloc(&p->d_items_w8, sorted[1].size()));
-  RCP(dev_alloc(&p->d_bounds, n_bounds));
-  RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
-  RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-  RCP(dev_alloc(&p->d_totals, Q));
-  RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
-  RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
-  RCP(dev_alloc(&p->d_counts, Q));
-  if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves.data(), out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
-  if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries.data(), Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
-  if (!sorted[2].empty()) CUP(cudaMemcpyAsync(p->d_items, sorted[2].data(), sorted[2].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
-  if (!sorted[0].empty()) CUP(cudaMemcpyAsync(p->d_items_w4, sorted[0].data(), sorted[0].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
-  if (!sorted[1].empty()) CUP(cudaMemcpyAsync(p->d_items_w8, sorted[1].data(), sorted[1].size() * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
-  CUP(cudaStreamSynchronize(h->stream));   // the host vectors go out of scope
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8;
+  std::vector<ItemRec> own_items;
+  ItemRec* h_items;
+  if (use_arena) {
+    // the sorted item records follow the leaf / query records in the pinned arena
+    const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec));
+    if (need > h->h_arena_cap) {
+      unsigned char* bigger = nullptr;
+      const size_t cap = align_up(need * 2, 1u << 20);
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&bigger), cap, cudaHostAllocDefault);
+      if (e != cudaSuccess) { delete p; return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e)); }
+      memcpy(bigger, h->h_arena, hl_bytes + hq_bytes);
+      cudaFreeHost(h->h_arena);
+      h->h_arena = bigger;
+      h->h_arena_cap = cap;
+      leaves = reinterpret_cast<LeafRec*>(h->h_arena);
+      queries = reinterpret_cast<QueryRec*>(h->h_arena + hl_bytes);
+    }
+    h_items = reinterpret_cast<ItemRec*>(h->h_arena + hl_bytes + hq_bytes);
+  } else {
+    own_items.resize(n_it);
+    h_items = own_items.data();
+  }
+  // layout of the item array: [CTA items][warp <= 4 leaves][warp <= 8 leaves]
+  order_items(items[2], item_w[2], h_items);
+  order_items(items[0], item_w[0], h_items + p->n_items);
+  order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
+
+  if (use_arena) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
+    const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
+                 o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)Q * 8),
+                 o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4);
+    if (off > h->d_arena_cap) {
+      CUP(cudaStreamSynchronize(h->stream));
+      cudaFree(h->d_arena);
+      h->d_arena = nullptr;
+      h->d_arena_cap = 0;
+      const size_t cap = align_up(off + off / 2, 1u << 20);
+      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap);
+      if (e != cudaSuccess) { delete p; return fail(BM25F_ENOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e)); }
+      h->d_arena_cap = cap;
+    }
+    unsigned char* d = h->d_arena;
+    p->d_leaves = reinterpret_cast<LeafRec*>(d + o_leaves);
+    p->d_queries = reinterpret_cast<QueryRec*>(d + o_queries);
+    p->d_items = reinterpret_cast<ItemRec*>(d + o_items);
+    p->d_bounds = reinterpret_cast<uint32_t*>(d + o_bounds);
+    p->d_part_keys = reinterpret_cast<unsigned long long*>(d + o_part);
+    p->d_keys = reinterpret_cast<unsigned long long*>(d + o_keys);
+    p->d_totals = reinterpret_cast<unsigned long long*>(d + o_tot);
+    p->d_scores = reinterpret_cast<float*>(d + o_sc);
+    p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
+    p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
+  } else {
+    RCP(dev_alloc(&p->d_leaves, out_leaf));
+    RCP(dev_alloc(&p->d_queries, Q));
+    RCP(dev_alloc(&p->d_items, n_it));
+    RCP(dev_alloc(&p->d_bounds, n_bounds));
+    RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
+    RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
+    RCP(dev_alloc(&p->d_totals, Q));
+    RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
+    RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
+    RCP(dev_alloc(&p->d_counts, Q));
+  }
+  p->d_items_w4 = p->d_items + p->n_items;
+  p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
+  if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
+  if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
+  if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
+  // pageable sources must outlive the copy; the pinned arena is only rewritten by the next
+  // search_batch, which runs after this one has synchronised in bm25f_fetch
+  if (!use_arena) CUP(cudaStreamSynchronize(h->stream));
   *out = p;
   return 0;
 #undef RCP
 #undef CUP
+}
+
+}  // namespace
+
+extern "C" {
+
+int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
+  return prepare_impl(h, b, k, out, false);
 }
 
 int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
@@ -1867,7 +1983,7 @@ int bm25f_plan_device_results(bm25f_plan* p, uint64_t** d_keys, uint64_t** d_tot
 int bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* b, int k, float* out_scores, uint32_t* out_docids,
                        uint32_t* out_counts, uint64_t* out_totals) {
   bm25f_plan* p = nullptr;
-  int rc = bm25f_prepare(h, b, k, &p);
+  int rc = prepare_impl(h, b, k, &p, true);
   if (rc) return rc;
   rc = bm25f_execute(h, p);
   if (!rc) rc = bm25f_fetch(h, p, out_scores, out_docids, out_counts, out_totals);
