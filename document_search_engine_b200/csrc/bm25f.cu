@@ -147,6 +147,66 @@ __global__ void k_pack_postings(const uint32_t* __restrict__ docids, const float
   }
 }
 
+// pairs[i] = {docid, impact} with impact = tf / (tf + norm[lb]) for the postings [begin, end) of one
+// field (float64 divide, rounded once); refreshed whenever the weighting changes.
+// score = leaf weight * impact.
+__global__ void k_impacts(const uint32_t* __restrict__ docids, const uint32_t* __restrict__ payload, const uint8_t* __restrict__ lb,
+                          const float* __restrict__ norm_field, unsigned long long begin, unsigned long long end,
+                          int packed, uint2* __restrict__ pairs) {
+  unsigned long long i = begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (; i < end; i += stride) {
+    const uint32_t pl = payload[i];
+    double tf;
+    uint32_t b;
+    if (packed) { tf = (double)(pl >> 8); b = pl & 255u; }
+    else { tf = (double)__uint_as_float(pl); b = lb[i]; }
+    const float u = tf > 0.0 ? (float)(tf / (tf + (double)norm_field[b])) : 0.0f;
+    pairs[i] = make_uint2(docids[i], __float_as_uint(u));
+  }
+}
+
+// W9: postings of deleted documents never match.  They are removed from the device store at
+// upload (df / dc used for idf stay the stored ones: those are host-side statistics).
+__global__ void k_live_counts(const uint32_t* __restrict__ docids, const unsigned long long* __restrict__ offs,
+                              unsigned long long n_terms, const uint8_t* __restrict__ deleted, uint32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long t = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (; t < n_terms; t += stride) {
+    uint32_t c = 0;
+    for (unsigned long long i = offs[t] + lane; i < offs[t + 1]; i += 32) c += deleted[docids[i]] ? 0u : 1u;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+    if (lane == 0) counts[t] = c;
+  }
+}
+
+__global__ void k_compact_lists(const uint32_t* __restrict__ docids, const float* __restrict__ tfs,
+                                const unsigned long long* __restrict__ offs, const unsigned long long* __restrict__ new_offs,
+                                unsigned long long n_terms, const uint8_t* __restrict__ deleted,
+                                uint32_t* __restrict__ out_docids, float* __restrict__ out_tfs) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long t = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (; t < n_terms; t += stride) {
+    unsigned long long w = new_offs[t];
+    const unsigned long long e = offs[t + 1];
+    for (unsigned long long i0 = offs[t]; i0 < e; i0 += 32) {
+      const unsigned long long i = i0 + lane;
+      uint32_t d = 0;
+      bool keep = false;
+      if (i < e) { d = docids[i]; keep = !deleted[d]; }
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) {
+        const unsigned long long o = w + __popc(m & ((1u << lane) - 1u));
+        out_docids[o] = d;
+        out_tfs[o] = tfs[i];
+      }
+      w += __popc(m);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Tile boundaries: bounds[q][j][l] = first posting of leaf l with docid >= j * S
 // ------------------------------------------------------------------------------------------
@@ -857,45 +917,11 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
 }
 
 // ------------------------------------------------------------------------------------------
-// The hot kernel, warp-stream form (default for k <= 32, <= 8 leaves per query, packed payload).
-//
-// Every WARP is an independent stream: it owns one work item = (query, document range) and
-// sweeps that range in sub-tiles of SW documents with warp-private state, so there are no CTA
-// barriers, no shared-memory atomics and 24-32 independent latency chains per SM.
-//
-//  * slots[SW] in shared memory, 8 bytes each: {generation << 8 | groups_matched, score f32}.
-//    A slot whose generation differs from the current sub-tile's is empty: nothing is ever
-//    zeroed and no list of touched slots is kept.
-//  * per leaf a WINDOW of 32 consecutive postings lives in registers (lane i holds posting
-//    base + i: coalesced 128-byte loads of docids and payload); the next window is loaded when
-//    the current one becomes active and lines further ahead are prefetched into L2, so a
-//    sub-tile only ever waits on registers.  Lists are sorted by docid, hence the lanes whose
-//    posting falls in the current sub-tile form one contiguous run.
-//  * matches are counted while accumulating (first hit of a slot for OR; the hit that completes
-//    the last group for AND).
-//  * top-k: lane i of the warp holds the i-th best 64-bit key.  A document is examined only when
-//    its running score crosses the k-th best score ("hot"); such documents are rare once k hits
-//    exist.  Until then every match is hot, the small hot list overflows and the warp scans its
-//    slots once.
+// Warp-level helpers shared by the stream kernel
 // ------------------------------------------------------------------------------------------
-constexpr int WARP_HOT = 64;            // hot-list entries per warp
-constexpr int WARP_PF_WINDOWS = 12;     // L2 prefetch distance, in 32-posting windows
-constexpr int WARP_NW = 8;              // warps (independent streams) per CTA
-constexpr int WARP_NF = 4;              // norm tables held in shared memory
-
-struct WarpParams {
-  ScoreParams sp;
-  uint32_t SW;            // documents per sub-tile (slots per warp)
-  uint32_t n_items;
-  uint32_t n_fields;
-};
-
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 __device__ __forceinline__ uint2 lds_v2(uint32_t addr) {
   uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
   return v;
 }
 __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
@@ -903,7 +929,7 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
 }
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
   float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
 
@@ -915,189 +941,7 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
   if (lane == pos) mine = key;
 }
 
-// Requires: k <= 32, <= LMAX leaves, packed payload, positive leaf weights, < 2^32 postings.
-template <int LMAX>
-__global__ void __launch_bounds__(WARP_NW * 32) k_score_warp(WarpParams wp) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];   // norm tables must be 256-byte aligned
-  const ScoreParams& p = wp.sp;
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const uint32_t SW = wp.SW;
-  const uint32_t item_idx = blockIdx.x * WARP_NW + warp;
-
-  // shared memory: [WARP_NW][SW] slots (8 B) | [WARP_NW][WARP_HOT] hot (2 B) | [n_fields][256] norm
-  uint2* slots = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * SW;
-  uint16_t* hot = reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)WARP_NW * SW) + warp * WARP_HOT;
-  float* snorm = reinterpret_cast<float*>(reinterpret_cast<uint16_t*>(reinterpret_cast<uint2*>(smem_raw) + (size_t)WARP_NW * SW) + WARP_NW * WARP_HOT);
-  __shared__ LeafRec s_leaf[WARP_NW][LMAX];
-
-  for (uint32_t i = threadIdx.x; i < wp.n_fields * 256u; i += blockDim.x) snorm[i] = p.norm[i];
-  __syncthreads();                       // the only CTA-wide barrier: norm tables are shared
-  if (item_idx >= wp.n_items) return;
-
-  const ItemRec item = p.items[item_idx];
-  const QueryRec q = p.queries[item.q];
-  const int L = (int)q.n_leaves;
-  const uint32_t G = q.n_groups;
-  const bool simple_or = (q.flags & QF_SIMPLE_OR) != 0;
-  const unsigned long long upper = q.after_key ? q.after_key : ~0ull;
-  const uint32_t* qbounds = p.bounds + (size_t)q.leaf_begin * (p.T + 1);
-  const uint32_t* __restrict__ docids = p.docids;
-  const uint32_t* __restrict__ payload = p.payload;
-
-  if (lane < L) s_leaf[warp][lane] = p.leaves[q.leaf_begin + lane];
-  for (uint32_t i = lane; i < SW; i += 32) slots[i] = make_uint2(0u, 0u);
-  __syncwarp();
-  const uint32_t slots_addr = smem_u32(slots);
-  const uint32_t snorm_addr = smem_u32(snorm);
-
-  // ---- per-leaf stream state (registers; all loops over leaves are fully unrolled) ----------
-  uint32_t cd[LMAX], cp[LMAX], nd[LMAX], np[LMAX];   // current / next window: docid, payload
-  uint32_t idx[LMAX];     // absolute posting index of this lane's element of the current window
-  uint32_t endx[LMAX];    // absolute end of the leaf's postings inside the item's document range
-  uint32_t cons[LMAX];    // lanes of the current window already consumed
-  uint32_t ngrp[LMAX];    // shared-memory address of the field's norm table | group rank (low 8 bits)
-  float lw[LMAX];
-#pragma unroll
-  for (int l = 0; l < LMAX; ++l) {
-    cd[l] = nd[l] = 0xFFFFFFFFu;
-    cp[l] = np[l] = 0u;
-    idx[l] = endx[l] = cons[l] = ngrp[l] = 0u;
-    lw[l] = 0.0f;
-    if (l < L) {
-      const LeafRec lf = s_leaf[warp][l];
-      const uint32_t base = (uint32_t)lf.off;
-      idx[l] = base + qbounds[(size_t)item.tile_begin * L + l] + lane;
-      endx[l] = base + qbounds[(size_t)item.tile_end * L + l];
-      lw[l] = lf.w;
-      ngrp[l] = (snorm_addr + lf.norm_off * 4u) | lf.group;     // table is 1 KB aligned inside a 16 B aligned base: keep group in a separate byte
-      const uint32_t i1 = idx[l] + 32u;
-      if (idx[l] < endx[l]) { cd[l] = __ldg(docids + idx[l]); cp[l] = __ldg(payload + idx[l]); }
-      if (i1 < endx[l]) { nd[l] = __ldg(docids + i1); np[l] = __ldg(payload + i1); }
-    }
-  }
-
-  unsigned long long top = 0ull;            // lane i: i-th best key of this item so far
-  unsigned long long thr_key = 0ull;
-  float thr_s = 1.17549435e-38f;            // FLT_MIN until k hits exist: every first hit is hot
-  unsigned int tot = 0;
-  uint32_t gen = 0;
-  const uint32_t d_lo = item.tile_begin * p.S;
-  const uint32_t d_hi = min(item.tile_end * p.S, p.n_docs);
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  for (uint32_t sub_lo = d_lo; sub_lo < d_hi; sub_lo += SW) {
-    const uint32_t sub_hi = min(sub_lo + SW, d_hi);
-    ++gen;
-    const uint32_t gtag = gen << 8;
-    const uint32_t sbase = slots_addr - sub_lo * 8u;       // slot address = sbase + docid * 8
-    int nhot = 0;
-#pragma unroll
-    for (int l = 0; l < LMAX; ++l) {
-      if (l < L) {
-        for (;;) {
-          const bool act = (lane >= (int)cons[l]) && (cd[l] < sub_hi);
-          const unsigned mk = __ballot_sync(0xFFFFFFFFu, act);
-          if (mk == 0u) break;
-          bool ishot = false;
-          uint32_t sa = 0;
-          if (act) {
-            const uint32_t pl = cp[l];
-            if (pl >= 256u) {                                   // tf == 0 marks a deleted document (W9)
-              sa = sbase + cd[l] * 8u;
-              const uint2 v = lds_v2(sa);
-              const float tf = (float)(pl >> 8);
-              const float nrm = lds_f32((ngrp[l] & ~255u) + (pl & 255u) * 4u);
-              const float s = __fdividef(lw[l] * tf, tf + nrm);
-              if (simple_or) {
-                const bool live = (v.x == (gtag | 1u));
-                const float old = live ? __uint_as_float(v.y) : 0.0f;
-                const float nw = old + s;
-                sts_v2(sa, gtag | 1u, __float_as_uint(nw));
-                tot += live ? 0u : 1u;                          // first hit of the slot: a match
-                ishot = (nw >= thr_s) && (old < thr_s);
-              } else {
-                const uint32_t g = ngrp[l] & 255u;
-                const bool live = (v.x >> 8) == gen;
-                const uint32_t c = live ? (v.x & 255u) : 0u;
-                if (c == g || c == g + 1u) {                    // alive: all earlier groups matched
-                  const float old = live ? __uint_as_float(v.y) : 0.0f;
-                  const float nw = old + s;
-                  sts_v2(sa, gtag | (g + 1u), __float_as_uint(nw));
-                  if (g + 1u == G) {                            // last group
-                    if (c == g) { ++tot; ishot = (nw >= thr_s); }   // this hit completes the match
-                    else ishot = (nw >= thr_s) && (old < thr_s);
-                  }
-                }
-              }
-            }
-          }
-          const unsigned hk = __ballot_sync(0xFFFFFFFFu, ishot);
-          if (hk) {
-            const int at = nhot + __popc(hk & lt_mask);
-            if (ishot && at < WARP_HOT) hot[at] = (uint16_t)((sa - slots_addr) >> 3);
-            nhot += __popc(hk);
-          }
-          cons[l] += (uint32_t)__popc(mk);
-          if (cons[l] < 32u) break;
-          // window exhausted: rotate, fetch the window after next, now and then prefetch far ahead
-          cd[l] = nd[l];
-          cp[l] = np[l];
-          idx[l] += 32u;
-          cons[l] = 0u;
-          const uint32_t i1 = idx[l] + 32u;
-          nd[l] = 0xFFFFFFFFu;
-          np[l] = 0u;
-          if (i1 < endx[l]) { nd[l] = __ldg(docids + i1); np[l] = __ldg(payload + i1); }
-          if (((idx[l] - lane) & 127u) == 0u) {                 // every 4th window: 4 lines of each array
-            const uint32_t ipf = idx[l] - lane + 32u * WARP_PF_WINDOWS + (lane & 3) * 32u;
-            if (lane < 8 && ipf < endx[l]) prefetch_l2((lane < 4 ? docids : payload) + ipf);
-          }
-        }
-      }
-    }
-    // ---- sub-tile epilogue: only documents that crossed the threshold are looked at ----------
-    if (nhot > 0) {
-      __syncwarp();
-      const bool overflow = nhot > WARP_HOT;
-      const int n = overflow ? (int)(sub_hi - sub_lo) : nhot;
-      for (int j0 = 0; j0 < n; j0 += 32) {
-        const int j = j0 + lane;
-        bool push = false;
-        unsigned long long key = 0ull;
-        if (j < n) {
-          const uint32_t slot = overflow ? (uint32_t)j : (uint32_t)hot[j];
-          const uint2 v = slots[slot];
-          bool ok = (v.x >> 8) == gen;
-          if (!simple_or) ok = ok && ((v.x & 255u) == G);
-          const float sc = __uint_as_float(v.y);
-          if (ok && sc >= thr_s) {
-            key = make_key(sc, p.doc_base + sub_lo + slot);
-            push = (key > thr_key) && (key < upper);
-          }
-        }
-        unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
-        while (pm) {
-          const int src = __ffs(pm) - 1;
-          pm &= pm - 1u;
-          const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
-          if (bk > thr_key) {
-            warp_topk_insert(top, bk, lane);
-            thr_key = __shfl_sync(0xFFFFFFFFu, top, p.k - 1);
-          }
-        }
-      }
-      if (thr_key != 0ull) thr_s = key_score(thr_key);
-      __syncwarp();
-    }
-  }
-
-  // ---- item epilogue -----------------------------------------------------------------------
-  unsigned long long* out = p.part_keys + (size_t)item.part * p.k;
-  if (lane < p.k) out[lane] = top;
-  for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
-  if (lane == 0 && tot) atomicAdd(p.totals + item.q, (unsigned long long)tot);
-}
+#include "stream.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -1178,13 +1022,14 @@ struct bm25f_handle {
   uint32_t* d_docids = nullptr;
   uint32_t* d_payload = nullptr;
   uint8_t* d_lb = nullptr;
-  uint8_t* d_deleted = nullptr;
+  uint2* d_pairs = nullptr;           // {docid, tf / (tf + norm[lb]) under the current weighting}: the stream kernel's store
   float* d_norm = nullptr;
   bool packed = true;
   bool have_weighting = false;
   uint32_t S = 8192, NT = 256, split = 1u << 16;
-  uint32_t variant = 0;               // 0: auto (warp streams where eligible, else pipeline), 1: pipeline, 2: direct loads, 3: warp streams
-  uint32_t SW = 1024, wsplit = 1u << 15;   // warp-stream kernel: docs per sub-tile, target work per item
+  uint32_t variant = 0;               // 0 / 3: auto (stream kernel where eligible, else pipeline), 1: pipeline, 2: direct loads
+  // stream kernel: warps per CTA, accumulator bytes per warp, target work per item, L2 prefetch distance
+  uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 16, st_pf = 2048;
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
   uint32_t nf_smem = 0;
   int n_sms = 148;
@@ -1247,8 +1092,8 @@ size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
   return b;
 }
 
-size_t warp_smem_bytes(const bm25f_handle* h) {
-  return (size_t)WARP_NW * h->SW * 8 + (size_t)WARP_NW * WARP_HOT * 2 + (size_t)h->n_fields * 256 * sizeof(float);
+size_t stream_smem_bytes(uint32_t warps, uint32_t slot_bytes) {
+  return (size_t)warps * (slot_bytes + ST_MAX_LEAVES * 256 + ST_HOT * 2 + 4);
 }
 
 int pipe_prune_at(int k) { return std::max(2 * k, 256); }
@@ -1306,7 +1151,7 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_docids);
   cudaFree(h->d_payload);
   cudaFree(h->d_lb);
-  cudaFree(h->d_deleted);
+  cudaFree(h->d_pairs);
   cudaFree(h->d_norm);
   cudaFree(h->d_prof);
   cudaFree(h->d_arena);
@@ -1357,13 +1202,22 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->threads) h->NT = opts->threads;
     if (opts->split_postings) h->split = opts->split_postings;
     if (opts->variant) h->variant = opts->variant;
-    if (opts->subtile_docs) h->SW = opts->subtile_docs;
+    if (opts->subtile_docs) h->st_slot_bytes = opts->subtile_docs * 4u;
     if (opts->warp_split) h->wsplit = opts->warp_split;
     if (opts->chunk_postings) h->chunk = opts->chunk_postings;
     if (opts->stages) h->stages = opts->stages;
+    if (opts->stream_warps) h->st_warps = opts->stream_warps;
+    if (opts->prefetch_postings) h->st_pf = opts->prefetch_postings == 0xFFFFFFFFu ? 0u : opts->prefetch_postings;
   }
-  if (h->variant > 3) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads) or 3 (warp streams)"); }
-  if (h->SW < 128 || h->SW > 8192 || (h->SW & 31)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 32 in 128..8192"); }
+  if (h->variant > 3) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads) or 3 (same as 0)"); }
+  if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
+  if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
+  if (h->st_pf & (ST_PF_CHUNK - 1u)) { delete h; return fail(BM25F_EINVAL, "prefetch_postings must be a multiple of %u", ST_PF_CHUNK); }
+  if (stream_smem_bytes(h->st_warps, h->st_slot_bytes) > (size_t)prop.sharedMemPerBlockOptin) {
+    const size_t need = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
+    delete h;
+    return fail(BM25F_EINVAL, "stream_warps x subtile_docs needs %zu bytes of shared memory (> %zu)", need, (size_t)prop.sharedMemPerBlockOptin);
+  }
   if (h->chunk < 64 || (h->chunk & 15) || h->chunk > 8192) { delete h; return fail(BM25F_EINVAL, "chunk_postings must be a multiple of 16 in 64..8192"); }
   if (h->stages < 2 || h->stages > (uint32_t)PIPE_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "stages must be 2..%d", PIPE_MAX_STAGES); }
   h->nf_smem = desc->n_fields <= 4 ? desc->n_fields : 0;
@@ -1392,40 +1246,94 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   for (auto& set : h->ev)
     for (auto& e : set) CUH(cudaEventCreate(&e));
 
-  const uint64_t P = desc->n_postings;
-  const size_t pad = 256;   // vector loads may run past the last posting of the last list
-  RCH(dev_alloc(&h->d_docids, P + pad, h));
-  RCH(dev_alloc(&h->d_payload, P + pad, h));
-  CUH(cudaMemsetAsync(h->d_docids + P, 0xFF, pad * 4, h->stream));
-  CUH(cudaMemsetAsync(h->d_payload + P, 0, pad * 4, h->stream));
+  uint64_t P = desc->n_postings;
+  const size_t pad = 1024;   // rows / prefetch chunks may run past the last posting of the last list
   RCH(dev_alloc(&h->d_norm, (size_t)h->n_fields * 256, h));
-  if (desc->deleted) {
-    RCH(dev_alloc(&h->d_deleted, h->n_docs, h));
-    CUH(cudaMemcpyAsync(h->d_deleted, desc->deleted, h->n_docs, cudaMemcpyDefault, h->stream));
-  }
-  // temporaries for packing
+  // temporaries for compaction and packing
+  uint32_t* d_raw_docids = nullptr;
   float* d_tfs = nullptr;
   uint8_t* d_len = nullptr;
+  uint8_t* d_deleted = nullptr;
+  unsigned long long* d_offs = nullptr;
+  unsigned long long* d_new_offs = nullptr;
+  uint32_t* d_counts = nullptr;
   int* d_flag = nullptr;
-  RCH(dev_alloc(&d_tfs, P));
-  RCH(dev_alloc(&d_len, (size_t)h->n_fields * h->n_docs));
-  RCH(dev_alloc(&d_flag, 1));
-  auto free_tmp = [&]() { cudaFree(d_tfs); cudaFree(d_len); cudaFree(d_flag); };
+  auto free_tmp = [&]() {
+    cudaFree(d_raw_docids); cudaFree(d_tfs); cudaFree(d_len); cudaFree(d_deleted); cudaFree(d_offs);
+    cudaFree(d_new_offs); cudaFree(d_counts); cudaFree(d_flag);
+  };
 #define CUT(x)                                                          \
   do {                                                                  \
     cudaError_t e_ = (x);                                               \
     if (e_ != cudaSuccess) {                                            \
-      int rc_ = fail(BM25F_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+      int rc_ = fail(e_ == cudaErrorMemoryAllocation ? BM25F_ENOMEM : BM25F_ECUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
       free_tmp();                                                       \
       bm25f_destroy(h);                                                 \
       return rc_;                                                       \
     }                                                                   \
   } while (0)
+#define RCT(x)                       \
+  do {                               \
+    int rc_ = (x);                   \
+    if (rc_) { free_tmp(); bm25f_destroy(h); return rc_; } \
+  } while (0)
+  RCT(dev_alloc(&h->d_docids, P + pad, h));
+  RCT(dev_alloc(&d_tfs, P));
+  RCT(dev_alloc(&d_len, (size_t)h->n_fields * h->n_docs));
+  RCT(dev_alloc(&d_flag, 1));
   if (P) {
     CUT(cudaMemcpyAsync(h->d_docids, desc->docids, P * 4, cudaMemcpyDefault, h->stream));
     CUT(cudaMemcpyAsync(d_tfs, desc->tfs, P * 4, cudaMemcpyDefault, h->stream));
   }
   CUT(cudaMemcpyAsync(d_len, desc->len_bytes, (size_t)h->n_fields * h->n_docs, cudaMemcpyDefault, h->stream));
+
+  // ---- W9: drop the postings of deleted documents from the device store -----------------------
+  if (desc->deleted && P && h->n_terms) {
+    RCT(dev_alloc(&d_deleted, h->n_docs));
+    RCT(dev_alloc(&d_offs, h->n_terms + 1));
+    RCT(dev_alloc(&d_counts, h->n_terms));
+    CUT(cudaMemcpyAsync(d_deleted, desc->deleted, h->n_docs, cudaMemcpyDefault, h->stream));
+    static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "offset width");
+    CUT(cudaMemcpyAsync(d_offs, h->term_offsets.data(), (h->n_terms + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    const unsigned blocks = (unsigned)std::min<uint64_t>((h->n_terms + 7) / 8, (uint64_t)h->n_sms * 16);
+    k_live_counts<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_offs, h->n_terms, d_deleted, d_counts);
+    CUT(cudaGetLastError());
+    std::vector<uint32_t> counts(h->n_terms);
+    CUT(cudaMemcpyAsync(counts.data(), d_counts, h->n_terms * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUT(cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> new_offs(h->n_terms + 1);
+    new_offs[0] = 0;
+    for (uint64_t t = 0; t < h->n_terms; ++t) new_offs[t + 1] = new_offs[t] + counts[t];
+    const uint64_t P_live = new_offs[h->n_terms];
+    if (P_live != P) {
+      float* d_tfs2 = nullptr;
+      d_raw_docids = h->d_docids;
+      h->d_docids = nullptr;
+      h->device_bytes -= (P + pad) * 4;
+      RCT(dev_alloc(&h->d_docids, P_live + pad, h));
+      RCT(dev_alloc(&d_new_offs, h->n_terms + 1));
+      cudaError_t e2 = cudaMalloc(reinterpret_cast<void**>(&d_tfs2), std::max<uint64_t>(P_live, 1) * 4);
+      if (e2 != cudaSuccess) { free_tmp(); bm25f_destroy(h); return fail(BM25F_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e2)); }
+      cudaError_t e3 = cudaMemcpyAsync(d_new_offs, new_offs.data(), (h->n_terms + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+      if (e3 == cudaSuccess) {
+        k_compact_lists<<<blocks, 256, 0, h->stream>>>(d_raw_docids, d_tfs, d_offs, d_new_offs, h->n_terms, d_deleted, h->d_docids, d_tfs2);
+        e3 = cudaGetLastError();
+      }
+      if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(h->stream);
+      cudaFree(d_tfs);
+      d_tfs = d_tfs2;
+      if (e3 != cudaSuccess) { free_tmp(); bm25f_destroy(h); return fail(BM25F_ECUDA, "compaction: %s", cudaGetErrorString(e3)); }
+      h->term_offsets.swap(new_offs);
+      P = P_live;
+      h->n_postings = P;
+    }
+  }
+  RCT(dev_alloc(&h->d_payload, P + pad, h));
+  RCT(dev_alloc(&h->d_pairs, P + pad, h));
+  CUT(cudaMemsetAsync(h->d_docids + P, 0xFF, pad * 4, h->stream));
+  CUT(cudaMemsetAsync(h->d_payload + P, 0, pad * 4, h->stream));
+  CUT(cudaMemsetAsync(h->d_pairs + P, 0xFF, pad * 8, h->stream));
+
   CUT(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
   int flag = 0;
   if (P) {
@@ -1441,9 +1349,6 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     h->device_bytes += P + pad;
     CUT(cudaMemsetAsync(h->d_lb + P, 0, pad, h->stream));
   }
-  // docids of every posting must be inside the shard, or the gather below would fault
-  // (checked on the host for host inputs only when small; the kernel clamps nothing, so
-  //  validate with a cheap device reduction instead)
   // runs of consecutive posting lists that belong to the same field
   uint64_t t = 0;
   while (t < h->n_terms) {
@@ -1454,7 +1359,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (e > b) {
       const uint64_t n = e - b;
       const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)h->n_sms * 16);
-      k_pack_postings<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_tfs, d_len + (size_t)f * h->n_docs, h->d_deleted, b, e,
+      k_pack_postings<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_tfs, d_len + (size_t)f * h->n_docs, nullptr, b, e,
                                                       h->packed ? 1 : 0, h->d_payload, h->d_lb);
       CUT(cudaGetLastError());
     }
@@ -1462,6 +1367,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   }
   CUT(cudaStreamSynchronize(h->stream));
   free_tmp();
+#undef RCT
 
   // kernel attributes: opt in to the large dynamic shared memory carve-out once
   const int cap_max = key_capacity(BM25F_MAX_K, (int)h->NT);
@@ -1475,7 +1381,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[2] = {(const void*)k_score_warp<4>, (const void*)k_score_warp<8>};
+    const void* wfns[1] = {(const void*)k_score_stream};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1515,6 +1421,20 @@ int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
   for (uint32_t i = 0; i < h->n_fields * 256; ++i)
     if (!(norm[i] > 0.0f) || !std::isfinite(norm[i])) return fail(BM25F_EINVAL, "norm table entry %u is not a positive finite number", i);
   CU(cudaMemcpyAsync(h->d_norm, norm, (size_t)h->n_fields * 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // refresh the per-posting impacts (one streaming pass over the store per field run)
+  uint64_t t = 0;
+  while (t < h->n_terms) {
+    uint64_t t2 = t;
+    const uint8_t f = h->term_field[t];
+    while (t2 < h->n_terms && h->term_field[t2] == f) ++t2;
+    const uint64_t b = h->term_offsets[t], e = h->term_offsets[t2];
+    if (e > b) {
+      const unsigned blocks = (unsigned)std::min<uint64_t>((e - b + 255) / 256, (uint64_t)h->n_sms * 16);
+      k_impacts<<<blocks, 256, 0, h->stream>>>(h->d_docids, h->d_payload, h->d_lb, h->d_norm + (size_t)f * 256, b, e, h->packed ? 1 : 0, h->d_pairs);
+      CU(cudaGetLastError());
+    }
+    t = t2;
+  }
   CU(cudaStreamSynchronize(h->stream));
   h->have_weighting = true;
   return 0;
@@ -1610,7 +1530,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
-  const uint64_t nsub = (h->n_docs + h->SW - 1) / h->SW;
 
   for (uint32_t qi = 0; qi < Q; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -1683,28 +1602,39 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     out_leaf += nlq;
     postings += P;
 
-    // Route the query: warp-stream kernel when it is eligible (top list fits one warp, payload is
-    // packed, few enough leaves for register-resident windows), else the CTA-per-item kernels.
-    const bool warp_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && h->packed && nlq <= 8 && all_pos &&
-                         h->n_fields <= (uint32_t)WARP_NF && h->n_postings < 0xFFFF0000ull;
-    const int cls = warp_ok ? (nlq <= 4 ? 0 : 1) : 2;
+    // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
+    // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
+    const bool stream_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    const int cls = stream_ok ? 0 : 2;
     uint32_t nsplit;
-    if (warp_ok) {
-      // cost model in posting-equivalents: every sub-tile costs a fixed amount even when empty
-      const uint64_t work = P + 24ull * nsub * nlq / 3;
-      nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (work + h->wsplit / 2) / h->wsplit));
+    if (stream_ok) {
+      // cost model in posting-equivalents: every (sub-range, leaf) visit costs a fixed amount
+      const uint64_t sw = h->st_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
+      const uint64_t nsub = (h->n_docs + sw - 1) / sw;
+      const uint64_t work = P + nsub * (16ull * nlq + 24ull);
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 1024), std::max<uint64_t>(1, (work + h->wsplit / 2) / h->wsplit));
+      qr.n_parts = nsplit;
+      for (uint32_t s = 0; s < nsplit; ++s) {
+        ItemRec it;
+        it.q = qi;
+        it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
+        it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
+        it.part = n_parts + s;
+        items[cls].push_back(it);
+        item_w[cls].push_back(work / nsplit);
+      }
     } else {
       nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (P + h->split / 2) / h->split));
-    }
-    qr.n_parts = nsplit;
-    for (uint32_t s = 0; s < nsplit; ++s) {
-      ItemRec it;
-      it.q = qi;
-      it.tile_begin = (uint32_t)((uint64_t)T * s / nsplit);
-      it.tile_end = (uint32_t)((uint64_t)T * (s + 1) / nsplit);
-      it.part = n_parts + s;
-      items[cls].push_back(it);
-      item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
+      qr.n_parts = nsplit;
+      for (uint32_t s = 0; s < nsplit; ++s) {
+        ItemRec it;
+        it.q = qi;
+        it.tile_begin = (uint32_t)((uint64_t)T * s / nsplit);
+        it.tile_end = (uint32_t)((uint64_t)T * (s + 1) / nsplit);
+        it.part = n_parts + s;
+        items[cls].push_back(it);
+        item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
+      }
     }
     n_parts += nsplit;
   }
@@ -1742,7 +1672,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       return rc_;                                                       \
     }                                                                   \
   } while (0)
-  const size_t n_bounds = (size_t)out_leaf * (T + 1);
+  const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
   const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8;
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
@@ -1776,7 +1706,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
     const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
-                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)Q * 8),
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 2) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4);
     if (off > h->d_arena_cap) {
       CUP(cudaStreamSynchronize(h->stream));
@@ -1806,7 +1736,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
     RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, Q));
+    RCP(dev_alloc(&p->d_totals, (size_t)Q + 2));
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
@@ -1844,8 +1774,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   cudaEvent_t* ev = h->ev[h->ev_head];
   CU(cudaEventRecord(ev[0], st));
-  if (p->Q) CU(cudaMemsetAsync(p->d_totals, 0, (size_t)p->Q * 8, st));
-  const unsigned long long nb = (unsigned long long)p->n_leaves * (p->T + 1);
+  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 2) * 8, st));   // totals + the two work counters
+  const unsigned long long nb = p->n_items ? (unsigned long long)p->n_leaves * (p->T + 1) : 0ull;
   if (nb) {
     k_tile_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(p->d_leaves, p->n_leaves, p->T, h->S, h->d_docids, p->d_bounds);
     CU(cudaGetLastError());
@@ -1857,7 +1787,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
     sp.lb = h->d_lb;
-    sp.deleted = h->d_deleted;
+    sp.deleted = nullptr;
     sp.norm = h->d_norm;
     sp.leaves = p->d_leaves;
     sp.queries = p->d_queries;
@@ -1872,27 +1802,24 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.k = p->k;
     sp.cap = p->cap;
     sp.prof = h->d_prof;
-    {
-      WarpParams wp;
-      wp.sp = sp;
-      wp.SW = h->SW;
-      wp.n_fields = h->n_fields;
-      const int nw = WARP_NW;
-      const size_t smem = warp_smem_bytes(h);
-      if (p->n_w4) {
-        wp.sp.items = p->d_items_w4;
-        wp.n_items = p->n_w4;
-        k_score_warp<4><<<(p->n_w4 + nw - 1) / nw, nw * 32, smem, st>>>(wp);
-        CU(cudaGetLastError());
-        ++launches;
-      }
-      if (p->n_w8) {
-        wp.sp.items = p->d_items_w8;
-        wp.n_items = p->n_w8;
-        k_score_warp<8><<<(p->n_w8 + nw - 1) / nw, nw * 32, smem, st>>>(wp);
-        CU(cudaGetLastError());
-        ++launches;
-      }
+    if (p->n_w4 || p->n_w8) {
+      StreamParams stp;
+      stp.pairs = h->d_pairs;
+      stp.leaves = p->d_leaves;
+      stp.queries = p->d_queries;
+      stp.part_keys = p->d_part_keys;
+      stp.totals = p->d_totals;
+      stp.doc_base = (uint32_t)h->doc_base;
+      stp.pf_dist = h->st_pf;
+      stp.k = p->k;
+      stp.items = p->d_items_w4;
+      stp.n_items = p->n_w4;
+      stp.slot_bytes = h->st_slot_bytes;
+      stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
+      const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
+      k_score_stream<<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      CU(cudaGetLastError());
+      ++launches;
     }
     if (!p->n_items) {
       // nothing for the CTA kernels
@@ -1931,7 +1858,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
     if (p->n_w4 || p->n_w8) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_warp<4>, WARP_NW * 32, warp_smem_bytes(h));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
     } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define BM25F_ABI_VERSION 1
+#define BM25F_ABI_VERSION 2
 
 #define BM25F_OK          0
 #define BM25F_EINVAL     -1   /* bad argument */
@@ -80,13 +80,18 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (warp streams where eligible: k <= 32, <= 8 leaves,
-                                    integral weights; else the bulk-copy pipeline), 1 = bulk-copy pipeline,
-                                    2 = direct loads, 3 = same as 0 */
+  uint32_t variant;              /* scoring kernel: 0 = auto (persistent stream kernel where eligible: k <= 32,
+                                    <= 8 leaves, positive weights; else the bulk-copy pipeline),
+                                    1 = bulk-copy pipeline, 2 = direct loads, 3 = same as 0 */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
-  uint32_t subtile_docs;         /* warp streams: documents per warp-private sub-tile (multiple of 32) */
-  uint32_t warp_split;           /* warp streams: target work (posting-equivalents) per warp item */
+  uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
+                                    (4-byte accumulators; AND queries use half as many 8-byte slots);
+                                    multiple of 128 */
+  uint32_t warp_split;           /* stream kernel: target work (posting-equivalents) per work item */
+  uint32_t stream_warps;         /* stream kernel: warps (independent workers) per CTA, 1..16 */
+  uint32_t prefetch_postings;    /* stream kernel: bulk L2 prefetch distance (multiple of 512;
+                                    0xFFFFFFFF = off) */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves
@@ -108,7 +113,7 @@ typedef struct {
   uint64_t n_items;              /* work items of the last execute */
   uint64_t n_launches;           /* kernels launched by the last execute */
   uint64_t n_executes;           /* executes folded into the ms_* sums since the last reset */
-  float    ms_bounds;            /* summed device time of the tile-boundary kernel (CUDA events) */
+  float    ms_bounds;            /* summed device time of the tile-boundary kernel (CUDA events; CTA kernels only) */
   float    ms_score;             /* summed device time of the scoring + top-k kernel */
   float    ms_merge;             /* summed device time of the merge + decode kernels */
   float    ms_total;             /* summed first-launch-to-last-kernel-end time */

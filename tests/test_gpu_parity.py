@@ -73,19 +73,23 @@ def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
     assert_batch_parity(o, qs.queries, res, 10)
 
 
-@pytest.mark.parametrize("subtile,wsplit", [(128, 2048), (512, 0), (1024, 1 << 14), (2048, 1 << 20)])
+@pytest.mark.parametrize("subtile,wsplit,warps,pf", [(128, 2048, 16, 512), (512, 0, 4, 0xFFFFFFFF), (1024, 1 << 14, 8, 0),
+                                                      (3072, 1 << 20, 16, 4096), (12288, 1 << 12, 4, 1024)])
 @pytest.mark.parametrize("mode", ["mixed", "variants"])
-def test_warp_streams(cfg1, subtile, wsplit, mode):
-    """Warp-stream kernel: sub-tile sizes, many small items per query, 8-leaf AND-of-OR queries."""
+def test_stream_kernel(cfg1, subtile, wsplit, warps, pf, mode):
+    """Stream kernel: sub-range sizes, many small items per query (document ranges that start
+    inside lists), warps per CTA, prefetch distances, 8-leaf AND-of-OR queries."""
     ix, o = cfg1
     if mode == "variants":
         qs = make_queries(150, 50_000, 31, 4, 4, "and", variants=True, skip_top=0)
     else:
         qs = make_queries(300, 50_000, 78, 1, 4, "mixed", skip_top=0)
-    with ix.searcher(variant=3, subtile_docs=subtile, warp_split=wsplit, tile_docs=1024) as s:
+    kw = dict(variant=3, subtile_docs=subtile, warp_split=wsplit, stream_warps=warps, prefetch_postings=pf)
+    with ix.searcher(**kw) as s:
         res = s.search_batch(qs.queries, limit=10)
+        assert s.engine.stats()["n_launches"] <= 4
     assert_batch_parity(o, qs.queries, res, 10)
-    with ix.searcher(variant=3, subtile_docs=subtile, warp_split=wsplit, tile_docs=1024) as s:
+    with ix.searcher(**kw) as s:
         res = s.search_batch(qs.queries[:60], limit=32)
     assert_batch_parity(o, qs.queries[:60], res, 32)
 
