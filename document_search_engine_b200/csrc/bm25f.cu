@@ -942,6 +942,7 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
 }
 
 #include "stream.cuh"
+#include "team.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -1030,10 +1031,13 @@ struct bm25f_handle {
   uint32_t variant = 0;               // 0 / 3: auto (stream kernel where eligible, else pipeline), 1: pipeline, 2: direct loads
   // stream kernel: warps per CTA, accumulator bytes per warp, target work per item, L2 prefetch distance
   uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 16, st_pf = 2048;
+  // team kernel (variant 4): warps per CTA, target work per item, slices ahead to prefetch
+  uint32_t tl_warps = 8, tl_slot_bytes = 10240, tl_split = 1u << 18, tl_prefetch = 0;
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
   uint32_t nf_smem = 0;
   int n_sms = 148;
   int ctas_per_sm = 0;
+  int tl_ctas_per_sm = 0;
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
   cudaEvent_t ev[EV_RING][4] = {};
   int ev_head = 0;                     // next slot to use
@@ -1051,7 +1055,7 @@ struct bm25f_handle {
 struct bm25f_plan {
   bm25f_handle* h = nullptr;
   uint32_t Q = 0, n_leaves = 0, n_items = 0, n_parts = 0, T = 0;
-  uint32_t n_w4 = 0, n_w8 = 0;            // warp-stream items (<= 4 / <= 8 leaves); the rest are CTA items
+  uint32_t n_w4 = 0, n_w8 = 0;            // stream-kernel items / team-kernel items; the rest are CTA items
   ItemRec* d_items_w4 = nullptr;
   ItemRec* d_items_w8 = nullptr;
   int k = 0, kp = 1, cap = 1024;
@@ -1091,6 +1095,8 @@ size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
   b += (size_t)HOTCAP * sizeof(uint16_t);
   return b;
 }
+
+size_t team_smem_bytes(const bm25f_handle* h) { return (size_t)h->tl_warps * h->tl_slot_bytes + sizeof(TeamShared); }
 
 size_t stream_smem_bytes(uint32_t warps, uint32_t slot_bytes) {
   return (size_t)warps * (slot_bytes + ST_MAX_LEAVES * 256 + ST_HOT * 2 + 4);
@@ -1209,14 +1215,27 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->stream_warps) h->st_warps = opts->stream_warps;
     if (opts->prefetch_postings) h->st_pf = opts->prefetch_postings == 0xFFFFFFFFu ? 0u : opts->prefetch_postings;
   }
-  if (h->variant > 3) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads) or 3 (same as 0)"); }
+  if (opts) {
+    if (opts->cta_warps) h->tl_warps = opts->cta_warps;
+    if (opts->cta_prefetch) h->tl_prefetch = opts->cta_prefetch == 0xFFFFFFFFu ? 0u : opts->cta_prefetch;
+    if (opts->cta_split) h->tl_split = opts->cta_split;
+    if (opts->cta_slice_docs) h->tl_slot_bytes = opts->cta_slice_docs * 4u;
+  }
+  if (h->tl_slot_bytes < 512 || (h->tl_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "cta_slice_docs must be a multiple of 128, at least 128"); }
+  if (h->variant > 4) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams) or 4 (warp teams)"); }
+  if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
   if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
   if (h->st_pf & (ST_PF_CHUNK - 1u)) { delete h; return fail(BM25F_EINVAL, "prefetch_postings must be a multiple of %u", ST_PF_CHUNK); }
-  if (stream_smem_bytes(h->st_warps, h->st_slot_bytes) > (size_t)prop.sharedMemPerBlockOptin) {
+  if (h->variant != 4 && h->variant != 1 && h->variant != 2 && stream_smem_bytes(h->st_warps, h->st_slot_bytes) > (size_t)prop.sharedMemPerBlockOptin) {
     const size_t need = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
     delete h;
     return fail(BM25F_EINVAL, "stream_warps x subtile_docs needs %zu bytes of shared memory (> %zu)", need, (size_t)prop.sharedMemPerBlockOptin);
+  }
+  if ((h->variant == 4 || h->variant == 0) && team_smem_bytes(h) > (size_t)prop.sharedMemPerBlockOptin) {
+    const size_t need = team_smem_bytes(h);
+    delete h;
+    return fail(BM25F_EINVAL, "cta_warps x subtile_docs needs %zu bytes of shared memory (> %zu)", need, (size_t)prop.sharedMemPerBlockOptin);
   }
   if (h->chunk < 64 || (h->chunk & 15) || h->chunk > 8192) { delete h; return fail(BM25F_EINVAL, "chunk_postings must be a multiple of 16 in 64..8192"); }
   if (h->stages < 2 || h->stages > (uint32_t)PIPE_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "stages must be 2..%d", PIPE_MAX_STAGES); }
@@ -1381,7 +1400,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[1] = {(const void*)k_score_stream};
+    const void* wfns[2] = {(const void*)k_score_stream, (const void*)k_score_team};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1604,10 +1623,29 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant == 3) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
-    const int cls = stream_ok ? 0 : 2;
+    const bool stream_ok = (h->variant == 0 || h->variant == 3 || h->variant == 4) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
+    // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
+    const bool use_team = stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const int cls = stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
-    if (stream_ok) {
+    if (use_team) {
+      // warp teams: an item is a document range; its slices are handed out inside the CTA
+      const uint64_t sw = h->tl_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
+      const uint64_t nsl = (h->n_docs + sw - 1) / sw;
+      const uint64_t work = P + nsl * (16ull * nlq + 24ull);
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, nsl / 32), std::max<uint64_t>(1, (work + h->tl_split / 2) / h->tl_split));
+      qr.n_parts = nsplit;
+      for (uint32_t s = 0; s < nsplit; ++s) {
+        ItemRec it;
+        it.q = qi;
+        it.tile_begin = (uint32_t)((nsl * s / nsplit) * sw);                    // document range [lo, hi), slice-aligned
+        it.tile_end = (uint32_t)std::min<uint64_t>(h->n_docs, (nsl * (s + 1) / nsplit) * sw);
+        it.part = n_parts + s;
+        items[cls].push_back(it);
+        item_w[cls].push_back(work / nsplit);
+      }
+    } else if (stream_ok) {
       // cost model in posting-equivalents: every (sub-range, leaf) visit costs a fixed amount
       const uint64_t sw = h->st_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
       const uint64_t nsub = (h->n_docs + sw - 1) / sw;
@@ -1802,7 +1840,31 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.k = p->k;
     sp.cap = p->cap;
     sp.prof = h->d_prof;
-    if (p->n_w4 || p->n_w8) {
+    if (p->n_w8) {
+      TeamParams tp;
+      tp.pairs = h->d_pairs;
+      tp.leaves = p->d_leaves;
+      tp.queries = p->d_queries;
+      tp.items = p->d_items_w8;
+      tp.part_keys = p->d_part_keys;
+      tp.totals = p->d_totals;
+      tp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 1);
+      tp.n_items = p->n_w8;
+      tp.slot_bytes = h->tl_slot_bytes;
+      tp.doc_base = (uint32_t)h->doc_base;
+      tp.prefetch = h->tl_prefetch;
+      tp.k = p->k;
+      if (h->tl_ctas_per_sm == 0) {
+        int nb_ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_team, (int)h->tl_warps * 32, team_smem_bytes(h)));
+        h->tl_ctas_per_sm = std::max(1, nb_);
+      }
+      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->tl_ctas_per_sm), p->n_w8);
+      k_score_team<<<grid, h->tl_warps * 32u, team_smem_bytes(h), st>>>(tp);
+      CU(cudaGetLastError());
+      ++launches;
+    }
+    if (p->n_w4) {
       StreamParams stp;
       stp.pairs = h->d_pairs;
       stp.leaves = p->d_leaves;
@@ -1857,7 +1919,9 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
-    if (p->n_w4 || p->n_w8) {
+    if (p->n_w8 && !p->n_w4) {
+      nb_ = h->tl_ctas_per_sm;
+    } else if (p->n_w4) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
     } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);

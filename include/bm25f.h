@@ -80,9 +80,11 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (persistent stream kernel where eligible: k <= 32,
-                                    <= 8 leaves, positive weights; else the bulk-copy pipeline),
-                                    1 = bulk-copy pipeline, 2 = direct loads, 3 = same as 0 */
+  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 32, <= 8 leaves, positive
+                                    weights, no paging bound - flat ORs on warp streams and ANDs on warp
+                                    teams; else the bulk-copy pipeline),
+                                    1 = bulk-copy pipeline, 2 = direct loads, 3 = warp streams,
+                                    4 = warp teams (same eligibility as 3) */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
   uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
@@ -91,7 +93,12 @@ typedef struct {
   uint32_t warp_split;           /* stream kernel: target work (posting-equivalents) per work item */
   uint32_t stream_warps;         /* stream kernel: warps (independent workers) per CTA, 1..16 */
   uint32_t prefetch_postings;    /* stream kernel: bulk L2 prefetch distance (multiple of 512;
-                                    0xFFFFFFFF = off) */
+                                    0xFFFFFFFF = off; also switches the tile kernel's prefetch) */
+  uint32_t cta_warps;            /* team kernel: warps per CTA, 1..16 */
+  uint32_t cta_prefetch;         /* team kernel: slices ahead to bulk-prefetch into L2 (0xFFFFFFFF = off) */
+  uint32_t cta_split;            /* team kernel: target work (posting-equivalents) per work item */
+  uint32_t cta_slice_docs;       /* team kernel: documents per warp-private slice of a flat OR (AND: half);
+                                    multiple of 128 */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

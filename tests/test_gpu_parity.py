@@ -94,6 +94,28 @@ def test_stream_kernel(cfg1, subtile, wsplit, warps, pf, mode):
     assert_batch_parity(o, qs.queries[:60], res, 32)
 
 
+@pytest.mark.parametrize("subtile,warps,split,pf", [(128, 16, 2048, 2), (512, 4, 0, 0xFFFFFFFF), (1024, 8, 1 << 12, 0),
+                                                     (2944, 16, 0, 16), (12288, 3, 1 << 20, 1)])
+@pytest.mark.parametrize("mode", ["mixed", "variants"])
+def test_team_kernel(cfg1, subtile, warps, split, pf, mode):
+    """Warp-team kernel: slice sizes (several table windows per item / one slice per item), warps
+    per CTA, item splitting (document ranges that start inside lists), prefetch distances, 8-leaf
+    AND-of-OR queries, k = 10 and 32."""
+    ix, o = cfg1
+    if mode == "variants":
+        qs = make_queries(150, 50_000, 31, 4, 4, "and", variants=True, skip_top=0)
+    else:
+        qs = make_queries(300, 50_000, 78, 1, 4, "mixed", skip_top=0)
+    kw = dict(variant=4, cta_slice_docs=subtile, cta_warps=warps, cta_split=split, cta_prefetch=pf)
+    with ix.searcher(**kw) as s:
+        res = s.search_batch(qs.queries, limit=10)
+        assert s.engine.stats()["n_launches"] <= 4
+    assert_batch_parity(o, qs.queries, res, 10)
+    with ix.searcher(**kw) as s:
+        res = s.search_batch(qs.queries[:60], limit=32)
+    assert_batch_parity(o, qs.queries[:60], res, 32)
+
+
 @pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])
 def test_limits(cfg1, k):
     ix, o = cfg1

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Time the hot path for several engine options on one GPU (development tool).
 
-Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split[:variant:chunk:stages:subtile:warp_split:stream_warps:prefetch]`` tuple
+Generates the BASELINE config corpus once, then for every ``tile_docs:threads:split[:variant:chunk:stages:subtile:warp_split:stream_warps:prefetch:cta_warps:cta_prefetch:cta_split]`` tuple
 creates an engine, checks a query sample against the oracle, and times ``execute`` with the
 library's CUDA events.  Prints one JSON line per configuration.
 """
@@ -48,12 +48,12 @@ def main():
             qsets[m] = make_queries(nq, c["vocab"], 20261000 + args.config, c["min_terms"], c["max_terms"], m).queries
     k = c["k"]
     for opt in args.opts:
-        f = [int(x) for x in opt.split(":")] + [0] * 10
-        S, NT, split, variant, chunk, stages, sw, wsplit, swarps, pf = f[:10]
+        f = [int(x) for x in opt.split(":")] + [0] * 14
+        S, NT, split, variant, chunk, stages, sw, wsplit, swarps, pf, cw, ct, cs, csd = f[:14]
         ix._engine_cache.clear()
         s = Searcher(ix, weighting=BM25F, tile_docs=S, threads=NT, split_postings=split, variant=variant,
                      chunk_postings=chunk, stages=stages, subtile_docs=sw, warp_split=wsplit,
-                     stream_warps=swarps, prefetch_postings=pf)
+                     stream_warps=swarps, prefetch_postings=pf, cta_warps=cw, cta_prefetch=ct, cta_split=cs, cta_slice_docs=csd)
         eng = s.engine
         for m, queries in qsets.items():
             batch = s.pack(queries)
