@@ -154,6 +154,18 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernels of one step, from the
+    committed ncu capture of this same command (profiles/r01_traffic.json), or None."""
+    if world != 1:
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return float(json.load(f)["dram_bytes_per_step"])
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------
 def workload(args):
     from document_search_engine_b200.corpus import CONFIGS
@@ -233,9 +245,10 @@ def main():
     ap.add_argument("--docs", type=int, default=0)
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--tile-docs", type=int, default=0)
-    ap.add_argument("--threads", type=int, default=0)
-    ap.add_argument("--split", type=int, default=0)
+    ap.add_argument("--variant", type=int, default=0, help="scoring kernel (include/bm25f.h); 0 = auto")
+    ap.add_argument("--subtile-docs", type=int, default=0)
+    ap.add_argument("--cta-slice-docs", type=int, default=0)
+    ap.add_argument("--cta-warps", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--check", type=int, default=32, help="queries checked against the oracle before timing")
     args = ap.parse_args()
@@ -271,7 +284,8 @@ def main():
     torch.cuda.empty_cache()
     t0 = time.perf_counter()
     ss = ShardedSearcher(ix, rank=rank, world=world, device=local_rank, weighting=BM25F,
-                         tile_docs=args.tile_docs, threads=args.threads, split_postings=args.split)
+                         variant=args.variant, subtile_docs=args.subtile_docs, cta_slice_docs=args.cta_slice_docs,
+                         cta_warps=args.cta_warps)
     eng = ss.engine
     batch = ss.pack(qs.queries)
     if rank == 0:
@@ -354,8 +368,9 @@ def main():
     if rank == 0:
         cfg = config_json(args, c, world)
         cfg["l2"] = cfg["l2"] % (st["device_bytes"] / 2 ** 30)
-        cfg["engine"] = {"tile_docs": st["tile_docs"], "threads": st["threads"], "ctas_per_sm": st["ctas_per_sm"],
-                         "packed_payload": bool(st["packed_payload"]), "work_items": int(st["n_items"])}
+        cfg["engine"] = {"variant": args.variant, "ctas_per_sm": st["ctas_per_sm"],
+                         "packed_payload": bool(st["packed_payload"]), "work_items": int(st["n_items"]),
+                         "kernels_per_step": int(st["n_launches"])}
         out = {"metric": "BM25F top-%d queries/sec" % k, "value": value, "unit": "queries/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
@@ -363,8 +378,10 @@ def main():
                        "d2h_bytes_per_step": int(d2h)},
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                            "kernel": "k_score_warp", "kernel_ms_per_step": ms_score,
+                            "frac": achieved / peak, "traffic": measured_traffic(world), "peak_source": peak_src,
+                            "kernel": "k_score_stream + k_score_team (flat ORs on warp streams, ANDs on warp "
+                                      "teams; timed together, back to back on one stream)",
+                            "kernel_ms_per_step": ms_score,
                             "algorithmic_bytes_per_step": BYTES_PER_POSTING * st["postings_touched"],
                             "frac_of_nominal_8000": achieved / 8000.0},
                "kernel_ms": {"bounds": st["ms_bounds"] / max(1, st["n_executes"]), "score": ms_score,

@@ -1,0 +1,103 @@
+"""N > 1 path on CPU: world_size-2 ``gloo`` run of the exchange step (SURVEY.md §8 e).
+
+Each rank holds one document shard with local docids, scores it with corpus-wide statistics (here
+with the oracle, since there is no GPU), encodes its local top-k as the engine's 64-bit W11 keys over
+GLOBAL docnums, and the ranks exchange with all_gather / all_reduce exactly as ShardedSearcher does;
+the merged list must equal the whole-corpus result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from document_search_engine_b200.corpus import make_corpus, make_queries
+from document_search_engine_b200.distributed import decode_keys_host, merge_keys_host
+from document_search_engine_b200.searching import make_keys
+from oracle.numpy_oracle import NumpyOracle
+
+K = 10
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _local_keys(full_ix, shard, queries):
+    """Local top-k keys [Q, K] (global docnums) and local totals [Q] of one shard."""
+    o = NumpyOracle(full_ix, shards=[shard])
+    keys = np.zeros((len(queries), K), dtype=np.uint64)
+    totals = np.zeros(len(queries), dtype=np.int64)
+    for i, q in enumerate(queries):
+        top, total = o.search(q, limit=K)
+        totals[i] = total
+        if top:
+            s = np.array([t[0] for t in top], dtype=np.float32)
+            d = np.array([t[1] for t in top], dtype=np.uint64)
+            keys[i, :len(top)] = make_keys(s, d)
+    return keys, totals
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ix = make_corpus(4000, 3000, 7, device="cpu")
+        qs = make_queries(80, 3000, 8, 1, 4, "mixed", skip_top=0).queries
+        shard = ix.shard(rank, world)
+        assert shard.doc_base == ix.n_docs_all * rank // world
+        keys, totals = _local_keys(ix, shard, qs)
+        local = torch.from_numpy(keys.view(np.int64).reshape(-1))
+        gathered = torch.empty(world * local.numel(), dtype=torch.int64)
+        dist.all_gather_into_tensor(gathered, local)
+        tot = torch.from_numpy(totals.copy())
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        merged = merge_keys_host(gathered.numpy().view(np.uint64).reshape(world, len(qs), K), K)
+        if rank == 0:
+            scores, docids, counts = decode_keys_host(merged)
+            np.savez(out, scores=scores, docids=docids, counts=counts, totals=tot.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_exchange_equals_whole(tmp_path):
+    out = str(tmp_path / "merged.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    ix = make_corpus(4000, 3000, 7, device="cpu")
+    qs = make_queries(80, 3000, 8, 1, 4, "mixed", skip_top=0).queries
+    o = NumpyOracle(ix)
+    for i, q in enumerate(qs):
+        top, total = o.search(q, limit=K)
+        assert int(got["totals"][i]) == total
+        n = int(got["counts"][i])
+        assert n == len(top)
+        assert got["docids"][i, :n].tolist() == [d for _, d in top]
+        assert got["scores"][i, :n].tolist() == pytest.approx([s for s, _ in top], rel=1e-6)
+
+
+def test_shards_partition_the_corpus():
+    ix = make_corpus(1000, 500, 3, device="cpu")
+    for world in (2, 3, 8):
+        shards = [ix.shard(g, world) for g in range(world)]
+        assert sum(s.n_docs_all for s in shards) == ix.n_docs_all
+        assert sum(s.n_postings for s in shards) == ix.n_postings
+        assert [s.doc_base for s in shards] == [ix.n_docs_all * g // world for g in range(world)]
+        # W8: statistics stay corpus-wide, docids become local
+        for s in shards:
+            assert s.docids.max(initial=0) < max(1, s.n_docs_all)
+
+
+def test_key_roundtrip_and_order():
+    s = np.array([3.5, 3.5, 1.0, 0.25, 7.0], dtype=np.float32)
+    d = np.array([9, 2, 5, 5, 100], dtype=np.uint64)
+    keys = make_keys(s, d)
+    order = np.argsort(keys)[::-1]
+    assert order.tolist() == [4, 1, 0, 2, 3]          # score desc, docnum asc (W11)
+    sc, dc, cnt = decode_keys_host(keys[None, :])
+    assert sc[0].tolist() == s.tolist() and dc[0].tolist() == d.tolist() and cnt[0] == 5

@@ -1,0 +1,66 @@
+"""Committed golden vectors (tests/golden/*.json, produced by tests/golden/make_golden.py).
+
+CPU: both oracle implementations must reproduce them.  GPU: the CUDA path is compared with the
+committed vectors directly (no oracle run needed on the GPU box for these cases)."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.numpy_oracle import NumpyOracle
+from oracle.whoosh_port import OracleSearcher
+from tests.golden.make_golden import build_case
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.json")))
+REL_TOL = 1e-5
+
+
+def load(path):
+    with open(path) as f:
+        return json.load(f)
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 4
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-5] for p in FIXTURES])
+@pytest.mark.parametrize("oracle_cls", [OracleSearcher, NumpyOracle])
+def test_oracles_reproduce_golden(path, oracle_cls):
+    fx = load(path)
+    c = fx["case"]
+    ix, queries = build_case(c)
+    o = oracle_cls(ix, B=c["B"], K1=c["K1"], field_B=c["field_B"])
+    assert len(queries) == len(fx["results"])
+    for q, want in zip(queries, fx["results"]):
+        top, total = o.search(q, limit=c["k"])
+        assert total == want["total"]
+        assert [d for _, d in top] == [d for _, d in want["top"]]
+        assert [s for s, _ in top] == pytest.approx([s for s, _ in want["top"]], rel=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [0, 3, 4, 1])
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-5] for p in FIXTURES])
+def test_engine_matches_golden(path, variant):
+    """Totals bit-exact, scores within 1e-5 relative (fp32 vs float64), order identical except among
+    ties inside that tolerance (north star)."""
+    from document_search_engine_b200 import BM25F
+    fx = load(path)
+    c = fx["case"]
+    ix, queries = build_case(c)
+    w = BM25F(B=c["B"], K1=c["K1"], **{f + "_B": b for f, b in c["field_B"].items()})
+    with ix.searcher(weighting=w, variant=variant) as s:
+        res = s.search_batch(queries, limit=c["k"])
+    for i, (r, want) in enumerate(zip(res, fx["results"])):
+        assert len(r) == want["total"], "query %d total" % i
+        assert len(r.top_n) == len(want["top"]), "query %d hits" % i
+        for rank, ((gs, gd), (ws, wd)) in enumerate(zip(r.top_n, want["top"])):
+            assert abs(gs - ws) <= REL_TOL * abs(ws), "query %d rank %d: score %r vs %r" % (i, rank, gs, ws)
+            if gd != wd:
+                # a different document at this rank is only acceptable as a tie inside the tolerance
+                ties = [d for s2, d in want["top"] if abs(s2 - ws) <= REL_TOL * abs(ws)]
+                assert gd in ties or rank == len(want["top"]) - 1, "query %d rank %d: doc %d vs %d" % (i, rank, gd, wd)
