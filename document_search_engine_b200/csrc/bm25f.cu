@@ -943,6 +943,7 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
 
 #include "stream.cuh"
 #include "team.cuh"
+#include "isect.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -984,6 +985,44 @@ __global__ void k_merge_topk(const unsigned long long* __restrict__ keys_in, con
   for (int i = tid; i < k; i += nt) keys_out[(size_t)q * k + i] = buf[i];
 }
 
+// Same merge for k <= 32: one warp per query, lane i keeps the i-th best key, candidates are inserted
+// with shuffles (no shared memory, no barriers).
+__global__ void k_merge_topk_warp(const unsigned long long* __restrict__ keys_in, const QueryRec* __restrict__ queries,
+                                  int mode, int n_lists_fixed, unsigned long long stride_fixed, uint32_t Q, int k,
+                                  unsigned long long* __restrict__ keys_out) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  unsigned long long start, stride;
+  int n_lists;
+  if (mode == 0) {
+    const QueryRec qr = queries[q];
+    start = (unsigned long long)qr.part_begin * k;
+    stride = (unsigned long long)k;
+    n_lists = (int)qr.n_parts;
+  } else {
+    start = (unsigned long long)q * k;
+    stride = stride_fixed;
+    n_lists = n_lists_fixed;
+  }
+  unsigned long long best = (n_lists > 0 && lane < k) ? keys_in[start + lane] : 0ull;
+  unsigned long long thr = __shfl_sync(0xFFFFFFFFu, best, k - 1);
+  for (int l = 1; l < n_lists; ++l) {
+    const unsigned long long key = (lane < k) ? keys_in[start + l * stride + lane] : 0ull;
+    unsigned pm = __ballot_sync(0xFFFFFFFFu, key > thr);
+    while (pm) {
+      const int src = __ffs(pm) - 1;
+      pm &= pm - 1u;
+      const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
+      if (bk > thr) {
+        warp_topk_insert(best, bk, lane);
+        thr = __shfl_sync(0xFFFFFFFFu, best, k - 1);
+      }
+    }
+  }
+  if (lane < k) keys_out[(size_t)q * k + lane] = best;
+}
+
 __global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint32_t Q, int k,
                               float* __restrict__ scores, uint32_t* __restrict__ docids,
                               uint32_t* __restrict__ counts) {
@@ -1016,6 +1055,8 @@ struct bm25f_handle {
   int device = 0;
   cudaStream_t stream = nullptr;      // stream in use
   cudaStream_t own_stream = nullptr;  // created by the library
+  cudaStream_t aux_stream = nullptr;  // the candidate-driven / team kernels run here, beside the stream kernel
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t n_docs = 0, n_terms = 0, n_postings = 0, doc_base = 0;
   uint32_t n_fields = 0;
   std::vector<uint64_t> term_offsets;
@@ -1030,7 +1071,7 @@ struct bm25f_handle {
   uint32_t S = 8192, NT = 256, split = 1u << 16;
   uint32_t variant = 0;               // 0 / 3: auto (stream kernel where eligible, else pipeline), 1: pipeline, 2: direct loads
   // stream kernel: warps per CTA, accumulator bytes per warp, target work per item, L2 prefetch distance
-  uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 16, st_pf = 2048;
+  uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 17, st_pf = 2048;
   // team kernel (variant 4): warps per CTA, target work per item, slices ahead to prefetch
   uint32_t tl_warps = 8, tl_slot_bytes = 10240, tl_split = 1u << 18, tl_prefetch = 0;
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
@@ -1038,6 +1079,8 @@ struct bm25f_handle {
   int n_sms = 148;
   int ctas_per_sm = 0;
   int tl_ctas_per_sm = 0;
+  int is_ctas_per_sm = 0;
+  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 16000;   // candidate-driven AND: cost of a lookup in postings, candidates per item
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
   cudaEvent_t ev[EV_RING][4] = {};
   int ev_head = 0;                     // next slot to use
@@ -1058,6 +1101,8 @@ struct bm25f_plan {
   uint32_t n_w4 = 0, n_w8 = 0;            // stream-kernel items / team-kernel items; the rest are CTA items
   ItemRec* d_items_w4 = nullptr;
   ItemRec* d_items_w8 = nullptr;
+  uint32_t n_is = 0;                      // candidate-driven AND items
+  ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
   LeafRec* d_leaves = nullptr;
@@ -1165,6 +1210,9 @@ void bm25f_destroy(bm25f_handle* h) {
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -1222,7 +1270,12 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->cta_slice_docs) h->tl_slot_bytes = opts->cta_slice_docs * 4u;
   }
   if (h->tl_slot_bytes < 512 || (h->tl_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "cta_slice_docs must be a multiple of 128, at least 128"); }
-  if (h->variant > 4) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams) or 4 (warp teams)"); }
+  if (opts) {
+    if (opts->isect_ratio) h->is_ratio = opts->isect_ratio;
+    if (opts->isect_split) h->is_split = opts->isect_split;
+    if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
+  }
+  if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
   if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
@@ -1261,6 +1314,9 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   } while (0)
 
   CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->stream = h->own_stream;
   for (auto& set : h->ev)
     for (auto& e : set) CUH(cudaEventCreate(&e));
@@ -1541,8 +1597,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     queries = own_queries.data();
   }
 
-  std::vector<ItemRec> items[3];     // 0: warp streams, <= 4 leaves; 1: warp streams, <= 8; 2: CTA kernels
-  std::vector<uint64_t> item_w[3];
+  std::vector<ItemRec> items[4];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven AND
+  std::vector<uint64_t> item_w[4];
   items[0].reserve(Q * 2);
   item_w[0].reserve(Q * 2);
   uint64_t postings = 0;
@@ -1623,13 +1679,35 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant == 3 || h->variant == 4) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    const bool stream_ok = (h->variant == 0 || h->variant == 3 || h->variant == 4 || h->variant == 5) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
     // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
     // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
-    const bool use_team = stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
-    const int cls = stream_ok ? (use_team ? 1 : 0) : 2;
+    // ... unless its smallest group is so much sparser than the rest that looking its documents up in
+    // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
+    const uint64_t g0 = gsize[order[0]];
+    const bool isect_ok = k <= 32 && nlq <= 32 && all_pos && qr.after_key == 0ull;
+    // A flat OR with few postings is also cheaper that way (every posting is a candidate and is still
+    // read exactly once; sweeping every sub-range of the document space for it is what costs).
+    const bool use_isect = isect_ok && (h->variant == 5 || (h->variant == 0 &&
+        ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
+                                   : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
+    const uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P : g0;
+    const bool use_team = !use_isect && stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
-    if (use_team) {
+    if (use_isect) {
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + h->is_split / 2) / h->is_split));
+      qr.n_parts = nsplit;
+      for (uint32_t s = 0; s < nsplit; ++s) {
+        ItemRec it;
+        it.q = qi;
+        it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
+        it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
+        it.part = n_parts + s;
+        items[cls].push_back(it);
+        item_w[cls].push_back(n_cand * (uint64_t)(nlq > 1 ? nlq - 1 : 1) / nsplit + 64);
+      }
+    } else if (use_team) {
       // warp teams: an item is a document range; its slices are handed out inside the CTA
       const uint64_t sw = h->tl_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
       const uint64_t nsl = (h->n_docs + sw - 1) / sw;
@@ -1690,6 +1768,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_items = (uint32_t)items[2].size();
   p->n_w4 = (uint32_t)items[0].size();
   p->n_w8 = (uint32_t)items[1].size();
+  p->n_is = (uint32_t)items[3].size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
@@ -1711,7 +1790,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }                                                                   \
   } while (0)
   const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
-  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8;
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
   if (use_arena) {
@@ -1734,17 +1813,18 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     own_items.resize(n_it);
     h_items = own_items.data();
   }
-  // layout of the item array: [CTA items][warp <= 4 leaves][warp <= 8 leaves]
+  // layout of the item array: [CTA items][warp streams][warp teams][candidate-driven AND]
   order_items(items[2], item_w[2], h_items);
   order_items(items[0], item_w[0], h_items + p->n_items);
   order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
+  order_items(items[3], item_w[3], h_items + p->n_items + p->n_w4 + p->n_w8);
 
   if (use_arena) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
     const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
-                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 2) * 8),
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 3) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4);
     if (off > h->d_arena_cap) {
       CUP(cudaStreamSynchronize(h->stream));
@@ -1774,13 +1854,14 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
     RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, (size_t)Q + 2));
+    RCP(dev_alloc(&p->d_totals, (size_t)Q + 3));
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
   }
   p->d_items_w4 = p->d_items + p->n_items;
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
+  p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
   if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
@@ -1812,7 +1893,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   cudaEvent_t* ev = h->ev[h->ev_head];
   CU(cudaEventRecord(ev[0], st));
-  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 2) * 8, st));   // totals + the two work counters
+  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 3) * 8, st));   // totals + the three work counters
   const unsigned long long nb = p->n_items ? (unsigned long long)p->n_leaves * (p->T + 1) : 0ull;
   if (nb) {
     k_tile_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(p->d_leaves, p->n_leaves, p->T, h->S, h->d_docids, p->d_bounds);
@@ -1820,7 +1901,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items || p->n_w4 || p->n_w8) {
+  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -1840,6 +1921,55 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.k = p->k;
     sp.cap = p->cap;
     sp.prof = h->d_prof;
+    // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
+    // registers) fit on an SM together and stall on different things: launch them side by side.
+    const bool side = p->n_w4 && (p->n_is || p->n_w8);
+    cudaStream_t ax = side ? h->aux_stream : st;
+    if (side) {
+      CU(cudaEventRecord(h->ev_fork, st));
+      CU(cudaStreamWaitEvent(ax, h->ev_fork, 0));
+    }
+    if (p->n_w4) {
+      StreamParams stp;
+      stp.pairs = h->d_pairs;
+      stp.leaves = p->d_leaves;
+      stp.queries = p->d_queries;
+      stp.part_keys = p->d_part_keys;
+      stp.totals = p->d_totals;
+      stp.doc_base = (uint32_t)h->doc_base;
+      stp.pf_dist = h->st_pf;
+      stp.k = p->k;
+      stp.items = p->d_items_w4;
+      stp.n_items = p->n_w4;
+      stp.slot_bytes = h->st_slot_bytes;
+      stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
+      const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
+      k_score_stream<<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      CU(cudaGetLastError());
+      ++launches;
+    }
+    if (p->n_is) {
+      IsectParams ip;
+      ip.pairs = h->d_pairs;
+      ip.leaves = p->d_leaves;
+      ip.queries = p->d_queries;
+      ip.items = p->d_items_is;
+      ip.part_keys = p->d_part_keys;
+      ip.totals = p->d_totals;
+      ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 2);
+      ip.n_items = p->n_is;
+      ip.doc_base = (uint32_t)h->doc_base;
+      ip.k = p->k;
+      if (h->is_ctas_per_sm == 0) {
+        int nb_ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect, IS_WARPS * 32, 0));
+        h->is_ctas_per_sm = std::max(1, nb_);
+      }
+      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_is + IS_WARPS - 1) / IS_WARPS);
+      k_score_isect<<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      CU(cudaGetLastError());
+      ++launches;
+    }
     if (p->n_w8) {
       TeamParams tp;
       tp.pairs = h->d_pairs;
@@ -1860,28 +1990,13 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
         h->tl_ctas_per_sm = std::max(1, nb_);
       }
       const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->tl_ctas_per_sm), p->n_w8);
-      k_score_team<<<grid, h->tl_warps * 32u, team_smem_bytes(h), st>>>(tp);
+      k_score_team<<<grid, h->tl_warps * 32u, team_smem_bytes(h), ax>>>(tp);
       CU(cudaGetLastError());
       ++launches;
     }
-    if (p->n_w4) {
-      StreamParams stp;
-      stp.pairs = h->d_pairs;
-      stp.leaves = p->d_leaves;
-      stp.queries = p->d_queries;
-      stp.part_keys = p->d_part_keys;
-      stp.totals = p->d_totals;
-      stp.doc_base = (uint32_t)h->doc_base;
-      stp.pf_dist = h->st_pf;
-      stp.k = p->k;
-      stp.items = p->d_items_w4;
-      stp.n_items = p->n_w4;
-      stp.slot_bytes = h->st_slot_bytes;
-      stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
-      const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
-      k_score_stream<<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
-      CU(cudaGetLastError());
-      ++launches;
+    if (side) {
+      CU(cudaEventRecord(h->ev_join, ax));
+      CU(cudaStreamWaitEvent(st, h->ev_join, 0));
     }
     if (!p->n_items) {
       // nothing for the CTA kernels
@@ -1905,7 +2020,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q) {
-    k_merge_topk<<<p->Q, 128, (size_t)2 * p->kp * 8, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->kp, p->d_keys);
+    if (p->k <= 32) k_merge_topk_warp<<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->d_keys);
+    else k_merge_topk<<<p->Q, 128, (size_t)2 * p->kp * 8, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->kp, p->d_keys);
     CU(cudaGetLastError());
     k_decode_keys<<<p->Q, 64, 0, st>>>(p->d_keys, p->Q, p->k, p->d_scores, p->d_docids, p->d_counts);
     CU(cudaGetLastError());
@@ -1915,7 +2031,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
   h->stats.postings_touched = p->postings;
-  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8;
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
@@ -1991,9 +2107,14 @@ int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint3
   int kp = 1;
   while (kp < k) kp <<= 1;
   if (n_queries) {
-    k_merge_topk<<<n_queries, 128, (size_t)2 * kp * 8, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), nullptr, 1, n_lists,
-                                                             (unsigned long long)n_queries * k, n_queries, k, kp,
-                                                             reinterpret_cast<unsigned long long*>(d_out_keys));
+    if (k <= 32)
+      k_merge_topk_warp<<<(n_queries + 7) / 8, 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), nullptr, 1, n_lists,
+                                                           (unsigned long long)n_queries * k, n_queries, k,
+                                                           reinterpret_cast<unsigned long long*>(d_out_keys));
+    else
+      k_merge_topk<<<n_queries, 128, (size_t)2 * kp * 8, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), nullptr, 1, n_lists,
+                                                               (unsigned long long)n_queries * k, n_queries, k, kp,
+                                                               reinterpret_cast<unsigned long long*>(d_out_keys));
     CU(cudaGetLastError());
   }
   return 0;

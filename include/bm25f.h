@@ -81,10 +81,12 @@ typedef struct {
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
   uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 32, <= 8 leaves, positive
-                                    weights, no paging bound - flat ORs on warp streams and ANDs on warp
-                                    teams; else the bulk-copy pipeline),
+                                    weights, no paging bound - flat ORs on warp streams, ANDs whose smallest
+                                    group is far sparser than the rest by candidate-driven lookups, other
+                                    ANDs on warp teams; else the bulk-copy pipeline),
                                     1 = bulk-copy pipeline, 2 = direct loads, 3 = warp streams,
-                                    4 = warp teams (same eligibility as 3) */
+                                    4 = warp teams (same eligibility as 3),
+                                    5 = candidate-driven lookups for every eligible query (<= 32 leaves) */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
   uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
@@ -99,6 +101,11 @@ typedef struct {
   uint32_t cta_split;            /* team kernel: target work (posting-equivalents) per work item */
   uint32_t cta_slice_docs;       /* team kernel: documents per warp-private slice of a flat OR (AND: half);
                                     multiple of 128 */
+  uint32_t isect_ratio;          /* candidate-driven AND: used when (postings of the smallest group) x
+                                    (leaves - 1) x isect_ratio < postings of the query; default 1 */
+  uint32_t isect_split;          /* candidate-driven AND: target candidates per work item; default 2048 */
+  uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
+                                    below this (0xFFFFFFFF = never) */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

@@ -116,6 +116,26 @@ def test_team_kernel(cfg1, subtile, warps, split, pf, mode):
     assert_batch_parity(o, qs.queries[:60], res, 32)
 
 
+@pytest.mark.parametrize("split,ratio", [(0, 0), (64, 1), (1 << 20, 1000)])
+@pytest.mark.parametrize("mode", ["mixed", "variants", "or", "and"])
+def test_isect_kernel(cfg1, split, ratio, mode):
+    """Candidate-driven kernel forced for every eligible query (variant 5): flat ORs (every leaf is a
+    candidate leaf, duplicates dropped), ANDs, AND-of-OR groups; tiny items (document ranges that start
+    inside lists); and the auto routing with extreme ratios (everything / nothing goes to it)."""
+    ix, o = cfg1
+    if mode == "variants":
+        qs = make_queries(150, 50_000, 31, 4, 4, "and", variants=True, skip_top=0)
+    else:
+        qs = make_queries(300, 50_000, 78, 1, 4, mode, skip_top=0)
+    for variant in (5, 0):
+        with ix.searcher(variant=variant, isect_split=split, isect_ratio=ratio) as s:
+            res = s.search_batch(qs.queries, limit=10)
+        assert_batch_parity(o, qs.queries, res, 10)
+    with ix.searcher(variant=5, isect_split=split) as s:
+        res = s.search_batch(qs.queries[:60], limit=32)
+    assert_batch_parity(o, qs.queries[:60], res, 32)
+
+
 @pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])
 def test_limits(cfg1, k):
     ix, o = cfg1
