@@ -48,7 +48,7 @@ class Options(C.Structure):
                 ("subtile_docs", C.c_uint32), ("warp_split", C.c_uint32), ("stream_warps", C.c_uint32),
                 ("prefetch_postings", C.c_uint32), ("cta_warps", C.c_uint32), ("cta_prefetch", C.c_uint32),
                 ("cta_split", C.c_uint32), ("cta_slice_docs", C.c_uint32), ("isect_ratio", C.c_uint32),
-                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32)]
+                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("or1_ratio", C.c_uint32), ("hash_split", C.c_uint32)]
 
 
 class QueryBatchDesc(C.Structure):
@@ -194,14 +194,14 @@ class Engine:
     def __init__(self, ix, device: int = 0, tile_docs: int = 0, threads: int = 0, split_postings: int = 0,
                  variant: int = 0, chunk_postings: int = 0, stages: int = 0, subtile_docs: int = 0,
                  warp_split: int = 0, stream_warps: int = 0, prefetch_postings: int = 0, cta_warps: int = 0,
-                 cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0):
+                 cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0, or1_ratio: int = 0, hash_split: int = 0):
         self.lib = load_library()
         self._h = None
         desc = IndexDesc(ABI_VERSION, len(ix.field_names), ix.n_docs_all, ix.n_terms, ix.n_postings, ix.doc_base,
                          _ptr(ix.term_offsets), _ptr(ix.term_field), _ptr(ix.docids), _ptr(ix.tfs),
                          _ptr(ix.len_bytes), _ptr(ix.deleted))
         opts = Options(tile_docs, threads, split_postings, variant, chunk_postings, stages, subtile_docs,
-                       warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit)
+                       warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit, or1_ratio, hash_split)
         h = C.c_void_p()
         _check(self.lib, self.lib.bm25f_create(C.byref(desc), device, C.byref(opts), C.byref(h)))
         self._h = h

@@ -78,6 +78,7 @@ struct ItemRec {            // 16 B
 };
 
 constexpr uint32_t QF_SIMPLE_OR = 1u;
+constexpr uint32_t QF_STREAM_LAST = 2u;   // one-dense OR: the last leaf is looked up, then streamed (k_score_isect)
 constexpr int MAXL = BM25F_MAX_LEAVES_PER_QUERY;
 
 // W11 order as one unsigned 64-bit key: score descending, docnum ascending.  All keys of
@@ -944,6 +945,7 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
 #include "stream.cuh"
 #include "team.cuh"
 #include "isect.cuh"
+#include "hash.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -1080,7 +1082,9 @@ struct bm25f_handle {
   int ctas_per_sm = 0;
   int tl_ctas_per_sm = 0;
   int is_ctas_per_sm = 0;
-  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 16000;   // candidate-driven AND: cost of a lookup in postings, candidates per item
+  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000, is_or1_ratio = 0;
+  uint32_t hs_split = 1u << 16;   // hash OR: target work (posting-equivalents) per item
+  int hs_ctas_per_sm = 0;   // candidate-driven AND: cost of a lookup in postings, candidates per item
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
   cudaEvent_t ev[EV_RING][4] = {};
   int ev_head = 0;                     // next slot to use
@@ -1101,7 +1105,11 @@ struct bm25f_plan {
   uint32_t n_w4 = 0, n_w8 = 0;            // stream-kernel items / team-kernel items; the rest are CTA items
   ItemRec* d_items_w4 = nullptr;
   ItemRec* d_items_w8 = nullptr;
-  uint32_t n_is = 0;                      // candidate-driven AND items
+  uint32_t n_hs = 0;                      // hash OR items
+  ItemRec* d_items_hs = nullptr;
+  uint32_t n_is = 0;                      // candidate-driven items
+  unsigned int* d_taken = nullptr;        // one-dense ORs: bitmaps over the dense leaves' postings
+  uint64_t taken_words = 0;
   ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
@@ -1273,9 +1281,11 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   if (opts) {
     if (opts->isect_ratio) h->is_ratio = opts->isect_ratio;
     if (opts->isect_split) h->is_split = opts->isect_split;
+    if (opts->or1_ratio) h->is_or1_ratio = opts->or1_ratio;
+    if (opts->hash_split) h->hs_split = opts->hash_split;
     if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
   }
-  if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
+  if (h->variant > 7) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams), 5 (candidate-driven), 6 (one-dense OR by lookups) or 7 (one-dense OR by hashing)"); }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
   if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
@@ -1529,6 +1539,7 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_scores);
   cudaFree(p->d_docids);
   cudaFree(p->d_counts);
+  cudaFree(p->d_taken);
   delete p;
 }
 
@@ -1597,14 +1608,15 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     queries = own_queries.data();
   }
 
-  std::vector<ItemRec> items[4];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven AND
-  std::vector<uint64_t> item_w[4];
+  std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR
+  std::vector<uint64_t> item_w[5];
   items[0].reserve(Q * 2);
   item_w[0].reserve(Q * 2);
   uint64_t postings = 0;
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
+  uint64_t taken_words = 0;   // one-dense ORs: words of "taken" bitmaps
 
   for (uint32_t qi = 0; qi < Q; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -1679,24 +1691,50 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant == 3 || h->variant == 4 || h->variant == 5) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
     // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
     // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
     // ... unless its smallest group is so much sparser than the rest that looking its documents up in
     // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
     const uint64_t g0 = gsize[order[0]];
     const bool isect_ok = k <= 32 && nlq <= 32 && all_pos && qr.after_key == 0ull;
-    // A flat OR with few postings is also cheaper that way (every posting is a candidate and is still
-    // read exactly once; sweeping every sub-range of the document space for it is what costs).
-    const bool use_isect = isect_ok && (h->variant == 5 || (h->variant == 0 &&
+    // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
+    // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
+    uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
+    bool use_or1 = false;
+    bool use_hash = false;
+    if ((qr.flags & QF_SIMPLE_OR) && isect_ok && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
+      uint32_t imax = 0;
+      for (uint32_t i = 1; i < nlq; ++i)
+        if (leaves[out_leaf - nlq + i].df > leaves[out_leaf - nlq + imax].df) imax = i;
+      const uint64_t dmax = leaves[out_leaf - nlq + imax].df;
+      const uint64_t rest = P - dmax;
+      if (h->variant == 6 || h->variant == 7 || (h->is_or1_ratio && rest * h->is_or1_ratio < P)) {
+        std::swap(leaves[out_leaf - nlq + imax], leaves[out_leaf - 1]);     // the dense leaf goes last
+        qr.flags |= QF_STREAM_LAST;
+        if (h->variant == 6) {
+          // lookups + "taken" bitmap (k_score_isect)
+          use_or1 = true;
+          qr.after_key = taken_words;               // word offset of this query's bitmap
+          taken_words += (dmax + 31) / 32 + 1;
+          n_cand = rest * (uint64_t)(nlq > 1 ? nlq - 1 : 1) + dmax / 16;   // work, in candidate lookups
+        } else {
+          // per-warp hash table for the other leaves' documents (k_score_hash)
+          use_hash = true;
+          n_cand = rest * 4 + dmax / 2;             // work, in posting-equivalents
+        }
+      }
+    }
+    // A flat OR with few postings is also cheaper the candidate-driven way (every posting is a candidate
+    // and is still read exactly once; sweeping every sub-range of the document space is what costs).
+    const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
-                                   : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
-    const uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P : g0;
-    const bool use_team = !use_isect && stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
-    const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
+                                   : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
+    const bool use_team = !use_isect && !use_hash && stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const int cls = use_hash ? 4 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
-    if (use_isect) {
-      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + h->is_split / 2) / h->is_split));
+    if (use_hash) {
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 4096), std::max<uint64_t>(1, (n_cand + h->hs_split / 2) / h->hs_split));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
         ItemRec it;
@@ -1705,7 +1743,19 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
         it.part = n_parts + s;
         items[cls].push_back(it);
-        item_w[cls].push_back(n_cand * (uint64_t)(nlq > 1 ? nlq - 1 : 1) / nsplit + 64);
+        item_w[cls].push_back(n_cand / nsplit + 64);
+      }
+    } else if (use_isect) {
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + h->is_split) / (2ull * h->is_split)));
+      qr.n_parts = nsplit;
+      for (uint32_t s = 0; s < nsplit; ++s) {
+        ItemRec it;
+        it.q = qi;
+        it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
+        it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
+        it.part = n_parts + s;
+        items[cls].push_back(it);
+        item_w[cls].push_back(n_cand / nsplit + 64);
       }
     } else if (use_team) {
       // warp teams: an item is a document range; its slices are handed out inside the CTA
@@ -1769,6 +1819,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_w4 = (uint32_t)items[0].size();
   p->n_w8 = (uint32_t)items[1].size();
   p->n_is = (uint32_t)items[3].size();
+  p->n_hs = (uint32_t)items[4].size();
+  p->taken_words = taken_words;
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
@@ -1790,7 +1842,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }                                                                   \
   } while (0)
   const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
-  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs;
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
   if (use_arena) {
@@ -1818,14 +1870,16 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   order_items(items[0], item_w[0], h_items + p->n_items);
   order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
   order_items(items[3], item_w[3], h_items + p->n_items + p->n_w4 + p->n_w8);
+  order_items(items[4], item_w[4], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is);
 
   if (use_arena) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
     const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
-                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 3) * 8),
-                 o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4);
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 4) * 8),
+                 o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
+                 o_taken = take((size_t)(taken_words + 1) * 4);
     if (off > h->d_arena_cap) {
       CUP(cudaStreamSynchronize(h->stream));
       cudaFree(h->d_arena);
@@ -1847,6 +1901,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     p->d_scores = reinterpret_cast<float*>(d + o_sc);
     p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
     p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
+    p->d_taken = reinterpret_cast<unsigned int*>(d + o_taken);
   } else {
     RCP(dev_alloc(&p->d_leaves, out_leaf));
     RCP(dev_alloc(&p->d_queries, Q));
@@ -1854,14 +1909,16 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
     RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, (size_t)Q + 3));
+    RCP(dev_alloc(&p->d_totals, (size_t)Q + 4));
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
+    RCP(dev_alloc(&p->d_taken, (size_t)taken_words + 1));
   }
   p->d_items_w4 = p->d_items + p->n_items;
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
   p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
+  p->d_items_hs = p->d_items_is + p->n_is;
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
   if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
@@ -1893,7 +1950,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   cudaEvent_t* ev = h->ev[h->ev_head];
   CU(cudaEventRecord(ev[0], st));
-  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 3) * 8, st));   // totals + the three work counters
+  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 4) * 8, st));   // totals + the four work counters
+  if (p->taken_words) CU(cudaMemsetAsync(p->d_taken, 0, (size_t)p->taken_words * 4, st));
   const unsigned long long nb = p->n_items ? (unsigned long long)p->n_leaves * (p->T + 1) : 0ull;
   if (nb) {
     k_tile_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(p->d_leaves, p->n_leaves, p->T, h->S, h->d_docids, p->d_bounds);
@@ -1901,7 +1959,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is) {
+  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_hs) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -1923,11 +1981,34 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.prof = h->d_prof;
     // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
     // registers) fit on an SM together and stall on different things: launch them side by side.
-    const bool side = p->n_w4 && (p->n_is || p->n_w8);
+    const bool side = (p->n_w4 || p->n_hs) && (p->n_is || p->n_w8);
     cudaStream_t ax = side ? h->aux_stream : st;
     if (side) {
       CU(cudaEventRecord(h->ev_fork, st));
       CU(cudaStreamWaitEvent(ax, h->ev_fork, 0));
+    }
+    if (p->n_hs) {
+      HashParams hp;
+      hp.pairs = h->d_pairs;
+      hp.leaves = p->d_leaves;
+      hp.queries = p->d_queries;
+      hp.items = p->d_items_hs;
+      hp.part_keys = p->d_part_keys;
+      hp.totals = p->d_totals;
+      hp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 3);
+      hp.n_items = p->n_hs;
+      hp.doc_base = (uint32_t)h->doc_base;
+      hp.n_docs = (uint32_t)h->n_docs;
+      hp.k = p->k;
+      if (h->hs_ctas_per_sm == 0) {
+        int nb_ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_hash, HS_WARPS * 32, 0));
+        h->hs_ctas_per_sm = std::max(1, nb_);
+      }
+      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->hs_ctas_per_sm), (p->n_hs + HS_WARPS - 1) / HS_WARPS);
+      k_score_hash<<<grid, HS_WARPS * 32, 0, st>>>(hp);
+      CU(cudaGetLastError());
+      ++launches;
     }
     if (p->n_w4) {
       StreamParams stp;
@@ -1957,6 +2038,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.part_keys = p->d_part_keys;
       ip.totals = p->d_totals;
       ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 2);
+      ip.taken = p->d_taken;
       ip.n_items = p->n_is;
       ip.doc_base = (uint32_t)h->doc_base;
       ip.k = p->k;
@@ -2031,7 +2113,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
   h->stats.postings_touched = p->postings;
-  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;

@@ -190,7 +190,7 @@ class Searcher:
     def __init__(self, ix, weighting=None, device: int = 0, tile_docs: int = 0, threads: int = 0,
                  split_postings: int = 0, stats_ix=None, variant: int = 0, chunk_postings: int = 0,
                  stages: int = 0, subtile_docs: int = 0, warp_split: int = 0, stream_warps: int = 0,
-                 prefetch_postings: int = 0, cta_warps: int = 0, cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0):
+                 prefetch_postings: int = 0, cta_warps: int = 0, cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0, or1_ratio: int = 0, hash_split: int = 0):
         self.ix = ix
         #: index the corpus statistics come from (the whole corpus when ``ix`` is a shard, W8)
         self.stats_ix = stats_ix or ix
@@ -200,7 +200,7 @@ class Searcher:
         self.device = device
         self.ixreader = self.stats_ix.reader()
         key = (device, tile_docs, threads, split_postings, variant, chunk_postings, stages, subtile_docs,
-               warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit)
+               warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit, or1_ratio, hash_split)
         eng = ix._engine_cache.get(key)
         if eng is None:
             eng = _ffi.Engine(ix, device=device, tile_docs=tile_docs, threads=threads,
@@ -209,7 +209,7 @@ class Searcher:
                               warp_split=warp_split, stream_warps=stream_warps,
                               prefetch_postings=prefetch_postings, cta_warps=cta_warps,
                               cta_prefetch=cta_prefetch, cta_split=cta_split, cta_slice_docs=cta_slice_docs, isect_ratio=isect_ratio,
-                              isect_split=isect_split, isect_or_limit=isect_or_limit)
+                              isect_split=isect_split, isect_or_limit=isect_or_limit, or1_ratio=or1_ratio, hash_split=hash_split)
             ix._engine_cache[key] = eng
         self.engine = eng
         wkey = self.weighting.key() + (self.stats_ix.doc_count_all(),)

@@ -86,7 +86,9 @@ typedef struct {
                                     ANDs on warp teams; else the bulk-copy pipeline),
                                     1 = bulk-copy pipeline, 2 = direct loads, 3 = warp streams,
                                     4 = warp teams (same eligibility as 3),
-                                    5 = candidate-driven lookups for every eligible query (<= 32 leaves) */
+                                    5 = candidate-driven lookups for every eligible query (<= 32 leaves),
+                                    6 = as 0 but every eligible flat OR scored one-dense by lookups,
+                                    7 = as 0 but every eligible flat OR scored one-dense by hashing */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
   uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
@@ -106,6 +108,11 @@ typedef struct {
   uint32_t isect_split;          /* candidate-driven AND: target candidates per work item; default 2048 */
   uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
                                     below this (0xFFFFFFFF = never) */
+  uint32_t or1_ratio;            /* experimental: a flat OR is scored "one-dense" (densest leaf streamed without
+                                    accumulators, the others accumulated in a per-warp hash table) when (postings
+                                    of the other leaves) x or1_ratio < postings of the query; 0 = never (default:
+                                    measured slower than the stream kernel) */
+  uint32_t hash_split;           /* one-dense OR: target work (posting-equivalents) per work item */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

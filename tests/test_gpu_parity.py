@@ -127,13 +127,28 @@ def test_isect_kernel(cfg1, split, ratio, mode):
         qs = make_queries(150, 50_000, 31, 4, 4, "and", variants=True, skip_top=0)
     else:
         qs = make_queries(300, 50_000, 78, 1, 4, mode, skip_top=0)
-    for variant in (5, 0):
-        with ix.searcher(variant=variant, isect_split=split, isect_ratio=ratio) as s:
+    for variant in (5, 0, 6, 7):
+        with ix.searcher(variant=variant, isect_split=split, isect_ratio=ratio, or1_ratio=ratio, hash_split=split) as s:
             res = s.search_batch(qs.queries, limit=10)
         assert_batch_parity(o, qs.queries, res, 10)
-    with ix.searcher(variant=5, isect_split=split) as s:
-        res = s.search_batch(qs.queries[:60], limit=32)
-    assert_batch_parity(o, qs.queries[:60], res, 32)
+    for variant in (5, 6, 7):
+        with ix.searcher(variant=variant, isect_split=split, hash_split=split) as s:
+            res = s.search_batch(qs.queries[:60], limit=32)
+        assert_batch_parity(o, qs.queries[:60], res, 32)
+
+
+def test_one_dense_or_single_terms_and_skew(cfg1):
+    """One-dense OR: single-term queries (pure accumulator-free streaming), a dense term with rare
+    ones, repeated documents across the rare leaves, many items per query."""
+    ix, o = cfg1
+    qs = [Term("body", 1), Term("body", 3), Term("body", 40000), Or([Term("body", 1), Term("body", 900), Term("body", 901)]),
+          Or([Term("body", 2), Term("body", 30), Term("body", 31), Term("body", 32)]), Or([Term("body", 5), Term("body", 5000)]),
+          Or([Term("body", 1), Term("body", 2)]), Or([Term("body", 7), Term("body", 49999), Term("body", 12345)])]
+    for variant in (6, 7):
+        for split in (0, 64):
+            with ix.searcher(variant=variant, isect_split=split, hash_split=split) as s:
+                res = s.search_batch(qs, limit=10)
+            assert_batch_parity(o, qs, res, 10)
 
 
 @pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])

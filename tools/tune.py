@@ -48,12 +48,12 @@ def main():
             qsets[m] = make_queries(nq, c["vocab"], 20261000 + args.config, c["min_terms"], c["max_terms"], m).queries
     k = c["k"]
     for opt in args.opts:
-        f = [int(x) for x in opt.split(":")] + [0] * 17
-        S, NT, split, variant, chunk, stages, sw, wsplit, swarps, pf, cw, ct, cs, csd, isr, iss, iso = f[:17]
+        f = [int(x) for x in opt.split(":")] + [0] * 19
+        S, NT, split, variant, chunk, stages, sw, wsplit, swarps, pf, cw, ct, cs, csd, isr, iss, iso, o1, hsp = f[:19]
         ix._engine_cache.clear()
         s = Searcher(ix, weighting=BM25F, tile_docs=S, threads=NT, split_postings=split, variant=variant,
                      chunk_postings=chunk, stages=stages, subtile_docs=sw, warp_split=wsplit,
-                     stream_warps=swarps, prefetch_postings=pf, cta_warps=cw, cta_prefetch=ct, cta_split=cs, cta_slice_docs=csd, isect_ratio=isr, isect_split=iss, isect_or_limit=iso)
+                     stream_warps=swarps, prefetch_postings=pf, cta_warps=cw, cta_prefetch=ct, cta_split=cs, cta_slice_docs=csd, isect_ratio=isr, isect_split=iss, isect_or_limit=iso, or1_ratio=o1, hash_split=hsp)
         eng = s.engine
         for m, queries in qsets.items():
             batch = s.pack(queries)
