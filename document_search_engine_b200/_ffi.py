@@ -61,7 +61,9 @@ class Stats(C.Structure):
     _fields_ = [("postings_touched", C.c_uint64), ("n_items", C.c_uint64), ("n_launches", C.c_uint64),
                 ("n_executes", C.c_uint64), ("ms_bounds", C.c_float), ("ms_score", C.c_float), ("ms_merge", C.c_float), ("ms_total", C.c_float),
                 ("tile_docs", C.c_uint32), ("threads", C.c_uint32), ("ctas_per_sm", C.c_uint32),
-                ("packed_payload", C.c_uint32), ("device_bytes", C.c_uint64)]
+                ("packed_payload", C.c_uint32), ("device_bytes", C.c_uint64), ("postings_stream", C.c_uint64),
+                ("postings_team", C.c_uint64), ("postings_cta", C.c_uint64), ("postings_lookup", C.c_uint64),
+                ("postings_hash", C.c_uint64), ("ms_stream", C.c_float), ("reserved", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

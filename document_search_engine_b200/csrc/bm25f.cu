@@ -1073,7 +1073,7 @@ struct bm25f_handle {
   uint32_t S = 8192, NT = 256, split = 1u << 16;
   uint32_t variant = 0;               // 0 / 3: auto (stream kernel where eligible, else pipeline), 1: pipeline, 2: direct loads
   // stream kernel: warps per CTA, accumulator bytes per warp, target work per item, L2 prefetch distance
-  uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 17, st_pf = 2048;
+  uint32_t st_warps = 16, st_slot_bytes = 9216, wsplit = 1u << 17, st_pf = 2048;
   // team kernel (variant 4): warps per CTA, target work per item, slices ahead to prefetch
   uint32_t tl_warps = 8, tl_slot_bytes = 10240, tl_split = 1u << 18, tl_prefetch = 0;
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
@@ -1086,7 +1086,7 @@ struct bm25f_handle {
   uint32_t hs_split = 1u << 16;   // hash OR: target work (posting-equivalents) per item
   int hs_ctas_per_sm = 0;   // candidate-driven AND: cost of a lookup in postings, candidates per item
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
-  cudaEvent_t ev[EV_RING][4] = {};
+  cudaEvent_t ev[EV_RING][6] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone
   int ev_head = 0;                     // next slot to use
   int ev_pending = 0;                  // slots recorded but not yet folded into the stats
   bm25f_stats stats{};
@@ -1113,6 +1113,7 @@ struct bm25f_plan {
   ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
+  uint64_t postings_cls[5] = {0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, hash
   LeafRec* d_leaves = nullptr;
   QueryRec* d_queries = nullptr;
   ItemRec* d_items = nullptr;
@@ -1186,6 +1187,9 @@ int fold_events(bm25f_handle* h, int n) {
     CU(cudaEventElapsedTime(&b, e[1], e[2]));
     CU(cudaEventElapsedTime(&c, e[2], e[3]));
     CU(cudaEventElapsedTime(&d, e[0], e[3]));
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, e[4], e[5]));
+    h->stats.ms_stream += f;
     h->stats.ms_bounds += a;
     h->stats.ms_score += b;
     h->stats.ms_merge += c;
@@ -1617,6 +1621,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   bool any_nonpos = false;
   uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
   uint64_t taken_words = 0;   // one-dense ORs: words of "taken" bitmaps
+  uint64_t cls_postings[5] = {0, 0, 0, 0, 0};
 
   for (uint32_t qi = 0; qi < Q; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -1802,6 +1807,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
       }
     }
+    cls_postings[cls] += P;
     n_parts += nsplit;
   }
 
@@ -1824,6 +1830,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
+  for (int c = 0; c < 5; ++c) p->postings_cls[c] = cls_postings[c];
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
 
@@ -2025,7 +2032,9 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       stp.slot_bytes = h->st_slot_bytes;
       stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
       const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
+      CU(cudaEventRecord(ev[4], st));
       k_score_stream<<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      CU(cudaEventRecord(ev[5], st));
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2100,6 +2109,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ++launches;
     }
   }
+  if (!p->n_w4) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventRecord(ev[5], st)); }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q) {
     if (p->k <= 32) k_merge_topk_warp<<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->d_keys);
@@ -2113,6 +2123,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
   h->stats.postings_touched = p->postings;
+  h->stats.postings_stream = p->postings_cls[0];
+  h->stats.postings_team = p->postings_cls[1];
+  h->stats.postings_cta = p->postings_cls[2];
+  h->stats.postings_lookup = p->postings_cls[3];
+  h->stats.postings_hash = p->postings_cls[4];
   h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
@@ -2235,7 +2250,7 @@ int bm25f_reset_stats(bm25f_handle* h) {
     cudaMemset(h->d_prof, 0, sizeof v);
   }
 #endif
-  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = 0.0f;
+  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = h->stats.ms_stream = 0.0f;
   h->stats.n_executes = 0;
   return 0;
 }

@@ -47,7 +47,7 @@ constexpr int IS_WARPS = 8;
 
 // Requires: k <= 32, <= 32 leaves, <= 32 groups, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store.
-__global__ void __launch_bounds__(IS_WARPS * 32) k_score_isect(IsectParams ip) {
+__global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip) {
   const int lane = threadIdx.x & 31;
   const uint2* __restrict__ store = ip.pairs;
 

@@ -143,6 +143,15 @@ typedef struct {
   uint32_t ctas_per_sm;
   uint32_t packed_payload;       /* 1: (tf,lb) packed in 32 bits; 0: float tf + length byte */
   uint64_t device_bytes;         /* device memory held by the index */
+  /* last execute, algorithmic postings (sum of live df over leaves) per kernel class: */
+  uint64_t postings_stream;      /* k_score_stream: every posting is read and accumulated */
+  uint64_t postings_team;        /* k_score_team: every posting of the slices not skipped is read */
+  uint64_t postings_cta;         /* k_score_pipe / k_score_topk */
+  uint64_t postings_lookup;      /* k_score_isect: postings of the smallest group are read, the other lists are
+                                    searched (skip_to), so most of these postings are NOT read */
+  uint64_t postings_hash;        /* k_score_hash (experimental) */
+  float    ms_stream;            /* summed device time of k_score_stream alone (it overlaps k_score_isect) */
+  uint32_t reserved;
 } bm25f_stats;
 
 int  bm25f_abi_version(void);
