@@ -16,12 +16,17 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -1052,7 +1057,68 @@ __global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint3
 
 // ==========================================================================================
 // Host side
+
 // ==========================================================================================
+
+// A few persistent host threads for query planning (creating threads per call costs more than the work).
+class PlanPool {
+ public:
+  explicit PlanPool(unsigned n) {
+    for (unsigned i = 0; i < n; ++i) workers_.emplace_back([this, i] { run(i); });
+  }
+  ~PlanPool() {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      stop_ = true;
+      ++gen_;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  unsigned size() const { return (unsigned)workers_.size(); }
+  // run fn(i) for i in [0, n) on the workers (n <= size()) and wait
+  void parallel(unsigned n, const std::function<void(unsigned)>& fn) {
+    {
+      std::lock_guard<std::mutex> g(m_);
+      fn_ = &fn;
+      n_ = n;
+      pending_ = n;
+      ++gen_;
+    }
+    cv_.notify_all();
+    std::unique_lock<std::mutex> g(m_);
+    done_.wait(g, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run(unsigned i) {
+    unsigned long long seen = 0;
+    for (;;) {
+      const std::function<void(unsigned)>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        if (i < n_) fn = fn_;
+      }
+      if (fn) {
+        (*fn)(i);
+        std::lock_guard<std::mutex> g(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(unsigned)>* fn_ = nullptr;
+  unsigned n_ = 0, pending_ = 0;
+  unsigned long long gen_ = 0;
+  bool stop_ = false;
+};
+
 struct bm25f_handle {
   int device = 0;
   cudaStream_t stream = nullptr;      // stream in use
@@ -1097,6 +1163,7 @@ struct bm25f_handle {
   size_t d_arena_cap = 0;
   unsigned char* h_arena = nullptr;       // pinned
   size_t h_arena_cap = 0;
+  PlanPool* pool = nullptr;              // created on the first large batch
 };
 
 struct bm25f_plan {
@@ -1226,6 +1293,7 @@ void bm25f_destroy(bm25f_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h->pool;
   delete h;
 }
 
@@ -1612,30 +1680,41 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     queries = own_queries.data();
   }
 
-  std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR
-  std::vector<uint64_t> item_w[5];
-  items[0].reserve(Q * 2);
-  item_w[0].reserve(Q * 2);
-  uint64_t postings = 0;
-  uint32_t n_parts = 0;
-  bool any_nonpos = false;
-  uint32_t out_leaf = 0;   // leaves are compacted: unknown / empty lists are dropped where that is exact
-  uint64_t taken_words = 0;   // one-dense ORs: words of "taken" bitmaps
-  uint64_t cls_postings[5] = {0, 0, 0, 0, 0};
-
-  for (uint32_t qi = 0; qi < Q; ++qi) {
+  // Planning is per query and independent: ranges of queries are planned by a few host threads (each
+  // into its own item lists and counters), then stitched together.  A query's leaf records live at
+  // the positions of its input leaves, so no thread needs another's running totals.
+  struct PlanLocal {
+    std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR
+    std::vector<uint64_t> item_w[5];
+    uint64_t postings = 0, taken_words = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+    uint32_t n_parts = 0;
+    bool any_nonpos = false;
+    int rc = 0;
+    char err[256] = {0};
+  };
+#define PFAIL(code, ...)                                   \
+  do {                                                     \
+    L.rc = (code);                                         \
+    snprintf(L.err, sizeof L.err, __VA_ARGS__);            \
+    return;                                                \
+  } while (0)
+  auto dummy_leaves = [&](uint32_t a, uint32_t e) {
+    for (uint32_t i = a; i < e; ++i) { leaves[i] = LeafRec{}; leaves[i].qleaf0 = i; leaves[i].qnl = 1; }
+  };
+  auto plan_range = [&](uint32_t q_begin, uint32_t q_end, PlanLocal& L) {
+    for (uint32_t qi = q_begin; qi < q_end; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
-    if (e < a || e > NL) return fail(BM25F_EINVAL, "query %u: bad leaf range", qi);
+    if (e < a || e > NL) PFAIL(BM25F_EINVAL, "query %u: bad leaf range", qi);
     const uint32_t nl = e - a;
     const uint32_t G = b->query_n_groups[qi];
     QueryRec& qr = queries[qi];
     qr = QueryRec{};
     qr.after_key = b->after_keys ? b->after_keys[qi] : 0ull;
-    qr.leaf_begin = out_leaf;
-    qr.part_begin = n_parts;
-    if (nl > (uint32_t)MAXL) return fail(BM25F_EINVAL, "query %u has %u leaves (max %d)", qi, nl, MAXL);
-    if (G > 32) return fail(BM25F_EINVAL, "query %u has %u groups (max 32)", qi, G);
-    if (G == 0 || nl == 0) continue;   // null query
+    qr.leaf_begin = a;
+    qr.part_begin = L.n_parts;
+    if (nl > (uint32_t)MAXL) PFAIL(BM25F_EINVAL, "query %u has %u leaves (max %d)", qi, nl, MAXL);
+    if (G > 32) PFAIL(BM25F_EINVAL, "query %u has %u groups (max 32)", qi, G);
+    if (G == 0 || nl == 0) { dummy_leaves(a, e); continue; }   // null query
 
     // per-group size; validates group ordering
     uint64_t gsize[32];
@@ -1645,21 +1724,21 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     bool all_pos = true;
     for (uint32_t i = a; i < e; ++i) {
       const uint32_t g = b->leaf_group[i];
-      if (g >= G || g < prev_g) return fail(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
+      if (g >= G || g < prev_g) PFAIL(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
       prev_g = g;
       gseen[g] = true;
       const uint32_t term = b->leaf_term[i];
       if (term != BM25F_TERM_UNKNOWN) {
-        if (term >= h->n_terms) return fail(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, term);
+        if (term >= h->n_terms) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, term);
         gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
       }
       if (!(b->leaf_weight[i] > 1e-30f)) all_pos = false;
-      if (!std::isfinite(b->leaf_weight[i])) return fail(BM25F_EINVAL, "query %u: leaf weight is not finite", qi);
+      if (!std::isfinite(b->leaf_weight[i])) PFAIL(BM25F_EINVAL, "query %u: leaf weight is not finite", qi);
     }
     bool dead = false;
     for (uint32_t g = 0; g < G; ++g)
       if (!gseen[g] || gsize[g] == 0) dead = true;   // an empty group: the AND matches nothing (W10)
-    if (dead) continue;
+    if (dead) { dummy_leaves(a, e); continue; }
 
     // smallest group first: it defines the candidate set, later groups only filter it
     uint32_t order[32], rank[32];
@@ -1675,24 +1754,25 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         if (term == BM25F_TERM_UNKNOWN) continue;
         const uint64_t off = h->term_offsets[term], df = h->term_offsets[term + 1] - off;
         if (df == 0) continue;
-        LeafRec& lf = leaves[out_leaf + nlq];
+        LeafRec& lf = leaves[a + nlq];
         lf.off = off;
         lf.df = (uint32_t)df;
         lf.w = b->leaf_weight[i];
         lf.norm_off = (uint32_t)h->term_field[term] * 256u;
         lf.group = rank[b->leaf_group[i]];
-        lf.qleaf0 = out_leaf;
+        lf.qleaf0 = a;
         P += df;
         ++nlq;
       }
     }
-    for (uint32_t i = 0; i < nlq; ++i) leaves[out_leaf + i].qnl = nlq;
+    for (uint32_t i = 0; i < nlq; ++i) leaves[a + i].qnl = nlq;
+    for (uint32_t i = a + nlq; i < e; ++i) { leaves[i] = LeafRec{}; leaves[i].qleaf0 = i; leaves[i].qnl = 1; }   // unused slots stay harmless
     qr.n_leaves = nlq;
     qr.n_groups = G;
     qr.flags = (G == 1 && all_pos) ? QF_SIMPLE_OR : 0u;
-    if (!all_pos) any_nonpos = true;
-    out_leaf += nlq;
-    postings += P;
+    if (!all_pos) L.any_nonpos = true;
+    const uint32_t out_leaf = a + nlq;   // one past the query's last leaf record
+    L.postings += P;
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
@@ -1720,8 +1800,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         if (h->variant == 6) {
           // lookups + "taken" bitmap (k_score_isect)
           use_or1 = true;
-          qr.after_key = taken_words;               // word offset of this query's bitmap
-          taken_words += (dmax + 31) / 32 + 1;
+          qr.after_key = L.taken_words;               // word offset of this query's bitmap
+          L.taken_words += (dmax + 31) / 32 + 1;
           n_cand = rest * (uint64_t)(nlq > 1 ? nlq - 1 : 1) + dmax / 16;   // work, in candidate lookups
         } else {
           // per-warp hash table for the other leaves' documents (k_score_hash)
@@ -1730,7 +1810,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         }
       }
     }
-    // A flat OR with few postings is also cheaper the candidate-driven way (every posting is a candidate
+    // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
     const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
@@ -1746,9 +1826,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.q = qi;
         it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
         it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
-        it.part = n_parts + s;
-        items[cls].push_back(it);
-        item_w[cls].push_back(n_cand / nsplit + 64);
+        it.part = L.n_parts + s;
+        L.items[cls].push_back(it);
+        L.item_w[cls].push_back(n_cand / nsplit + 64);
       }
     } else if (use_isect) {
       nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + h->is_split) / (2ull * h->is_split)));
@@ -1758,9 +1838,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.q = qi;
         it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
         it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
-        it.part = n_parts + s;
-        items[cls].push_back(it);
-        item_w[cls].push_back(n_cand / nsplit + 64);
+        it.part = L.n_parts + s;
+        L.items[cls].push_back(it);
+        L.item_w[cls].push_back(n_cand / nsplit + 64);
       }
     } else if (use_team) {
       // warp teams: an item is a document range; its slices are handed out inside the CTA
@@ -1774,9 +1854,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.q = qi;
         it.tile_begin = (uint32_t)((nsl * s / nsplit) * sw);                    // document range [lo, hi), slice-aligned
         it.tile_end = (uint32_t)std::min<uint64_t>(h->n_docs, (nsl * (s + 1) / nsplit) * sw);
-        it.part = n_parts + s;
-        items[cls].push_back(it);
-        item_w[cls].push_back(work / nsplit);
+        it.part = L.n_parts + s;
+        L.items[cls].push_back(it);
+        L.item_w[cls].push_back(work / nsplit);
       }
     } else if (stream_ok) {
       // cost model in posting-equivalents: every (sub-range, leaf) visit costs a fixed amount
@@ -1790,9 +1870,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.q = qi;
         it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
         it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
-        it.part = n_parts + s;
-        items[cls].push_back(it);
-        item_w[cls].push_back(work / nsplit);
+        it.part = L.n_parts + s;
+        L.items[cls].push_back(it);
+        L.item_w[cls].push_back(work / nsplit);
       }
     } else {
       nsplit = (uint32_t)std::min<uint64_t>(T, std::max<uint64_t>(1, (P + h->split / 2) / h->split));
@@ -1802,14 +1882,64 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         it.q = qi;
         it.tile_begin = (uint32_t)((uint64_t)T * s / nsplit);
         it.tile_end = (uint32_t)((uint64_t)T * (s + 1) / nsplit);
-        it.part = n_parts + s;
-        items[cls].push_back(it);
-        item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
+        it.part = L.n_parts + s;
+        L.items[cls].push_back(it);
+        L.item_w[cls].push_back(P / nsplit + (uint64_t)(it.tile_end - it.tile_begin) * 64);
       }
     }
-    cls_postings[cls] += P;
-    n_parts += nsplit;
+    L.cls_postings[cls] += P;
+    L.n_parts += nsplit;
+    }
+  };
+#undef PFAIL
+  const bool trace = getenv("BM25F_TRACE") != nullptr;
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto t_a = now();
+  unsigned n_thr = 1;
+  if (Q >= 2048) n_thr = std::min<unsigned>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), Q / 1024);
+  std::vector<PlanLocal> locals(n_thr);
+  if (n_thr == 1) {
+    plan_range(0, Q, locals[0]);
+  } else {
+    if (!h->pool) h->pool = new PlanPool(8);
+    n_thr = std::min(n_thr, h->pool->size());
+    locals.resize(n_thr);
+    const std::function<void(unsigned)> job = [&](unsigned t) {
+      plan_range((uint32_t)((uint64_t)Q * t / n_thr), (uint32_t)((uint64_t)Q * (t + 1) / n_thr), locals[t]);
+    };
+    h->pool->parallel(n_thr, job);
   }
+  for (auto& L : locals)
+    if (L.rc) return fail(L.rc, "%s", L.err);
+  // stitch: partial-list indices and bitmap offsets become global
+  std::vector<ItemRec> items[5];
+  std::vector<uint64_t> item_w[5];
+  uint64_t postings = 0, taken_words = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+  uint32_t n_parts = 0;
+  bool any_nonpos = false;
+  for (unsigned t = 0; t < n_thr; ++t) {
+    PlanLocal& L = locals[t];
+    if (t > 0 && (n_parts || taken_words)) {
+      const uint32_t q0 = (uint32_t)((uint64_t)Q * t / n_thr), q1 = (uint32_t)((uint64_t)Q * (t + 1) / n_thr);
+      for (uint32_t qi = q0; qi < q1; ++qi) {
+        queries[qi].part_begin += n_parts;
+        if ((queries[qi].flags & QF_STREAM_LAST) && h->variant == 6) queries[qi].after_key += taken_words;
+      }
+      for (int c = 0; c < 5; ++c)
+        for (auto& it : L.items[c]) it.part += n_parts;
+    }
+    for (int c = 0; c < 5; ++c) {
+      items[c].insert(items[c].end(), L.items[c].begin(), L.items[c].end());
+      item_w[c].insert(item_w[c].end(), L.item_w[c].begin(), L.item_w[c].end());
+      cls_postings[c] += L.cls_postings[c];
+    }
+    postings += L.postings;
+    taken_words += L.taken_words;
+    n_parts += L.n_parts;
+    any_nonpos = any_nonpos || L.any_nonpos;
+  }
+  const uint32_t out_leaf = NL;            // leaf records sit at their input positions
+  auto t_b = now();
 
   bm25f_plan* p = new (std::nothrow) bm25f_plan();
   if (!p) return fail(BM25F_ENOMEM, "host allocation failed");
@@ -1926,12 +2056,17 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
   p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
   p->d_items_hs = p->d_items_is + p->n_is;
+  auto t_c = now();
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
   if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
   // pageable sources must outlive the copy; the pinned arena is only rewritten by the next
   // search_batch, which runs after this one has synchronised in bm25f_fetch
   if (!use_arena) CUP(cudaStreamSynchronize(h->stream));
+  if (trace) {
+    auto us = [](auto x, auto y) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count() / 1e3; };
+    fprintf(stderr, "[bm25f prepare] plan %.0f us (%u threads), order+alloc %.0f us, enqueue copies %.0f us\n", us(t_a, t_b), n_thr, us(t_b, t_c), us(t_c, now()));
+  }
   *out = p;
   return 0;
 #undef RCP
