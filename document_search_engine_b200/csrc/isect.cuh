@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
       const uint32_t c_df = __shfl_sync(0xFFFFFFFFu, s_df, c);
       const float c_w = __shfl_sync(0xFFFFFFFFu, s_w, c);
       uint32_t s_cur = s_start;               // the other leaves' cursors restart with every candidate leaf
+      uint32_t s_win = 64u;                   // size of the leaf's previous window
       for (uint32_t row = __shfl_sync(0xFFFFFFFFu, s_start, c); row < c_df; row += 32u) {
         const uint32_t i = row + (uint32_t)lane;
         uint2 r = make_uint2(0xFFFFFFFFu, 0u);
@@ -115,8 +116,13 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
           const uint2* __restrict__ lp = store + __shfl_sync(0xFFFFFFFFu, s_off, l);
           const uint32_t g = __shfl_sync(0xFFFFFFFFu, s_grp, l);
           const float wl = __shfl_sync(0xFFFFFFFFu, s_w, l);
-          // end of the window: first posting past the step's last docid (the cursor of the next step)
-          const uint32_t wend = cur + warp_lower_bound(lp + cur, df - cur, d_last + 1u, lane);
+          // end of the window: first posting past the step's last docid (the cursor of the next step).
+          // Windows of consecutive steps are about the same size, so look in twice the previous window
+          // first (nearby lines, two probe rounds) and in the rest of the list only if that fails.
+          const uint32_t near = min(df - cur, 2u * __shfl_sync(0xFFFFFFFFu, s_win, l) + 32u);
+          uint32_t wlen = warp_lower_bound(lp + cur, near, d_last + 1u, lane);
+          if (wlen == near && near < df - cur) wlen = near + warp_lower_bound(lp + cur + near, df - cur - near, d_last + 1u, lane);
+          const uint32_t wend = cur + wlen;
           uint32_t lo = cur, hi = wend;
           if (!valid) hi = lo;
           while (lo < hi) {
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
             }
           }
           __syncwarp();
-          if (lane == l) s_cur = wend;
+          if (lane == l) { s_cur = wend; s_win = wlen; }
         }
         const bool alive = !dead && sat == full;
         tot += alive ? 1u : 0u;
