@@ -947,6 +947,40 @@ __device__ __forceinline__ void warp_topk_insert(unsigned long long& mine, unsig
   if (lane == pos) mine = key;
 }
 
+// The same list with KR keys per lane (k <= 32 * KR): row j of lane i holds rank 32 * j + i.
+template <int KR>
+__device__ __forceinline__ void warp_topk_insert_rows(unsigned long long (&top)[KR], unsigned long long key, int lane) {
+  bool inserted = false;
+  unsigned long long carry = 0ull;
+#pragma unroll
+  for (int j = 0; j < KR; ++j) {
+    const unsigned long long last = __shfl_sync(0xFFFFFFFFu, top[j], 31);
+    const unsigned long long up = __shfl_up_sync(0xFFFFFFFFu, top[j], 1);
+    if (!inserted) {
+      const int pos = __popc(__ballot_sync(0xFFFFFFFFu, top[j] > key));
+      if (pos < 32) {                       // the key belongs in this row; its last element moves on
+        if (lane > pos) top[j] = up;
+        if (lane == pos) top[j] = key;
+        carry = last;
+        inserted = true;
+      }
+    } else {                                // rows after it shift by one
+      top[j] = (lane == 0) ? carry : up;
+      carry = last;
+    }
+  }
+}
+template <int KR>
+__device__ __forceinline__ unsigned long long warp_topk_kth(const unsigned long long (&top)[KR], int k) {
+  unsigned long long v = 0ull;
+#pragma unroll
+  for (int j = 0; j < KR; ++j) {
+    const unsigned long long t = __shfl_sync(0xFFFFFFFFu, top[j], (k - 1) & 31);
+    if (j == ((k - 1) >> 5)) v = t;
+  }
+  return v;
+}
+
 #include "stream.cuh"
 #include "team.cuh"
 #include "isect.cuh"
@@ -1538,7 +1572,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[2] = {(const void*)k_score_stream, (const void*)k_score_team};
+    const void* wfns[3] = {(const void*)k_score_stream<1>, (const void*)k_score_stream<4>, (const void*)k_score_team};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1776,19 +1810,19 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= 32 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= 128 && nlq <= 8 && all_pos && qr.after_key == 0ull;
     // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
     // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
     // ... unless its smallest group is so much sparser than the rest that looking its documents up in
     // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
     const uint64_t g0 = gsize[order[0]];
-    const bool isect_ok = k <= 32 && nlq <= 32 && all_pos && qr.after_key == 0ull;
+    const bool isect_ok = k <= 128 && nlq <= 32 && all_pos && qr.after_key == 0ull;
     // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
     // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
     uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
     bool use_or1 = false;
     bool use_hash = false;
-    if ((qr.flags & QF_SIMPLE_OR) && isect_ok && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
+    if ((qr.flags & QF_SIMPLE_OR) && isect_ok && k <= 32 && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
       uint32_t imax = 0;
       for (uint32_t i = 1; i < nlq; ++i)
         if (leaves[out_leaf - nlq + i].df > leaves[out_leaf - nlq + imax].df) imax = i;
@@ -1815,7 +1849,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
-    const bool use_team = !use_isect && !use_hash && stream_ok && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const bool use_team = !use_isect && !use_hash && stream_ok && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_hash ? 4 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
     if (use_hash) {
@@ -2168,7 +2202,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
       const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
       CU(cudaEventRecord(ev[4], st));
-      k_score_stream<<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      if (p->k <= 32) k_score_stream<1><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      else k_score_stream<4><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
       CU(cudaEventRecord(ev[5], st));
       CU(cudaGetLastError());
       ++launches;
@@ -2188,11 +2223,12 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.k = p->k;
       if (h->is_ctas_per_sm == 0) {
         int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect, IS_WARPS * 32, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1>, IS_WARPS * 32, 0));
         h->is_ctas_per_sm = std::max(1, nb_);
       }
       const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_is + IS_WARPS - 1) / IS_WARPS);
-      k_score_isect<<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      if (p->k <= 32) k_score_isect<1><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<4><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2270,7 +2306,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     if (p->n_w8 && !p->n_w4) {
       nb_ = h->tl_ctas_per_sm;
     } else if (p->n_w4) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream<1>, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
     } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);

@@ -45,9 +45,10 @@ struct IsectParams {
 
 constexpr int IS_WARPS = 8;
 
-// Requires: k <= 32, <= 32 leaves, <= 32 groups, every leaf weight > 0, no after_key, no postings of
+// Requires: k <= 32 * KR, <= 32 leaves, <= 32 groups, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store.
-__global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip) {
+template <int KR>
+__global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
   const int lane = threadIdx.x & 31;
   const uint2* __restrict__ store = ip.pairs;
 
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
     // candidate leaves: the leaves of the smallest group (they come first); all but the dense one for a one-dense OR
     const int n_cand = stream_last ? L - 1 : __popc(__ballot_sync(0xFFFFFFFFu, s_grp == 0u));
 
-    unsigned long long top = 0ull;            // lane i: i-th best key of this item so far
+    unsigned long long top[KR];               // lane i, row j: the (32 j + i)-th best key of this item so far
+#pragma unroll
+    for (int j = 0; j < KR; ++j) top[j] = 0ull;
     unsigned long long thr_key = 0ull;
     float thr = 0.0f;
     unsigned int tot = 0;
@@ -151,8 +154,8 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
           pm &= pm - 1u;
           const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
           if (bk > thr_key) {
-            warp_topk_insert(top, bk, lane);
-            thr_key = __shfl_sync(0xFFFFFFFFu, top, ip.k - 1);
+            warp_topk_insert_rows<KR>(top, bk, lane);
+            thr_key = warp_topk_kth<KR>(top, ip.k);
           }
         }
         if (thr_key != 0ull) thr = key_score(thr_key);
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
             pm &= pm - 1u;
             const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
             if (bk > thr_key) {
-              warp_topk_insert(top, bk, lane);
-              thr_key = __shfl_sync(0xFFFFFFFFu, top, ip.k - 1);
+              warp_topk_insert_rows<KR>(top, bk, lane);
+              thr_key = warp_topk_kth<KR>(top, ip.k);
             }
           }
           if (thr_key != 0ull) thr = key_score(thr_key);
@@ -209,7 +212,9 @@ __global__ void __launch_bounds__(IS_WARPS * 32, 5) k_score_isect(IsectParams ip
     }
 
     unsigned long long* out = ip.part_keys + (size_t)item.part * ip.k;
-    if (lane < ip.k) out[lane] = top;
+#pragma unroll
+    for (int j = 0; j < KR; ++j)
+      if (32 * j + lane < ip.k) out[32 * j + lane] = top[j];
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
     if (lane == 0 && tot) atomicAdd(ip.totals + item.q, (unsigned long long)tot);
   }

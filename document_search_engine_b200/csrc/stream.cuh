@@ -190,8 +190,9 @@ __device__ __forceinline__ void and_four(const SubCtx& cx, float w, uint32_t g, 
   }
 }
 
-// Requires: k <= 32, <= ST_MAX_LEAVES leaves, every leaf weight > 0, no after_key, no postings of
+// Requires: k <= 32 * KR, <= ST_MAX_LEAVES leaves, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store (bm25f_create compacts them away).
+template <int KR>
 __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -260,7 +261,9 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
       }
     }
 
-    unsigned long long top = 0ull;            // lane i: i-th best key of this item so far
+    unsigned long long top[KR];               // lane i, row j: the (32 j + i)-th best key of this item so far
+#pragma unroll
+    for (int j = 0; j < KR; ++j) top[j] = 0ull;
     unsigned long long thr_key = 0ull;
     cx.thr = 1.17549435e-38f;                 // FLT_MIN until k hits exist: every first hit is hot
     unsigned int tot = 0;
@@ -394,8 +397,8 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
             pm &= pm - 1u;
             const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
             if (bk > thr_key) {
-              warp_topk_insert(top, bk, lane);
-              thr_key = __shfl_sync(0xFFFFFFFFu, top, sp.k - 1);
+              warp_topk_insert_rows<KR>(top, bk, lane);
+              thr_key = warp_topk_kth<KR>(top, sp.k);
             }
           }
         }
@@ -409,7 +412,9 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
 
     // ---- item epilogue -------------------------------------------------------------------------
     unsigned long long* out = sp.part_keys + (size_t)item.part * sp.k;
-    if (lane < sp.k) out[lane] = top;
+#pragma unroll
+    for (int j = 0; j < KR; ++j)
+      if (32 * j + lane < sp.k) out[32 * j + lane] = top[j];
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
     if (lane == 0 && tot) atomicAdd(sp.totals + item.q, (unsigned long long)tot);
   }

@@ -160,6 +160,21 @@ def test_limits(cfg1, k):
     assert_batch_parity(o, qs.queries, res, k)
 
 
+@pytest.mark.parametrize("variant", [0, 3, 5])
+@pytest.mark.parametrize("k", [33, 64, 100, 128])
+def test_four_keys_per_lane(cfg1, k, variant):
+    """32 < k <= 128 on the stream and candidate-driven kernels (four keys per lane): ORs with thousands
+    of matches, ANDs with fewer than k, AND-of-OR groups, many partial lists to merge."""
+    ix, o = cfg1
+    qs = (make_queries(80, 50_000, 5, 2, 3, "mixed", skip_top=0).queries
+          + make_queries(40, 50_000, 6, 4, 4, "and", variants=True, skip_top=0).queries)
+    with ix.searcher(variant=variant, warp_split=4096, isect_split=128) as s:
+        res = s.search_batch(qs, limit=k)
+        st = s.engine.stats()
+    assert st["postings_cta"] == 0               # nothing fell back to the CTA kernels
+    assert_batch_parity(o, qs, res, k)
+
+
 def test_limit_none_and_paging_past_kernel_k(cfg1):
     ix, o = cfg1
     qs = make_queries(6, 50_000, 9, 2, 3, "or", skip_top=0)            # thousands of matches each
