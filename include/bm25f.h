@@ -80,7 +80,7 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 32, <= 8 leaves, positive
+  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 128, <= 8 leaves, positive
                                     weights, no paging bound - flat ORs on warp streams, ANDs whose smallest
                                     group is far sparser than the rest by candidate-driven lookups, other
                                     ANDs on warp teams; else the bulk-copy pipeline),
