@@ -4,13 +4,17 @@
 // calls it (reference my_flask.py:184, :208, :211, :304; cli.py:9).  See include/bm25f.h for
 // the boundary and DESIGN.md for the data layout and the kernels.
 //
-// Kernel inventory (all hand-written for sm_100a):
-//   k_check_tf / k_pack_postings  index upload: fold (tf, length byte) into one 32-bit payload
-//   k_tile_bounds                 per (leaf, tile) posting sub-range by binary search
-//   k_score_topk                  the hot kernel: tile-wise BM25F accumulate in shared memory,
-//                                 match filtering, exact top-k with 64-bit composite keys
-//   k_merge_topk                  merge of per-item (or per-GPU) top-k lists, decode
-//   k_decode_keys                 keys -> (score, docid, count)
+// Kernel inventory (all hand-written for sm_100a; DESIGN.md section 4 has the table):
+//   k_check_tf / k_pack_postings          index upload: fold (tf, length byte) into one 32-bit payload
+//   k_live_counts / k_compact_lists       index upload: drop the postings of deleted documents (W9)
+//   k_impacts                             re-weighting: {docid, tf / (tf + norm)} pairs, the scoring store
+//   k_score_stream    (stream.cuh)        flat ORs: independent warps, accumulators in shared memory
+//   k_score_isect     (isect.cuh)         ANDs: candidate-driven lookups (IntersectionMatcher + skip_to)
+//   k_score_team      (team.cuh)          symmetric ANDs: CTA-built bounds table, private slices
+//   k_score_hash      (hash.cuh)          experimental one-dense OR
+//   k_tile_bounds, k_score_pipe, k_score_topk   general fallback (k > 128, many leaves, paging, odd weights)
+//   k_merge_topk_warp / k_merge_topk      merge of per-item (or per-GPU) top-k lists
+//   k_decode_keys                         keys -> (score, docid, count)
 #include "../../include/bm25f.h"
 
 #include <cuda_runtime.h>
