@@ -1177,7 +1177,7 @@ struct bm25f_handle {
   uint32_t S = 8192, NT = 256, split = 1u << 16;
   uint32_t variant = 0;               // 0 / 3: auto (stream kernel where eligible, else pipeline), 1: pipeline, 2: direct loads
   // stream kernel: warps per CTA, accumulator bytes per warp, target work per item, L2 prefetch distance
-  uint32_t st_warps = 16, st_slot_bytes = 9216, wsplit = 1u << 17, st_pf = 2048;
+  uint32_t st_warps = 16, st_slot_bytes = 11776, wsplit = 1u << 17, st_pf = 2048;
   // team kernel (variant 4): warps per CTA, target work per item, slices ahead to prefetch
   uint32_t tl_warps = 8, tl_slot_bytes = 10240, tl_split = 1u << 18, tl_prefetch = 0;
   uint32_t chunk = 512, stages = 4;   // pipeline geometry
