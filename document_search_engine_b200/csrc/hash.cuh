@@ -12,9 +12,10 @@
 //  * per block: the postings of every S leaf in the block are inserted / accumulated (atomicCAS on
 //    the key claims a slot; docids are unique inside a list, so the score update needs no atomic);
 //    then D's postings of the block are streamed in super-rows of 128 (four 64-bit loads in flight per
-//    lane): probe the table - nearly always an empty slot on the first probe, then score = w * impact
-//    is compared with the k-th best score and that is all; on a hit the entry's score is raised
-//    instead; finally the table is flushed: every entry is a match and is offered to the top-k;
+//    lane): test the block's exact BITMAP of S documents (one shared load + a bit test) - nearly always
+//    clear, then score = w * impact is compared with the k-th best score and that is all; only a set
+//    bit walks the hash chain and raises the entry's score instead; finally the table is flushed: every
+//    entry is a match and is offered to the top-k;
 //  * matches = |D| + |entries| - |hits|, exactly; every posting is read exactly once.
 //
 // Results are identical to the other kernels (same impacts, FMA order: S leaves in leaf order, D last).
@@ -25,6 +26,7 @@ constexpr uint32_t HS_SLOTS = 1024;      // table entries per warp (8 KB)
 constexpr uint32_t HS_TARGET = 320;      // postings of S aimed at per block
 constexpr uint32_t HS_MAX_FILL = 640;    // a block with more is halved
 constexpr uint32_t HS_EMPTY = 0xFFFFFFFFu;
+constexpr uint32_t HS_BITMAP_DOCS = 16384; // widest block: one bit per document of the block (2 KB per warp)
 
 struct HashParams {
   const uint2* pairs;
@@ -51,12 +53,15 @@ __device__ __forceinline__ uint32_t atoms_cas(uint32_t addr, uint32_t cmp, uint3
 // <= 32 leaves, every leaf weight > 0, no after_key, no postings of deleted documents in the store.
 __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
   __shared__ __align__(16) uint2 s_table[HS_WARPS][HS_SLOTS];
+  __shared__ __align__(16) uint32_t s_bits[HS_WARPS][HS_BITMAP_DOCS / 32];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const uint2* __restrict__ store = hp.pairs;
   const uint32_t tab = smem_u32(&s_table[warp][0]);
+  const uint32_t bits = smem_u32(&s_bits[warp][0]);
 
   for (uint32_t j = (uint32_t)lane; j < HS_SLOTS; j += 32u) sts_v2(tab + j * 8u, HS_EMPTY, 0u);
+  for (uint32_t o = (uint32_t)lane * 16u; o < HS_BITMAP_DOCS / 8u; o += 512u) sts_zero16(bits + o);
   __syncwarp();
 
   for (;;) {
@@ -91,11 +96,12 @@ __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
     // in the synthetic corpora; a block that turns out fuller than HS_MAX_FILL is halved below)
     uint32_t s_total = (lane < dl) ? s_df : 0u;
     s_total = __reduce_add_sync(0xFFFFFFFFu, s_total);
-    uint32_t W = d_hi - d_lo;
+    uint32_t W = min(d_hi - d_lo, HS_BITMAP_DOCS);
     if (s_total > 0u) {
       const unsigned long long w64 = (unsigned long long)hp.n_docs * HS_TARGET / s_total;
       W = (uint32_t)min((unsigned long long)W, max(w64, 64ull));
     }
+    uint32_t s_win = 64u;                     // lane l: size of leaf l's previous block (where to look first)
     const uint2* __restrict__ dp = store + __shfl_sync(0xFFFFFFFFu, s_off, dl);
     const uint32_t d_df = __shfl_sync(0xFFFFFFFFu, s_df, dl);
     const float d_w = __shfl_sync(0xFFFFFFFFu, s_w, dl);
@@ -117,7 +123,14 @@ __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
           const uint32_t cur = __shfl_sync(0xFFFFFFFFu, s_cur, l);
           const uint32_t df = __shfl_sync(0xFFFFFFFFu, s_df, l);
           uint32_t e = cur;
-          if (cur < df) e = cur + warp_lower_bound(store + __shfl_sync(0xFFFFFFFFu, s_off, l) + cur, df - cur, bhi, lane);
+          if (cur < df) {
+            // blocks of one query are about the same size: look in twice the previous block first
+            const uint2* __restrict__ lp = store + __shfl_sync(0xFFFFFFFFu, s_off, l) + cur;
+            const uint32_t near = min(df - cur, 2u * __shfl_sync(0xFFFFFFFFu, s_win, l) + 32u);
+            uint32_t n = warp_lower_bound(lp, near, bhi, lane);
+            if (n == near && near < df - cur) n = near + warp_lower_bound(lp + near, df - cur - near, bhi, lane);
+            e = cur + n;
+          }
           if (lane == l) s_end = e;
         }
         n_s = (lane < dl) ? s_end - s_cur : 0u;
@@ -135,6 +148,8 @@ __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
         const float w = __shfl_sync(0xFFFFFFFFu, s_w, l);
         for (uint32_t i = lo + (uint32_t)lane; i < hi; i += 32u) {
           const uint2 r = ldg_pair(lp + i);
+          const uint32_t rel = r.x - blo;
+          asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(bits + (rel >> 5) * 4u), "r"(1u << (rel & 31u)) : "memory");
           uint32_t h = hs_hash(r.x);
           for (;;) {
             const uint32_t a = tab + h * 8u;
@@ -170,8 +185,8 @@ __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
             const uint32_t d = qa[e].x;
             float score = d_w * __uint_as_float(qa[e].y);
             bool miss = valid;
-            if (valid && n_s) {
-              uint32_t h = hs_hash(d);
+            if (valid && n_s && ((lds_u32(bits + ((d - blo) >> 5) * 4u) >> ((d - blo) & 31u)) & 1u)) {
+              uint32_t h = hs_hash(d);                       // in a sparse leaf too: its entry exists
               for (;;) {
                 const uint32_t a = tab + h * 8u;
                 const uint2 t = lds_v2(a);
@@ -237,8 +252,10 @@ __global__ void __launch_bounds__(HS_WARPS * 32) k_score_hash(HashParams hp) {
             if (thr_key != 0ull) thr = key_score(thr_key);
           }
         }
+        for (uint32_t o = (uint32_t)lane * 16u; o < ((bhi - blo + 127u) >> 7) * 16u; o += 512u) sts_zero16(bits + o);
         __syncwarp();
       }
+      if (lane < L) s_win = s_end - s_cur;
       s_cur = s_end;
       blo = bhi;
     }
