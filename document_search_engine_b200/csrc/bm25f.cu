@@ -87,7 +87,8 @@ struct ItemRec {            // 16 B
 };
 
 constexpr uint32_t QF_SIMPLE_OR = 1u;
-constexpr uint32_t QF_STREAM_LAST = 2u;   // one-dense OR: the last leaf is looked up, then streamed (k_score_isect)
+constexpr uint32_t QF_STREAM_LAST = 2u;   // one-dense OR: the last leaf is streamed accumulator-free
+constexpr uint32_t QF_TAKEN = 4u;         // ... by k_score_isect: after_key is the word offset of its "taken" bitmap
 constexpr int MAXL = BM25F_MAX_LEAVES_PER_QUERY;
 
 // W11 order as one unsigned 64-bit key: score descending, docnum ascending.  All keys of
@@ -1186,7 +1187,7 @@ struct bm25f_handle {
   int ctas_per_sm = 0;
   int tl_ctas_per_sm = 0;
   int is_ctas_per_sm = 0;
-  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000, is_or1_ratio = 0;
+  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000, is_or1_ratio = 0, is_or1_lookup = 1;
   uint32_t hs_split = 1u << 16;   // hash OR: target work (posting-equivalents) per item
   int hs_ctas_per_sm = 0;   // candidate-driven AND: cost of a lookup in postings, candidates per item
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
@@ -1212,13 +1213,15 @@ struct bm25f_plan {
   ItemRec* d_items_w8 = nullptr;
   uint32_t n_hs = 0;                      // hash OR items
   ItemRec* d_items_hs = nullptr;
+  uint32_t n_o1 = 0;                      // one-dense OR (lookups) items
+  ItemRec* d_items_o1 = nullptr;
   uint32_t n_is = 0;                      // candidate-driven items
   unsigned int* d_taken = nullptr;        // one-dense ORs: bitmaps over the dense leaves' postings
   uint64_t taken_words = 0;
   ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
-  uint64_t postings_cls[5] = {0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, hash
+  uint64_t postings_cls[6] = {0, 0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, hash, one-dense OR
   LeafRec* d_leaves = nullptr;
   QueryRec* d_queries = nullptr;
   ItemRec* d_items = nullptr;
@@ -1722,9 +1725,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   // into its own item lists and counters), then stitched together.  A query's leaf records live at
   // the positions of its input leaves, so no thread needs another's running totals.
   struct PlanLocal {
-    std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR
-    std::vector<uint64_t> item_w[5];
-    uint64_t postings = 0, taken_words = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+    std::vector<ItemRec> items[6];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR; 5: one-dense OR by lookups
+    std::vector<uint64_t> item_w[6];
+    uint64_t postings = 0, taken_words = 0, cls_postings[6] = {0, 0, 0, 0, 0, 0};
     uint32_t n_parts = 0;
     bool any_nonpos = false;
     int rc = 0;
@@ -1835,9 +1838,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       if (h->variant == 6 || h->variant == 7 || (h->is_or1_ratio && rest * h->is_or1_ratio < P)) {
         std::swap(leaves[out_leaf - nlq + imax], leaves[out_leaf - 1]);     // the dense leaf goes last
         qr.flags |= QF_STREAM_LAST;
-        if (h->variant == 6) {
+        if (h->variant == 6 || (h->variant == 0 && h->is_or1_lookup)) {
           // lookups + "taken" bitmap (k_score_isect)
           use_or1 = true;
+          qr.flags |= QF_TAKEN;
           qr.after_key = L.taken_words;               // word offset of this query's bitmap
           L.taken_words += (dmax + 31) / 32 + 1;
           n_cand = rest * (uint64_t)(nlq > 1 ? nlq - 1 : 1) + dmax / 16;   // work, in candidate lookups
@@ -1854,7 +1858,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
     const bool use_team = !use_isect && !use_hash && stream_ok && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
-    const int cls = use_hash ? 4 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
+    const int cls = use_hash ? 4 : use_or1 ? 5 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
     if (use_hash) {
       nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 4096), std::max<uint64_t>(1, (n_cand + h->hs_split / 2) / h->hs_split));
@@ -1950,9 +1954,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   for (auto& L : locals)
     if (L.rc) return fail(L.rc, "%s", L.err);
   // stitch: partial-list indices and bitmap offsets become global
-  std::vector<ItemRec> items[5];
-  std::vector<uint64_t> item_w[5];
-  uint64_t postings = 0, taken_words = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+  std::vector<ItemRec> items[6];
+  std::vector<uint64_t> item_w[6];
+  uint64_t postings = 0, taken_words = 0, cls_postings[6] = {0, 0, 0, 0, 0, 0};
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   for (unsigned t = 0; t < n_thr; ++t) {
@@ -1961,12 +1965,12 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       const uint32_t q0 = (uint32_t)((uint64_t)Q * t / n_thr), q1 = (uint32_t)((uint64_t)Q * (t + 1) / n_thr);
       for (uint32_t qi = q0; qi < q1; ++qi) {
         queries[qi].part_begin += n_parts;
-        if ((queries[qi].flags & QF_STREAM_LAST) && h->variant == 6) queries[qi].after_key += taken_words;
+        if (queries[qi].flags & QF_TAKEN) queries[qi].after_key += taken_words;
       }
-      for (int c = 0; c < 5; ++c)
+      for (int c = 0; c < 6; ++c)
         for (auto& it : L.items[c]) it.part += n_parts;
     }
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < 6; ++c) {
       items[c].insert(items[c].end(), L.items[c].begin(), L.items[c].end());
       item_w[c].insert(item_w[c].end(), L.item_w[c].begin(), L.item_w[c].end());
       cls_postings[c] += L.cls_postings[c];
@@ -1994,11 +1998,12 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_w8 = (uint32_t)items[1].size();
   p->n_is = (uint32_t)items[3].size();
   p->n_hs = (uint32_t)items[4].size();
+  p->n_o1 = (uint32_t)items[5].size();
   p->taken_words = taken_words;
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
-  for (int c = 0; c < 5; ++c) p->postings_cls[c] = cls_postings[c];
+  for (int c = 0; c < 6; ++c) p->postings_cls[c] = cls_postings[c];
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
 
@@ -2017,7 +2022,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }                                                                   \
   } while (0)
   const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
-  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs;
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs + p->n_o1;
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
   if (use_arena) {
@@ -2046,13 +2051,14 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
   order_items(items[3], item_w[3], h_items + p->n_items + p->n_w4 + p->n_w8);
   order_items(items[4], item_w[4], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is);
+  order_items(items[5], item_w[5], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs);
 
   if (use_arena) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
     const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
-                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 4) * 8),
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 5) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
                  o_taken = take((size_t)(taken_words + 1) * 4);
     if (off > h->d_arena_cap) {
@@ -2084,7 +2090,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
     RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, (size_t)Q + 4));
+    RCP(dev_alloc(&p->d_totals, (size_t)Q + 5));
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
@@ -2094,6 +2100,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
   p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
   p->d_items_hs = p->d_items_is + p->n_is;
+  p->d_items_o1 = p->d_items_hs + p->n_hs;
   auto t_c = now();
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
@@ -2130,7 +2137,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   cudaEvent_t* ev = h->ev[h->ev_head];
   CU(cudaEventRecord(ev[0], st));
-  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 4) * 8, st));   // totals + the four work counters
+  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 5) * 8, st));   // totals + the five work counters
   if (p->taken_words) CU(cudaMemsetAsync(p->d_taken, 0, (size_t)p->taken_words * 4, st));
   const unsigned long long nb = p->n_items ? (unsigned long long)p->n_leaves * (p->T + 1) : 0ull;
   if (nb) {
@@ -2139,7 +2146,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_hs) {
+  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_hs || p->n_o1) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -2161,7 +2168,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.prof = h->d_prof;
     // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
     // registers) fit on an SM together and stall on different things: launch them side by side.
-    const bool side = (p->n_w4 || p->n_hs) && (p->n_is || p->n_w8);
+    const bool side = (p->n_w4 || p->n_hs) && (p->n_is || p->n_w8 || p->n_o1);
     cudaStream_t ax = side ? h->aux_stream : st;
     if (side) {
       CU(cudaEventRecord(h->ev_fork, st));
@@ -2209,6 +2216,31 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       if (p->k <= 32) k_score_stream<1><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
       else k_score_stream<4><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
       CU(cudaEventRecord(ev[5], st));
+      CU(cudaGetLastError());
+      ++launches;
+    }
+    if (p->n_o1) {
+      // one-dense ORs (experimental, or1_ratio): same kernel as the candidate-driven ANDs, on the second stream
+      IsectParams ip;
+      ip.pairs = h->d_pairs;
+      ip.leaves = p->d_leaves;
+      ip.queries = p->d_queries;
+      ip.items = p->d_items_o1;
+      ip.part_keys = p->d_part_keys;
+      ip.totals = p->d_totals;
+      ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 4);
+      ip.taken = p->d_taken;
+      ip.n_items = p->n_o1;
+      ip.doc_base = (uint32_t)h->doc_base;
+      ip.k = p->k;
+      if (h->is_ctas_per_sm == 0) {
+        int nb_ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1>, IS_WARPS * 32, 0));
+        h->is_ctas_per_sm = std::max(1, nb_);
+      }
+      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_o1 + IS_WARPS - 1) / IS_WARPS);
+      if (p->k <= 32) k_score_isect<1><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<4><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2302,8 +2334,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->stats.postings_team = p->postings_cls[1];
   h->stats.postings_cta = p->postings_cls[2];
   h->stats.postings_lookup = p->postings_cls[3];
-  h->stats.postings_hash = p->postings_cls[4];
-  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs;
+  h->stats.postings_hash = p->postings_cls[4] + p->postings_cls[5];
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs + p->n_o1;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
