@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbm25f.so")
 #: every symbol ``include/bm25f.h`` declares
 EXPORTS = (
     "bm25f_abi_version", "bm25f_last_error", "bm25f_create", "bm25f_destroy", "bm25f_set_weighting",
-    "bm25f_prepare", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
+    "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
     "bm25f_reset_stats",
 )
@@ -90,6 +90,7 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_destroy.restype = None
     lib.bm25f_set_weighting.argtypes = [vp, vp]
     lib.bm25f_prepare.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, C.POINTER(vp)]
+    lib.bm25f_prepare_arena.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, C.POINTER(vp)]
     lib.bm25f_execute.argtypes = [vp, vp]
     lib.bm25f_fetch.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bm25f_plan_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
@@ -218,10 +219,13 @@ class Engine:
         _check(self.lib, self.lib.bm25f_set_weighting(self._h, _ptr(norm)))
         self._weighting_key = key
 
-    def prepare(self, batch: PackedBatch, k: int) -> Plan:
+    def prepare(self, batch: PackedBatch, k: int, arena: bool = False) -> Plan:
+        """``arena=True``: the plan lives in the handle's reusable workspaces (no allocation) and is
+        valid until the next arena plan / ``search_batch`` on this engine."""
         d = batch.desc()
         p = C.c_void_p()
-        _check(self.lib, self.lib.bm25f_prepare(self._h, C.byref(d), k, C.byref(p)))
+        fn = self.lib.bm25f_prepare_arena if arena else self.lib.bm25f_prepare
+        _check(self.lib, fn(self._h, C.byref(d), k, C.byref(p)))
         return Plan(self, p, batch.n_queries, k)
 
     def search_batch(self, batch: PackedBatch, k: int):

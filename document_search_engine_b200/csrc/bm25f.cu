@@ -2126,6 +2126,10 @@ int bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan
   return prepare_impl(h, b, k, out, false);
 }
 
+int bm25f_prepare_arena(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
+  return prepare_impl(h, b, k, out, true);
+}
+
 int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
   CU(cudaSetDevice(h->device));

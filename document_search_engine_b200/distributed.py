@@ -118,14 +118,29 @@ class ShardedSearcher:
 
     def search_packed(self, batch: _ffi.PackedBatch, k: int):
         """Host buffers in, host buffers out: ``(scores, docids, counts, totals)`` of the whole corpus."""
-        plan = self.engine.prepare(batch, k)
+        plan = self.engine.prepare(batch, k, arena=True)
         try:
             b = self.run_plan(plan)
             Q = batch.n_queries
-            scores = b["scores"].cpu().numpy().reshape(Q, k)
-            docids = b["docids"].cpu().numpy().view(np.uint32).reshape(Q, k)
-            counts = b["counts"].cpu().numpy().view(np.uint32)
-            totals = b["totals"].cpu().numpy().view(np.uint64)
+            h = self._host_buffers(Q, k)
+            for name in ("scores", "docids", "counts", "totals"):
+                h[name].copy_(b[name], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            scores = h["scores"].numpy().reshape(Q, k).copy()
+            docids = h["docids"].numpy().view(np.uint32).reshape(Q, k).copy()
+            counts = h["counts"].numpy().view(np.uint32).copy()
+            totals = h["totals"].numpy().view(np.uint64).copy()
         finally:
             plan.close()
         return scores, docids, counts, totals
+
+    def _host_buffers(self, Q: int, k: int):
+        key = ("host", Q, k)
+        h = self._bufs.get(key)
+        if h is None:
+            h = dict(scores=torch.empty(Q * k, dtype=torch.float32).pin_memory(),
+                     docids=torch.empty(Q * k, dtype=torch.int32).pin_memory(),
+                     counts=torch.empty(Q, dtype=torch.int32).pin_memory(),
+                     totals=torch.empty(Q, dtype=torch.int64).pin_memory())
+            self._bufs[key] = h
+        return h

@@ -166,6 +166,10 @@ int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
 
 /* Host planning + upload of one batch.  The plan can be executed any number of times. */
 int  bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
+/* Same, but the plan's buffers live in the handle's reusable workspaces (no allocation): the plan is valid
+ * until the next bm25f_prepare_arena / bm25f_search_batch on this handle.  This is what the sharded host layer
+ * uses per batch (the per-GPU half of `Searcher.search`, reference my_flask.py:208, :211, :304). */
+int  bm25f_prepare_arena(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
 /* Launch the kernels of a plan on the handle's stream (asynchronous). */
 int  bm25f_execute(bm25f_handle* h, bm25f_plan* plan);
 /* Wait for the plan's kernels and copy the results to host buffers:
