@@ -7,6 +7,7 @@ import collections
 import csv
 import json
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -21,7 +22,7 @@ hdr = rows[0]
 ik, im, iv, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
 L = collections.OrderedDict()
 for r in rows[1:]:
-    d = L.setdefault(r[iid], {"k": r[ik].split("(")[0].replace("<unnamed>::", "")})
+    d = L.setdefault(r[iid], {"k": re.search(r"k_[a-z_]+", r[ik]).group(0)})
     d[r[im]] = float(r[iv].replace(",", ""))
 names = []
 for d in L.values():
