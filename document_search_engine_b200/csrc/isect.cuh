@@ -172,7 +172,16 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
       uint32_t i0 = __shfl_sync(0xFFFFFFFFu, s_start, dl) & ~31u;    // bitmap words are aligned to 32 postings
       const uint32_t first = __shfl_sync(0xFFFFFFFFu, s_start, dl);
       bool more = i0 < d_df;
+      if (more) {                                                   // the first 4 KB of the range
+        const uint32_t c0 = i0 + (uint32_t)lane * 16u;
+        if (c0 < d_df) prefetch_l2(dp + c0);
+      }
       while (more) {
+        if ((i0 & 511u) < 128u) {
+          // one 128-byte line per lane: the 4 KB chunk 2048 postings ahead (the loads below then hit L2)
+          const uint32_t c0 = (i0 & ~511u) + 2048u + (uint32_t)lane * 16u;
+          if (c0 < d_df) prefetch_l2(dp + c0);
+        }
         uint2 r[4];
         uint32_t tk[4];
 #pragma unroll
@@ -183,23 +192,31 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
           if (i0 + 32u * e < d_df) tk[e] = __ldcg(taken + ((i0 >> 5) + e));
           if (i < d_df) r[e] = ldg_pair(dp + i);
         }
+        bool hot[4];
+        bool any_hot = false;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const uint32_t i = i0 + 32u * e + (uint32_t)lane;
           const bool valid = (i >= first) && (r[e].x < d_hi);       // past the end: docid 0xFFFFFFFF
           const bool fresh = valid && !((tk[e] >> lane) & 1u);      // not already counted as a candidate
-          const float score = d_w * __uint_as_float(r[e].y);
           tot += fresh ? 1u : 0u;
-          unsigned long long key = 0ull;
-          if (fresh && score >= thr) key = make_key(score, ip.doc_base + r[e].x);
-          unsigned pm = __ballot_sync(0xFFFFFFFFu, key > thr_key);
-          while (pm) {
-            const int src = __ffs(pm) - 1;
-            pm &= pm - 1u;
-            const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
-            if (bk > thr_key) {
-              warp_topk_insert_rows<KR>(top, bk, lane);
-              thr_key = warp_topk_kth<KR>(top, ip.k);
+          hot[e] = fresh && (d_w * __uint_as_float(r[e].y) >= thr);
+          any_hot = any_hot || hot[e];
+        }
+        if (__any_sync(0xFFFFFFFFu, any_hot)) {                     // rare once k hits exist
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            unsigned long long key = 0ull;
+            if (hot[e]) key = make_key(d_w * __uint_as_float(r[e].y), ip.doc_base + r[e].x);
+            unsigned pm = __ballot_sync(0xFFFFFFFFu, key > thr_key);
+            while (pm) {
+              const int src = __ffs(pm) - 1;
+              pm &= pm - 1u;
+              const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
+              if (bk > thr_key) {
+                warp_topk_insert_rows<KR>(top, bk, lane);
+                thr_key = warp_topk_kth<KR>(top, ip.k);
+              }
             }
           }
           if (thr_key != 0ull) thr = key_score(thr_key);

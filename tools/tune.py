@@ -77,7 +77,9 @@ def main():
             gbs = 9.0 * st["postings_touched"] / (st["ms_score"] / n * 1e-3) / 1e9
             print(json.dumps({"opt": opt, "mode": m, "qps": len(queries) / (ms * 1e-3), "ms_total": ms,
                               "ms_bounds": st["ms_bounds"] / n, "ms_score": st["ms_score"] / n,
-                              "ms_merge": st["ms_merge"] / n, "algo_GBs": gbs, "frac_6547": gbs / 6547.2,
+                              "ms_merge": st["ms_merge"] / n, "ms_stream": st["ms_stream"] / n,
+                              "post_stream": st["postings_stream"], "post_lookup": st["postings_lookup"],
+                              "post_or1": st["postings_hash"], "algo_GBs": gbs, "frac_6547": gbs / 6547.2,
                               "items": st["n_items"], "ctas_per_sm": st["ctas_per_sm"],
                               "postings": st["postings_touched"]}), flush=True)
             eng.reset_stats()      # a BM25F_PROFILE build prints its phase timers here
