@@ -350,7 +350,9 @@ def main():
     ms_stream = st["ms_stream"] / nex
     achieved = BYTES_PER_POSTING * st["postings_stream"] / (ms_stream * 1e-3) / 1e9 if ms_stream > 0 else 0.0
     step_gbs = BYTES_PER_POSTING * st["postings_touched"] / (ms_score * 1e-3) / 1e9 if ms_score > 0 else 0.0
-    launches = int(st["n_launches"]) * args.steps + (2 * args.steps if world > 1 else 0)
+    # kernels of the library per timed step: the plan's own launches, run_plan's decode of the (merged) keys,
+    # and for N > 1 the merge of the gathered lists
+    launches = (int(st["n_launches"]) + 1 + (1 if world > 1 else 0)) * args.steps
 
     # ---- e2e: host buffers through the public entry point ---------------------------------------
     h2d = batch.nbytes
