@@ -16,6 +16,7 @@ ABI_VERSION = 2
 MAX_K = 1024
 MAX_LEAVES_PER_QUERY = 64
 TERM_UNKNOWN = 0xFFFFFFFF
+TERM_EVERY_BASE = 0xFFFFFF00       # + field index: Every(field)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbm25f.so")

@@ -1165,7 +1165,8 @@ struct bm25f_handle {
   cudaStream_t aux_stream = nullptr;  // the candidate-driven / team kernels run here, beside the stream kernel
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t n_docs = 0, n_terms = 0, n_postings = 0, doc_base = 0;
-  uint32_t n_fields = 0;
+  uint32_t n_fields = 0;               // real fields; field index n_fields is the constant-score pseudo-field of Every()
+  uint64_t n_real_terms = 0;           // posting lists of the caller; [n_real_terms, n_terms) are the Every(field) lists
   std::vector<uint64_t> term_offsets;
   std::vector<uint8_t> term_field;
   uint32_t* d_docids = nullptr;
@@ -1415,7 +1416,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   }
   if (h->chunk < 64 || (h->chunk & 15) || h->chunk > 8192) { delete h; return fail(BM25F_EINVAL, "chunk_postings must be a multiple of 16 in 64..8192"); }
   if (h->stages < 2 || h->stages > (uint32_t)PIPE_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "stages must be 2..%d", PIPE_MAX_STAGES); }
-  h->nf_smem = desc->n_fields <= 4 ? desc->n_fields : 0;
+  h->nf_smem = desc->n_fields + 1 <= 4 ? desc->n_fields + 1 : 0;
   if (h->S < 256 || h->S > 65536 || (h->S & 3)) { delete h; return fail(BM25F_EINVAL, "tile_docs must be a multiple of 4 in 256..65536"); }
   if (h->NT < 64 || h->NT > 512 || (h->NT & 31)) { delete h; return fail(BM25F_EINVAL, "threads must be a multiple of 32 in 64..512"); }
   h->term_offsets.assign(desc->term_offsets, desc->term_offsets + desc->n_terms + 1);
@@ -1446,7 +1447,8 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
 
   uint64_t P = desc->n_postings;
   const size_t pad = 1024;   // rows / prefetch chunks may run past the last posting of the last list
-  RCH(dev_alloc(&h->d_norm, (size_t)h->n_fields * 256, h));
+  RCH(dev_alloc(&h->d_norm, (size_t)(h->n_fields + 1) * 256, h));
+  CUH(cudaMemsetAsync(h->d_norm, 0, (size_t)(h->n_fields + 1) * 256 * sizeof(float), h->stream));   // the pseudo-field's row stays 0: impact = tf / (tf + 0) = 1
   // temporaries for compaction and packing
   uint32_t* d_raw_docids = nullptr;
   float* d_tfs = nullptr;
@@ -1475,15 +1477,42 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     int rc_ = (x);                   \
     if (rc_) { free_tmp(); bm25f_destroy(h); return rc_; } \
   } while (0)
+  // ---- Every(field) (reference cli.py:9): one more posting list per field with every document that has
+  // the field (non-zero length byte), weight 1, on a pseudo-field whose norm row is 0, so that its score is
+  // the constant w * 1 (Whoosh scores Every with the query boost).  Deleted documents leave it below.
+  std::vector<uint32_t> every_docs;
+  {
+    std::vector<uint8_t> h_len((size_t)h->n_fields * h->n_docs);
+    if (!h_len.empty()) CUT(cudaMemcpy(h_len.data(), desc->len_bytes, h_len.size(), cudaMemcpyDefault));
+    h->n_real_terms = h->n_terms;
+    for (uint32_t f = 0; f < h->n_fields; ++f) {
+      const uint8_t* lb = h_len.data() + (size_t)f * h->n_docs;
+      for (uint64_t d = 0; d < h->n_docs; ++d)
+        if (lb[d]) every_docs.push_back((uint32_t)d);
+      h->term_offsets.push_back(P + every_docs.size());
+      h->term_field.push_back((uint8_t)h->n_fields);
+    }
+    h->n_terms += h->n_fields;
+  }
+  const uint64_t P_real = P;
+  P += every_docs.size();
+  h->n_postings = P;
   RCT(dev_alloc(&h->d_docids, P + pad, h));
-  RCT(dev_alloc(&d_tfs, P));
-  RCT(dev_alloc(&d_len, (size_t)h->n_fields * h->n_docs));
+  RCT(dev_alloc(&d_tfs, std::max<uint64_t>(P, 1)));
+  RCT(dev_alloc(&d_len, (size_t)(h->n_fields + 1) * h->n_docs));
   RCT(dev_alloc(&d_flag, 1));
-  if (P) {
-    CUT(cudaMemcpyAsync(h->d_docids, desc->docids, P * 4, cudaMemcpyDefault, h->stream));
-    CUT(cudaMemcpyAsync(d_tfs, desc->tfs, P * 4, cudaMemcpyDefault, h->stream));
+  if (P_real) {
+    CUT(cudaMemcpyAsync(h->d_docids, desc->docids, P_real * 4, cudaMemcpyDefault, h->stream));
+    CUT(cudaMemcpyAsync(d_tfs, desc->tfs, P_real * 4, cudaMemcpyDefault, h->stream));
+  }
+  std::vector<float> every_tfs(every_docs.size(), 1.0f);
+  if (!every_docs.empty()) {
+    CUT(cudaMemcpyAsync(h->d_docids + P_real, every_docs.data(), every_docs.size() * 4, cudaMemcpyHostToDevice, h->stream));
+    CUT(cudaMemcpyAsync(d_tfs + P_real, every_tfs.data(), every_tfs.size() * 4, cudaMemcpyHostToDevice, h->stream));
   }
   CUT(cudaMemcpyAsync(d_len, desc->len_bytes, (size_t)h->n_fields * h->n_docs, cudaMemcpyDefault, h->stream));
+  CUT(cudaMemsetAsync(d_len + (size_t)h->n_fields * h->n_docs, 0, h->n_docs, h->stream));
+  CUT(cudaStreamSynchronize(h->stream));     // every_docs / every_tfs are pageable
 
   // ---- W9: drop the postings of deleted documents from the device store -----------------------
   if (desc->deleted && P && h->n_terms) {
@@ -1662,6 +1691,15 @@ namespace {
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) & ~(a - 1); }
 
+// BM25F_TERM_EVERY(field) -> the field's pseudo posting list; an unknown field matches nothing
+inline uint32_t resolve_term(const bm25f_handle* h, uint32_t term) {
+  if (term >= BM25F_TERM_EVERY_BASE && term != BM25F_TERM_UNKNOWN) {
+    const uint32_t f = term - BM25F_TERM_EVERY_BASE;
+    return f < h->n_fields ? (uint32_t)h->n_real_terms + f : BM25F_TERM_UNKNOWN;
+  }
+  return term;
+}
+
 // order items heaviest-first (longest-processing-time order for the block scheduler) with an O(n)
 // bucket pass: exact order inside a quarter-octave of weight does not matter
 void order_items(const std::vector<ItemRec>& items, const std::vector<uint64_t>& w, ItemRec* out) {
@@ -1768,9 +1806,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       if (g >= G || g < prev_g) PFAIL(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
       prev_g = g;
       gseen[g] = true;
-      const uint32_t term = b->leaf_term[i];
+      const uint32_t term = resolve_term(h, b->leaf_term[i]);
       if (term != BM25F_TERM_UNKNOWN) {
-        if (term >= h->n_terms) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, term);
+        if (term >= h->n_real_terms + h->n_fields) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, b->leaf_term[i]);
         gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
       }
       if (!(b->leaf_weight[i] > 1e-30f)) all_pos = false;
@@ -1791,7 +1829,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     for (uint32_t r = 0; r < G; ++r) {
       for (uint32_t i = a; i < e; ++i) {
         if (b->leaf_group[i] != order[r]) continue;
-        const uint32_t term = b->leaf_term[i];
+        const uint32_t term = resolve_term(h, b->leaf_term[i]);
         if (term == BM25F_TERM_UNKNOWN) continue;
         const uint64_t off = h->term_offsets[term], df = h->term_offsets[term + 1] - off;
         if (df == 0) continue;

@@ -273,7 +273,16 @@ class Searcher:
         for q in queries:
             leaves, g, kind = lower(q)
             if kind == "every":
-                raise UnsupportedQuery("Every() is not served by the GPU path yet (SURVEY.md §8 f3)")
+                # Whoosh's Every(field): every live document that has the field, constant score = boost
+                # (reference cli.py:9).  The library keeps one posting list per field for it.
+                lf = leaves[0]
+                f = ix.field_names.index(lf.fieldname) if lf.fieldname in ix.field_names else -1
+                terms.append(_ffi.TERM_UNKNOWN if f < 0 else _ffi.TERM_EVERY_BASE + f)
+                weights.append(float(lf.boost))
+                groups.append(0)
+                ngroups.append(1)
+                offs.append(len(terms))
+                continue
             if kind == "null":
                 ngroups.append(0)
                 offs.append(len(terms))

@@ -55,6 +55,8 @@ extern "C" {
 #define BM25F_MAX_LEAVES_PER_QUERY 64
 #define BM25F_MAX_K               1024
 #define BM25F_TERM_UNKNOWN 0xFFFFFFFFu  /* leaf_term value for a term/field not in the index (empty matcher) */
+#define BM25F_TERM_EVERY_BASE 0xFFFFFF00u  /* leaf_term = BASE + field: Whoosh's Every(field) - every live document
+                                              that has the field, constant score = leaf_weight (reference cli.py:9) */
 
 typedef struct bm25f_handle bm25f_handle;
 typedef struct bm25f_plan bm25f_plan;

@@ -61,7 +61,7 @@ def test_config1_variants_groups(cfg1):
 
 
 @pytest.mark.parametrize("variant,chunk,stages", [(1, 64, 2), (1, 256, 8), (1, 2048, 3), (2, 0, 0)])
-@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (20480, 1 << 20)])
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (19456, 1 << 20)])
 def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
     """Tiny tiles, tiny work items, tiny/huge pipeline stages: many tiles per query, chunks that
     split posting sub-ranges, many partial lists to merge."""
@@ -251,3 +251,23 @@ def test_sharded_equals_whole(cfg1):
     for i, q in enumerate(qs.queries):
         merged = sorted(tops[i], key=lambda t: (-t[0], t[1]))[:10]
         assert_query_parity(o, q, merged, totals[i], 10, ctx="query %d" % i)
+
+
+def test_every_field_and_cli_harness():
+    """``searcher.search(Every('session'), limit=None)`` is the reference's only harness (cli.py:9): every
+    live document that has the field, constant score, docnum order; here with deleted documents, documents
+    without the field, a boost, an unknown field, and more matches than one kernel pass returns."""
+    from document_search_engine_b200 import Every
+    ix = make_corpus(3000, 300, 17, (TITLE, BODY), device="cpu")
+    rng = np.random.default_rng(1)
+    ix.deleted = (rng.random(ix.n_docs_all) < 0.1).astype(np.uint8)
+    ix.len_bytes[0, rng.random(ix.n_docs_all) < 0.3] = 0           # 30 % of the documents have no title
+    o = NumpyOracle(ix)
+    with ix.searcher() as s:
+        for q, limit in ((Every("title"), 10), (Every("body"), None), (Every("title", boost=2.5), 1500), (Every("nope"), 10)):
+            r = s.search(q, limit=limit)
+            assert_query_parity(o, q, r.top_n, len(r), limit, ctx=str(q))
+        r = s.search(Every("title"), limit=None)
+        assert [h.docnum for h in r] == sorted(h.docnum for h in r) and all(h.score == 1.0 for h in r)
+        live_with_title = int(((ix.len_bytes[0] != 0) & (ix.deleted == 0)).sum())
+        assert len(r) == live_with_title == r.scored_length()
