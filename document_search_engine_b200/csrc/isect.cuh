@@ -14,7 +14,7 @@
 //    window that can hold the step's docids - which is also that leaf's cursor for the next step -
 //    and then every lane binary-searches its own docid inside the window;
 //  * a candidate that collected every group is a match: counted, and offered to the warp's top-k
-//    (one 64-bit key per lane, k <= 32) if its score reaches the current k-th best.
+//    (KR 64-bit keys per lane, k <= 32 * KR) if its score reaches the current k-th best.
 //
 // One-dense OR (QF_STREAM_LAST): a flat OR whose last leaf D is far denser than all the others
 // together.  Documents that occur only in D need no accumulator - their score is w * impact - so the

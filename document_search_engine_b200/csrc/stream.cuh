@@ -26,7 +26,7 @@
 //    instruction fetch (measured: profiles/r01_notes.md).
 //  * Matches are counted while accumulating.  A document is looked at for the top-k only when its
 //    running score crosses the current k-th best score; the warp keeps the k best 64-bit keys
-//    one per lane (k <= 32) and inserts with shuffles.
+//    in registers (KR per lane, k <= 32 * KR) and inserts with shuffles.
 #pragma once
 
 constexpr int ST_HOT = 64;              // hot-list entries per warp

@@ -14,7 +14,7 @@
  *       <- `ix.searcher(weighting=BM25F | AscDateBM25F | DescDateBM25F)`
  *                                                      reference my_flask.py:183-184
  *          (B, K1, per-field B and the corpus avgfl are folded into per-field norm tables).
- *   bm25f_search_batch  (= bm25f_prepare + bm25f_execute + bm25f_fetch)
+ *   bm25f_search_batch  (= bm25f_prepare_arena + bm25f_execute + bm25f_fetch)
  *       <- `searcher.search_page(qp, pagenum, pagelen)` reference my_flask.py:208, :211
  *          `searcher.search(qp, limit=3)`               reference my_flask.py:304
  *          `ix.searcher().search(Every('session'), limit=None)`   reference cli.py:9
