@@ -1759,6 +1759,22 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     queries = own_queries.data();
   }
 
+  // A small batch (a single interactive query is the reference's use) would be a handful of items on
+  // a handful of warps: cut its items finer so that the whole GPU works on it.
+  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
+  if (Q <= 1024) {
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < NL; ++i) {
+      const uint32_t term = resolve_term(h, b->leaf_term[i]);
+      if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
+    }
+    const uint64_t per_item = std::max<uint64_t>(4096, total / ((uint64_t)h->n_sms * 32));   // ~2 items per stream-kernel warp
+    if (per_item < wsplit) {
+      is_split = (uint32_t)std::max<uint64_t>(128, (uint64_t)is_split * per_item / wsplit);
+      tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
+      wsplit = (uint32_t)per_item;
+    }
+  }
   // Planning is per query and independent: ranges of queries are planned by a few host threads (each
   // into its own item lists and counters), then stitched together.  A query's leaf records live at
   // the positions of its input leaves, so no thread needs another's running totals.
@@ -1911,7 +1927,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         L.item_w[cls].push_back(n_cand / nsplit + 64);
       }
     } else if (use_isect) {
-      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + h->is_split) / (2ull * h->is_split)));
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + is_split) / (2ull * is_split)));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
         ItemRec it;
@@ -1927,7 +1943,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       const uint64_t sw = h->tl_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
       const uint64_t nsl = (h->n_docs + sw - 1) / sw;
       const uint64_t work = P + nsl * (16ull * nlq + 24ull);
-      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, nsl / 32), std::max<uint64_t>(1, (work + h->tl_split / 2) / h->tl_split));
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, nsl / 32), std::max<uint64_t>(1, (work + tl_split / 2) / tl_split));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
         ItemRec it;
@@ -1943,7 +1959,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       const uint64_t sw = h->st_slot_bytes / ((qr.flags & QF_SIMPLE_OR) ? 4u : 8u);
       const uint64_t nsub = (h->n_docs + sw - 1) / sw;
       const uint64_t work = P + nsub * (16ull * nlq + 24ull);
-      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 1024), std::max<uint64_t>(1, (work + h->wsplit / 2) / h->wsplit));
+      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 1024), std::max<uint64_t>(1, (work + wsplit / 2) / wsplit));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
         ItemRec it;
