@@ -33,6 +33,8 @@ def lower_query(q):
         return [[(q.fieldname, None, q.boost)]], "every"
     if name == "Term":
         return [[(q.fieldname, q.text, q.boost)]], "groups"
+    if name in ("Or", "And") and not q.subqueries:
+        return [], "null"                     # Whoosh: a compound query without subqueries matches nothing
     if name == "Or":
         return [[(t.fieldname, t.text, t.boost * q.boost) for t in q.subqueries]], "groups"
     if name == "And":

@@ -1,0 +1,104 @@
+"""Edge cases of the CUDA path through the C ABI: empty and ragged inputs, degenerate indexes, repeated
+terms, extreme weights.  Every case is compared with the oracle."""
+import numpy as np
+import pytest
+
+from document_search_engine_b200 import And, BM25F, Every, FlatIndex, NullQuery, Or, Term
+from document_search_engine_b200 import _ffi
+from document_search_engine_b200.corpus import make_corpus, make_queries
+from oracle.numpy_oracle import NumpyOracle
+from tests.parity import assert_batch_parity, assert_query_parity
+
+pytestmark = pytest.mark.gpu
+VARIANTS = [0, 3, 4, 5, 1]
+
+
+def check(ix, queries, limit=10, **kw):
+    o = NumpyOracle(ix)
+    with ix.searcher(**kw) as s:
+        res = s.search_batch(queries, limit=limit)
+    assert len(res) == len(queries)
+    assert_batch_parity(o, queries, res, limit)
+    ix._engine_cache.clear()
+    return res
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_empty_batch_and_null_queries(variant):
+    ix = make_corpus(500, 200, 3, device="cpu")
+    with ix.searcher(variant=variant) as s:
+        assert s.search_batch([], limit=10) == []
+        empty = _ffi.PackedBatch([0], [], [], [], [])
+        sc, dc, cn, tt = s.engine.search_batch(empty, 10)
+        assert sc.shape == (0, 10) and tt.size == 0
+    ix._engine_cache.clear()
+    qs = [Term("body", "nope"), Or([Term("body", "nope"), Term("nofield", 3)]), And([Term("body", 5), Term("body", "nope")]),
+          NullQuery, Or([]), And([]), Term("body", 5)]
+    res = check(ix, qs, variant=variant)
+    assert [len(r) for r in res[:6]] == [0] * 6 and len(res[6]) > 0
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_degenerate_indexes(variant):
+    one = FlatIndex.from_documents([{"f": ["a", "b", "a"]}], ["f"])
+    check(one, [Term("f", "a"), And([Term("f", "a"), Term("f", "b")]), Or([Term("f", "b"), Term("f", "c")]), Every("f")], variant=variant)
+    gone = FlatIndex.from_documents([{"f": ["a"]}, {"f": ["a", "b"]}, {"f": ["b"]}], ["f"], deleted=[0, 1, 2])
+    res = check(gone, [Term("f", "a"), Or([Term("f", "a"), Term("f", "b")]), Every("f")], variant=variant)
+    assert all(r.is_empty() for r in res)
+    no_postings = FlatIndex.from_documents([{"f": []}, {"f": []}], ["f"])
+    res = check(no_postings, [Term("f", "a"), Every("f")], variant=variant)
+    assert all(r.is_empty() for r in res)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_repeated_terms_and_extreme_boosts(variant):
+    ix = make_corpus(4000, 300, 21, device="cpu")
+    qs = [Or([Term("body", 3), Term("body", 3)]),                       # the same list twice: scores add (W10)
+          And([Term("body", 3), Term("body", 3), Term("body", 7)]),
+          And([Or([Term("body", 3), Term("body", 4)]), Or([Term("body", 4), Term("body", 3)])]),
+          Or([Term("body", 2, boost=1e6), Term("body", 250, boost=1e-6)]),
+          And([Term("body", 1, boost=1e-20), Term("body", 2)]),           # tiny but positive weight
+          Or([Term("body", 299), Term("body", 298), Term("body", 297), Term("body", 296), Term("body", 295),
+              Term("body", 294), Term("body", 293), Term("body", 292)]),  # eight rare leaves
+          Or([Term("body", i) for i in range(40, 52)])]                   # twelve leaves: past the stream kernels' eight
+    check(ix, qs, variant=variant)
+    check(ix, qs, limit=1, variant=variant)
+    check(ix, qs, limit=128, variant=variant)
+
+
+def test_ragged_batch_sizes_and_splits():
+    """Batches of 1, 2, 1023, 1025 queries (the small-batch item splitting switches at 1024) and a
+    dense query cut into hundreds of items."""
+    ix = make_corpus(30000, 2000, 8, device="cpu")
+    o = NumpyOracle(ix)
+    qs = make_queries(1025, 2000, 4, 1, 4, "mixed", skip_top=0).queries
+    with ix.searcher() as s:
+        for n in (1, 2, 1023, 1025):
+            res = s.search_batch(qs[:n], limit=10)
+            assert_batch_parity(o, qs[:n], res, 10, sample=range(0, n, max(1, n // 60)))
+    ix._engine_cache.clear()
+    dense = [Or([Term("body", 0), Term("body", 1), Term("body", 2)]), And([Term("body", 0), Term("body", 1)])]
+    with ix.searcher(warp_split=256, isect_split=128, cta_split=256, variant=0) as s:
+        res = s.search_batch(dense, limit=10)
+        assert s.engine.stats()["n_items"] > 100
+    assert_batch_parity(o, dense, res, 10)
+
+
+def test_bad_arguments_raise():
+    ix = make_corpus(200, 100, 1, device="cpu")
+    with ix.searcher() as s:
+        with pytest.raises(_ffi.EngineError):
+            s.engine.search_batch(_ffi.PackedBatch([0, 1], [1], [10 ** 6], [1.0], [0]), 10)      # term id out of range
+        with pytest.raises(_ffi.EngineError):
+            s.engine.search_batch(_ffi.PackedBatch([0, 2], [2], [1, 2], [1.0, 1.0], [1, 0]), 10)  # groups must not decrease
+        with pytest.raises(_ffi.EngineError):
+            s.engine.search_batch(_ffi.PackedBatch([0, 1], [1], [1], [float("nan")], [0]), 10)
+        with pytest.raises(_ffi.EngineError):
+            s.engine.search_batch(_ffi.PackedBatch([0, 1], [1], [1], [1.0], [0]), 0)             # k out of range
+        with pytest.raises(ValueError):
+            s.search(Term("body", 1), limit=0)
+        # the engine is still usable afterwards
+        assert len(s.search(Term("body", 1))) == int(ix.df[ix.term_id("body", 1)])
+    with pytest.raises(_ffi.EngineError):
+        ix._engine_cache.clear()
+        ix.searcher(subtile_docs=100)                                                          # not a multiple of 128
