@@ -1815,18 +1815,20 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     uint64_t gsize[32];
     bool gseen[32];
     for (uint32_t g = 0; g < G; ++g) { gsize[g] = 0; gseen[g] = false; }
-    uint32_t prev_g = 0;
+    uint32_t prev_g = 0, n_neg_in = 0;
     bool all_pos = true;
     for (uint32_t i = a; i < e; ++i) {
       const uint32_t g = b->leaf_group[i];
-      if (g >= G || g < prev_g) PFAIL(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
+      const bool neg = (g == BM25F_GROUP_NOT);             // a leaf of a NOT clause: excludes, never scores
+      if ((!neg && g >= G) || g < prev_g) PFAIL(BM25F_EINVAL, "query %u: leaf_group must be non-decreasing and < n_groups", qi);
       prev_g = g;
-      gseen[g] = true;
+      if (!neg) gseen[g] = true;
       const uint32_t term = resolve_term(h, b->leaf_term[i]);
       if (term != BM25F_TERM_UNKNOWN) {
         if (term >= h->n_real_terms + h->n_fields) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, b->leaf_term[i]);
-        gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
+        if (!neg) gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
       }
+      if (neg) { ++n_neg_in; continue; }
       if (!(b->leaf_weight[i] > 1e-30f)) all_pos = false;
       if (!std::isfinite(b->leaf_weight[i])) PFAIL(BM25F_EINVAL, "query %u: leaf weight is not finite", qi);
     }
@@ -1842,6 +1844,26 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     for (uint32_t r = 0; r < G; ++r) rank[order[r]] = r;
     uint64_t P = 0;
     uint32_t nlq = 0;
+    // the leaves of NOT clauses go first: the accumulating kernels visit leaves in this order and a
+    // poisoned slot must be poisoned before a positive posting looks at it
+    uint32_t n_neg = 0;
+    for (uint32_t i = a; n_neg_in && i < e; ++i) {
+      if (b->leaf_group[i] != BM25F_GROUP_NOT) continue;
+      const uint32_t term = resolve_term(h, b->leaf_term[i]);
+      if (term == BM25F_TERM_UNKNOWN) continue;
+      const uint64_t off = h->term_offsets[term], df = h->term_offsets[term + 1] - off;
+      if (df == 0) continue;
+      LeafRec& lf = leaves[a + nlq];
+      lf.off = off;
+      lf.df = (uint32_t)df;
+      lf.w = 1.0f;
+      lf.norm_off = (uint32_t)h->term_field[term] * 256u;
+      lf.group = NEG_GROUP;
+      lf.qleaf0 = a;
+      P += df;
+      ++nlq;
+      ++n_neg;
+    }
     for (uint32_t r = 0; r < G; ++r) {
       for (uint32_t i = a; i < e; ++i) {
         if (b->leaf_group[i] != order[r]) continue;
@@ -1864,7 +1886,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     for (uint32_t i = a + nlq; i < e; ++i) { leaves[i] = LeafRec{}; leaves[i].qleaf0 = i; leaves[i].qnl = 1; }   // unused slots stay harmless
     qr.n_leaves = nlq;
     qr.n_groups = G;
-    qr.flags = (G == 1 && all_pos) ? QF_SIMPLE_OR : 0u;
+    qr.flags = (G == 1 && all_pos && n_neg == 0) ? QF_SIMPLE_OR : 0u;
     if (!all_pos) L.any_nonpos = true;
     const uint32_t out_leaf = a + nlq;   // one past the query's last leaf record
     L.postings += P;
@@ -1877,6 +1899,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     // ... unless its smallest group is so much sparser than the rest that looking its documents up in
     // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
     const uint64_t g0 = gsize[order[0]];
+    if (n_neg && !(k <= 128 && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
+      PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 128, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
     const bool isect_ok = k <= 128 && nlq <= 32 && all_pos && qr.after_key == 0ull;
     // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
     // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
@@ -1908,10 +1932,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }
     // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
-    const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (h->variant == 0 &&
+    const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
-    const bool use_team = !use_isect && !use_hash && stream_ok && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const bool use_team = !use_isect && !use_hash && stream_ok && n_neg == 0 && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_hash ? 4 : use_or1 ? 5 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
     if (use_hash) {

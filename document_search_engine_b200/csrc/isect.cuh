@@ -83,8 +83,9 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
         if (lane == l) s_start = st;
       }
     }
-    // candidate leaves: the leaves of the smallest group (they come first); all but the dense one for a one-dense OR
-    const int n_cand = stream_last ? L - 1 : __popc(__ballot_sync(0xFFFFFFFFu, s_grp == 0u));
+    // candidate leaves: the leaves of the smallest group (rank 0; leaves of NOT clauses precede them); all but
+    // the dense one for a one-dense OR
+    const unsigned cand_mask = __ballot_sync(0xFFFFFFFFu, stream_last ? (lane < L - 1) : (s_grp == 0u));
 
     unsigned long long top[KR];               // lane i, row j: the (32 j + i)-th best key of this item so far
 #pragma unroll
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
     float thr = 0.0f;
     unsigned int tot = 0;
 
-    for (int c = 0; c < n_cand; ++c) {
+    for (unsigned cm = cand_mask; cm; cm &= cm - 1u) {
+      const int c = __ffs(cm) - 1;
       const uint2* __restrict__ cp = store + __shfl_sync(0xFFFFFFFFu, s_off, c);
       const uint32_t c_df = __shfl_sync(0xFFFFFFFFu, s_df, c);
       const float c_w = __shfl_sync(0xFFFFFFFFu, s_w, c);
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
             const uint2 h = ldg_pair(lp + lo);
             if (h.x == doc) {
               score = fmaf(wl, __uint_as_float(h.y), score);
-              sat |= 1u << g;
+              sat |= 1u << g;                      // a leaf of a NOT clause sets bit NEG_GROUP, which `full` never has
               if (g == 0u && l < c) dead = true;   // already a candidate of an earlier leaf of the group
               if (stream_last && l == L - 1 && !dead) atomicOr(taken + (lo >> 5), 1u << (lo & 31u));
             }

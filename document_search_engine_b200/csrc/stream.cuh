@@ -154,8 +154,16 @@ __device__ __forceinline__ void or_four(const SubCtx& cx, float w, const uint2 (
 }
 
 // ---- AND of OR-groups: 8-byte {groups matched, score} slots ---------------------------------
+// A leaf of a NOT clause (group NEG_GROUP; such queries have at most NEG_GROUP - 1 positive groups) poisons
+// the slot: leaves are visited negatives first, and no posting of a positive group ever finds "groups
+// matched" equal to its rank in a poisoned slot.
+constexpr uint32_t NEG_GROUP = 31u;
+constexpr uint32_t SLOT_POISON = 0xFFFFFFF0u;
+
+template <bool NEG>                                     // NEG: the kernel serves NOT clauses
 __device__ __forceinline__ void and_one(const SubCtx& cx, float w, uint32_t g, bool lastg, uint32_t d, uint32_t ubits, unsigned& tot) {
   const uint32_t a = cx.sbase + (d << 3);
+  if (NEG && g == NEG_GROUP) { sts_v2(a, SLOT_POISON, 0u); return; }
   const uint2 v = lds_v2(a);
   if (v.x - g <= 1u) {                                  // alive: all earlier groups matched
     const float old = __uint_as_float(v.y);
@@ -168,11 +176,17 @@ __device__ __forceinline__ void and_one(const SubCtx& cx, float w, uint32_t g, b
     }
   }
 }
+template <bool NEG>
 __device__ __forceinline__ void and_four(const SubCtx& cx, float w, uint32_t g, bool lastg, const uint2 (&q)[4], unsigned& tot) {
   uint32_t a[4];
   uint2 v[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) a[e] = cx.sbase + (q[e].x << 3);
+  if (NEG && g == NEG_GROUP) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sts_v2(a[e], SLOT_POISON, 0u);
+    return;
+  }
 #pragma unroll
   for (int e = 0; e < 4; ++e) v[e] = lds_v2(a[e]);
 #pragma unroll
@@ -303,7 +317,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
           const unsigned mk = __ballot_sync(0xFFFFFFFFu, act);
           if (act) {
             if (simple_or) or_one(cx, w, r.x, r.y, tot);
-            else and_one(cx, w, g, lastg, r.x, r.y, tot);
+            else and_one<true>(cx, w, g, lastg, r.x, r.y, tot);
           }
           const uint32_t n = (uint32_t)__popc(mk);
           cur += n;
@@ -330,7 +344,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
               const uint32_t dlast = __shfl_sync(0xFFFFFFFFu, qa[3].x, 31);
               if (dlast < cx.sub_hi) {          // entirely inside the sub-range: no masks
                 if (simple_or) or_four(cx, w, qa, tot);
-                else and_four(cx, w, g, lastg, qa, tot);
+                else and_four<true>(cx, w, g, lastg, qa, tot);
                 cur += 128u;
                 if (!have_next) break;          // fewer than 128 postings left: back to single rows
 #pragma unroll
@@ -344,7 +358,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
                     const unsigned m2 = __ballot_sync(0xFFFFFFFFu, a2);
                     if (a2) {
                       if (simple_or) or_one(cx, w, qa[e].x, qa[e].y, tot);
-                      else and_one(cx, w, g, lastg, qa[e].x, qa[e].y, tot);
+                      else and_one<true>(cx, w, g, lastg, qa[e].x, qa[e].y, tot);
                     }
                     const uint32_t n2 = (uint32_t)__popc(m2);
                     cur += n2;

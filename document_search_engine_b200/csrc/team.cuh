@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(TM_MAX_WARPS * 32, 1) k_score_team(TeamParams 
           if (hi - lo <= 32u) {
             if ((uint32_t)lane < hi - lo) {
               if (simple_or) or_one(cx, w, r.x, r.y, tot);
-              else and_one(cx, w, g, lastg, r.x, r.y, tot);
+              else and_one<false>(cx, w, g, lastg, r.x, r.y, tot);
             }
           } else {
             uint32_t i0 = lo & ~127u;
@@ -241,14 +241,14 @@ __global__ void __launch_bounds__(TM_MAX_WARPS * 32, 1) k_score_team(TeamParams 
               }
               if (i0 >= lo && i0 + 128u <= hi) {           // interior super-row: no masks
                 if (simple_or) or_four(cx, w, qa, tot);
-                else and_four(cx, w, g, lastg, qa, tot);
+                else and_four<false>(cx, w, g, lastg, qa, tot);
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const uint32_t idx = i0 + (uint32_t)lane + 32u * e;
                   if (idx >= lo && idx < hi) {
                     if (simple_or) or_one(cx, w, qa[e].x, qa[e].y, tot);
-                    else and_one(cx, w, g, lastg, qa[e].x, qa[e].y, tot);
+                    else and_one<false>(cx, w, g, lastg, qa[e].x, qa[e].y, tot);
                   }
                 }
               }

@@ -4,9 +4,10 @@ The reference builds its trees with ``whoosh.qparser.QueryParser`` (default
 group AND, ``OR`` keyword; reference ``my_flask.py:189-193``, ``:302``) and
 greps ``str(query)`` for ``"<field>:"`` (``my_flask.py:201-205``).  The engine
 needs ``Term`` / ``And`` / ``Or`` (b) plus ``Every`` for the
-CLI probe (``cli.py:8-9``).  A tiny parser for the ``a b OR c field:d`` subset
-is provided so the front ends have something to call; the full query language
-(phrases, wildcards, ranges, NOT) is out of scope.
+CLI probe (``cli.py:8-9``) and ``Not`` for the UI's ``a NOT b``
+(``search-form.html:20-40``).  A tiny parser for the ``a b OR c NOT e field:d``
+subset is provided so the front ends have something to call; the rest of the
+query language (phrases, wildcards, ranges) is out of scope.
 
 ``normalize()`` lowers a tree to the engine's input form: an AND of groups,
 each group an OR of weighted leaves.  ``Or`` of plain leaves is the one-group
@@ -188,6 +189,42 @@ class Or(_Compound):
     JOINT = " OR "
 
 
+class Not(Query):
+    """Excludes the documents matching ``query``.  Served inside ``And`` (Whoosh turns ``And([a, Not(b)])``
+    into an AndNot matcher: the documents of ``a`` that are not in ``b``, scored by ``a`` alone);
+    reference UI help ``search-form.html:20-40``."""
+
+    def __init__(self, query: Query, boost: float = 1.0):
+        if not isinstance(query, Query):
+            raise TypeError("%r is not a query" % (query,))
+        self.query = query
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return isinstance(other, Not) and other.query == self.query
+
+    def __hash__(self):
+        return hash(("Not", self.query))
+
+    def __repr__(self):
+        return "Not(%r)" % (self.query,)
+
+    def __str__(self):
+        return "NOT " + str(self.query)
+
+    def leaves(self):
+        return iter(())              # a negated term is not a scoring leaf
+
+    def normalize(self):
+        q = self.query.normalize()
+        if isinstance(q, _Null):
+            return NullQuery         # NOT nothing: no constraint (dropped by the enclosing And)
+        return Not(q)
+
+
+#: ``Leaf.group`` of a leaf inside a NOT clause (BM25F_GROUP_NOT in include/bm25f.h)
+GROUP_NOT = 255
+
 # --------------------------------------------------------------------------
 # Lowering to the engine's input form
 # --------------------------------------------------------------------------
@@ -218,28 +255,41 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
         return [Leaf(q.fieldname, None, q.boost, 0)], 1, "every"
     if isinstance(q, Term):
         return [Leaf(q.fieldname, q.text, q.boost, 0)], 1, "groups"
-    if isinstance(q, Or):
-        leaves = []
-        for s in q.subqueries:
-            if not isinstance(s, Term):
-                raise UnsupportedQuery("Or() may only contain Term leaves on the GPU path: %r" % (s,))
-            leaves.append(Leaf(s.fieldname, s.text, s.boost * q.boost, 0))
-        return leaves, 1, "groups"
-    if isinstance(q, And):
-        leaves = []
+    if isinstance(q, Not):
+        # Whoosh's root-level Not is an InverseMatcher over every document of the index, a full scan
+        # outside this path.
+        raise UnsupportedQuery("a top-level Not() has no positive part to score: %r" % (q,))
+    if isinstance(q, (And, Or)):
+        # Whoosh's compound matcher pulls the Not children out, builds the matcher of the rest and
+        # wraps it in AndNotMatcher(rest, union of the negated queries); nothing positive -> no hits.
+        conj = isinstance(q, And)
+        leaves: List[Leaf] = []
+        negatives: List[Leaf] = []
         g = 0
         for s in q.subqueries:
             if isinstance(s, Term):
                 leaves.append(Leaf(s.fieldname, s.text, s.boost * q.boost, g))
-            elif isinstance(s, Or):
+            elif isinstance(s, Or) and conj:
                 for t in s.subqueries:
                     if not isinstance(t, Term):
                         raise UnsupportedQuery("And(Or(...)) groups may only contain Term leaves: %r" % (t,))
                     leaves.append(Leaf(t.fieldname, t.text, t.boost * s.boost * q.boost, g))
+            elif isinstance(s, Not):
+                inner = s.query.subqueries if isinstance(s.query, Or) else [s.query]
+                for t in inner:
+                    if not isinstance(t, Term):
+                        raise UnsupportedQuery("Not() may contain a Term or an Or of Terms: %r" % (t,))
+                    negatives.append(Leaf(t.fieldname, t.text, 1.0, GROUP_NOT))
+                continue
+            elif conj:
+                raise UnsupportedQuery("And() may contain Term, Or(Term...) or Not(...) children: %r" % (s,))
             else:
-                raise UnsupportedQuery("And() may contain Term or Or(Term...) children: %r" % (s,))
-            g += 1
-        return leaves, g, "groups"
+                raise UnsupportedQuery("Or() may contain Term or Not(...) children on the GPU path: %r" % (s,))
+            if conj:
+                g += 1
+        if not leaves:
+            return [], 0, "null"
+        return leaves + negatives, (g if conj else 1), "groups"
     raise UnsupportedQuery("unsupported query node %r" % (q,))
 
 
@@ -252,7 +302,7 @@ _TOKEN_RE = re.compile(r"\s*(?:(\w+):)?([^\s()]+)")
 
 class QueryParser:
     """``QueryParser(fieldname, schema)`` for the subset ``a b``, ``a AND b``,
-    ``a OR b``, ``field:a``.  AND binds tighter than OR, as in Whoosh's default
+    ``a OR b``, ``a NOT b``, ``field:a``.  AND binds tighter than OR, as in Whoosh's default
     grammar.  ``analyzer`` maps a raw token to zero or more index terms
     (lower-casing, stemming ...); the default lower-cases.
     """
@@ -270,7 +320,7 @@ class QueryParser:
         nodes: List[object] = []          # Query nodes and the markers "AND" / "OR"
         for m in _TOKEN_RE.finditer(text or ""):
             field, tok = m.group(1), m.group(2)
-            if field is None and tok in ("AND", "OR"):
+            if field is None and tok in ("AND", "OR", "NOT"):
                 nodes.append(tok)
                 continue
             field = field or self.fieldname
@@ -281,6 +331,20 @@ class QueryParser:
                 nodes.append(terms[0])
             elif terms:
                 nodes.append(And(terms))
+        # NOT negates the node that follows it
+        out0: List[object] = []
+        i = 0
+        while i < len(nodes):
+            if nodes[i] == "NOT":
+                if i + 1 < len(nodes) and isinstance(nodes[i + 1], Query):
+                    out0.append(Not(nodes[i + 1]))
+                    i += 2
+                else:
+                    i += 1             # dangling NOT: drop it
+                continue
+            out0.append(nodes[i])
+            i += 1
+        nodes = out0
         # Infix operators take their immediate neighbours, AND before OR; what is
         # left side by side is joined by the default group (AND), as the
         # reference's form explains ("both words", search-form.html:21).

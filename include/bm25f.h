@@ -55,6 +55,9 @@ extern "C" {
 #define BM25F_MAX_LEAVES_PER_QUERY 64
 #define BM25F_MAX_K               1024
 #define BM25F_TERM_UNKNOWN 0xFFFFFFFFu  /* leaf_term value for a term/field not in the index (empty matcher) */
+#define BM25F_GROUP_NOT 0xFFu            /* leaf_group value of a leaf inside a NOT clause: its documents are excluded from
+                                            the query's matches and it contributes no score (Whoosh AndNot); such leaves
+                                            come last in the query (groups are non-decreasing) */
 #define BM25F_TERM_EVERY_BASE 0xFFFFFF00u  /* leaf_term = BASE + field: Whoosh's Every(field) - every live document
                                               that has the field, constant score = leaf_weight (reference cli.py:9) */
 
@@ -127,7 +130,7 @@ typedef struct {
   const uint8_t*  query_n_groups;      /* [n_queries]; 0 = null query (matches nothing) */
   const uint32_t* leaf_term;           /* [n_leaves] posting-list id or BM25F_TERM_UNKNOWN */
   const float*    leaf_weight;         /* [n_leaves] idf * (K1 + 1) * boost, rounded from float64 */
-  const uint8_t*  leaf_group;          /* [n_leaves] group index inside the query */
+  const uint8_t*  leaf_group;          /* [n_leaves] group index inside the query, or BM25F_GROUP_NOT */
   const uint64_t* after_keys;          /* [n_queries] or NULL: only hits ordered strictly after this
                                           key are collected (paging past BM25F_MAX_K); 0 = no bound */
 } bm25f_query_batch;

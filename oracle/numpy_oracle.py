@@ -24,29 +24,35 @@ B2L_SCORING[0] = 1.0            # W5: byte 0 → default length 1
 
 
 def lower_query(q):
-    """``(groups, kind)``: ``groups`` is a list of OR-groups, each a list of
-    ``(fieldname, text, boost)``; all groups must match (W10)."""
+    """``(groups, negatives, kind)``: ``groups`` is a list of OR-groups, each a list of
+    ``(fieldname, text, boost)``; all groups must match (W10) and no leaf of ``negatives``
+    (``(fieldname, text)`` from Not children, Whoosh's AndNotMatcher) may."""
     name = type(q).__name__
     if name == "_Null":
-        return [], "null"
+        return [], [], "null"
     if name == "Every":
-        return [[(q.fieldname, None, q.boost)]], "every"
+        return [[(q.fieldname, None, q.boost)]], [], "every"
     if name == "Term":
-        return [[(q.fieldname, q.text, q.boost)]], "groups"
-    if name in ("Or", "And") and not q.subqueries:
-        return [], "null"                     # Whoosh: a compound query without subqueries matches nothing
-    if name == "Or":
-        return [[(t.fieldname, t.text, t.boost * q.boost) for t in q.subqueries]], "groups"
-    if name == "And":
-        groups = []
+        return [[(q.fieldname, q.text, q.boost)]], [], "groups"
+    if name in ("Or", "And"):
+        groups, flat, neg = [], [], []
         for s in q.subqueries:
-            if type(s).__name__ == "Term":
-                groups.append([(s.fieldname, s.text, s.boost * q.boost)])
-            elif type(s).__name__ == "Or":
+            sn = type(s).__name__
+            if sn == "Term":
+                (groups if name == "And" else flat).append(
+                    [(s.fieldname, s.text, s.boost * q.boost)] if name == "And" else (s.fieldname, s.text, s.boost * q.boost))
+            elif sn == "Or" and name == "And":
                 groups.append([(t.fieldname, t.text, t.boost * s.boost * q.boost) for t in s.subqueries])
+            elif sn == "Not":
+                inner = s.query.subqueries if type(s.query).__name__ == "Or" else [s.query]
+                neg.extend((t.fieldname, t.text) for t in inner)
             else:
                 raise NotImplementedError(s)
-        return groups, "groups"
+        if flat:
+            groups = [flat]
+        if not groups:
+            return [], [], "null"             # Whoosh: a compound query without positive subqueries matches nothing
+        return groups, neg, "groups"
     raise NotImplementedError(name)
 
 
@@ -88,7 +94,7 @@ class NumpyOracle:
 
     def match_all(self, q):
         """All matches as (global docids ascending, float64 scores)."""
-        groups, kind = lower_query(q)
+        groups, negatives, kind = lower_query(q)
         if kind == "null":
             return np.zeros(0, np.int64), np.zeros(0, np.float64)
         ds, ss = [], []
@@ -114,6 +120,9 @@ class NumpyOracle:
                     acc[d] += s                                                  # W10: sum of leaf scores
                     hit[d] = True
                 cnt += hit
+            for fname, text in negatives:
+                d, _ = self.leaf_scores(sub, fname, text, 1.0)
+                cnt[d] = -1                                                      # AndNot: excluded
             d = np.nonzero(cnt == len(groups))[0]
             ds.append(d + sub.doc_base)
             ss.append(acc[d])

@@ -20,7 +20,7 @@ heap collector), because that is what the CPU baseline is meant to time.
 The index argument is duck-typed: any object with ``term_offsets``, ``docids``,
 ``tfs``, ``len_bytes[f, d]``, ``field_length_total``, ``df``, ``deleted``,
 ``doc_base``, ``field_names``, ``doc_count_all()`` and ``term_id(field, text)``.
-Queries are duck-typed on the class names ``Term`` / ``And`` / ``Or`` / ``Every``.
+Queries are duck-typed on the class names ``Term`` / ``And`` / ``Or`` / ``Not`` / ``Every``.
 """
 from __future__ import annotations
 
@@ -141,11 +141,18 @@ class OracleSearcher:
             ids = [d for d in range(lb.shape[0]) if lb[d] and not (dele is not None and dele[d])]
             return ConstMatcher(ids, q.boost)
         if name in ("And", "Or"):
-            subs = [self._matcher(s, sub) for s in q.subqueries]
+            # Whoosh's compound matcher takes the Not children out first, builds the matcher of the
+            # rest, and wraps it in AndNotMatcher(rest, union of the negated queries).
+            nots = [s.query for s in q.subqueries if type(s).__name__ == "Not"]
+            subs = [self._matcher(s, sub) for s in q.subqueries if type(s).__name__ != "Not"]
             if not subs:
                 return NullMatcher()
             cls = IntersectionMatcher if name == "And" else UnionMatcher
             m = _binary_tree(cls, subs)
+            if nots:
+                notm = _binary_tree(UnionMatcher, [self._matcher(s, sub) for s in nots])
+                if notm.is_active():
+                    m = AndNotMatcher(m, notm)
             return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
         if name == "_Null":
             return NullMatcher()
@@ -364,6 +371,42 @@ class IntersectionMatcher:
 
     def score(self):
         return self.a.score() + self.b.score()
+
+
+class AndNotMatcher:
+    """Whoosh matching.binary.AndNotMatcher: documents of ``a`` that are not in ``b``; score = a's."""
+
+    def __init__(self, a, b):
+        self.a = a
+        self.b = b
+        self._find()
+
+    def _find(self):
+        a, b = self.a, self.b
+        while a.is_active():
+            if b.is_active() and b.id() < a.id():
+                b.skip_to(a.id())
+            if b.is_active() and b.id() == a.id():
+                a.next()
+                continue
+            return
+
+    def is_active(self):
+        return self.a.is_active()
+
+    def id(self):
+        return self.a.id()
+
+    def next(self):
+        self.a.next()
+        self._find()
+
+    def skip_to(self, d):
+        self.a.skip_to(d)
+        self._find()
+
+    def score(self):
+        return self.a.score()
 
 
 # ---------------------------------------------------------------------------
