@@ -26,7 +26,7 @@ EXPORTS = (
     "bm25f_abi_version", "bm25f_last_error", "bm25f_create", "bm25f_destroy", "bm25f_set_weighting",
     "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
-    "bm25f_reset_stats",
+    "bm25f_reset_stats", "bm25f_submit", "bm25f_collect",
 )
 
 
@@ -104,6 +104,8 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_decode_keys.argtypes = [vp, vp, u32, i32, vp, vp, vp, vp]
     lib.bm25f_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.bm25f_reset_stats.argtypes = [vp]
+    lib.bm25f_submit.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, C.POINTER(vp)]
+    lib.bm25f_collect.argtypes = [vp, vp, vp, vp, vp, vp]
     if lib.bm25f_abi_version() != ABI_VERSION:
         raise RuntimeError("libbm25f ABI %d != binding ABI %d" % (lib.bm25f_abi_version(), ABI_VERSION))
     if path == os.environ.get("BM25F_LIB", LIB_PATH):
@@ -192,6 +194,32 @@ class Plan:
             pass
 
 
+class Pending:
+    """A batch submitted with ``Engine.submit``: its kernels and the copy of its results are in flight."""
+
+    def __init__(self, engine: "Engine", handle, n_queries: int, k: int):
+        self.engine = engine
+        self._p = handle
+        self.n_queries = n_queries
+        self.k = k
+
+    def collect(self):
+        """Wait for the batch; ``(scores, docids, counts, totals)`` as ``Engine.search_batch`` returns them."""
+        if self._p is None:
+            raise RuntimeError("batch already collected")
+        q, k = self.n_queries, self.k
+        scores = np.empty((q, k), dtype=np.float32)
+        docids = np.empty((q, k), dtype=np.uint32)
+        counts = np.empty(q, dtype=np.uint32)
+        totals = np.empty(q, dtype=np.uint64)
+        rc = self.engine.lib.bm25f_collect(self.engine._h, self._p, _ptr(scores), _ptr(docids), _ptr(counts),
+                                           _ptr(totals))
+        if rc != -1:                        # a refused call (BM25F_EINVAL) leaves the batch in flight;
+            self._p = None                  # otherwise bm25f_collect has freed the plan
+        _check(self.engine.lib, rc)
+        return scores, docids, counts, totals
+
+
 class Engine:
     """One uploaded index shard on one GPU."""
 
@@ -240,6 +268,14 @@ class Engine:
         _check(self.lib, self.lib.bm25f_search_batch(self._h, C.byref(d), k, _ptr(scores), _ptr(docids),
                                                      _ptr(counts), _ptr(totals)))
         return scores, docids, counts, totals
+
+    def submit(self, batch: PackedBatch, k: int) -> Pending:
+        """Plan, upload and launch a batch without waiting for it (``bm25f_submit``).  At most two batches
+        may be in flight; collect them in submission order."""
+        d = batch.desc()
+        p = C.c_void_p()
+        _check(self.lib, self.lib.bm25f_submit(self._h, C.byref(d), k, C.byref(p)))
+        return Pending(self, p, batch.n_queries, k)
 
     def merge_keys(self, d_keys: int, n_lists: int, n_queries: int, k: int, d_out: int):
         """Runs on the handle's stream (see ``set_stream``)."""

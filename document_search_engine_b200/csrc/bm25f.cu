@@ -1198,11 +1198,22 @@ struct bm25f_handle {
   bm25f_stats stats{};
   uint64_t device_bytes = 0;
   unsigned long long* d_prof = nullptr;   // BM25F_PROFILE builds only
-  // grow-only workspaces reused by bm25f_search_batch (no cudaMalloc / cudaFree per call)
-  unsigned char* d_arena = nullptr;
-  size_t d_arena_cap = 0;
-  unsigned char* h_arena = nullptr;       // pinned
-  size_t h_arena_cap = 0;
+  // Grow-only workspaces reused by bm25f_search_batch / bm25f_submit (no cudaMalloc / cudaFree per call).
+  // There are two, used alternately, so that the host can plan and upload batch i + 1 while the GPU
+  // still runs batch i.
+  struct Arena {
+    unsigned char* d = nullptr;           // device: plan records, partial lists, results
+    size_t d_cap = 0;
+    unsigned char* h = nullptr;           // pinned staging of the plan records
+    size_t h_cap = 0;
+    unsigned char* h_out = nullptr;       // pinned landing zone of a submitted batch's results
+    size_t h_out_cap = 0;
+    cudaEvent_t ev_ready = nullptr;       // the plan's records are on the device (copy stream)
+    cudaEvent_t ev_done = nullptr;        // a submitted batch's results are in h_out
+    bm25f_plan* submitted = nullptr;      // submitted and not yet collected
+  } arenas[2];
+  int arena_next = 0;
+  cudaStream_t copy_stream = nullptr;    // plan uploads, so that they do not queue behind the running batch
   PlanPool* pool = nullptr;              // created on the first large batch
 };
 
@@ -1234,7 +1245,9 @@ struct bm25f_plan {
   uint32_t* d_docids = nullptr;
   uint32_t* d_counts = nullptr;
   size_t smem_score = 0;
-  bool owns_memory = true;      // false: buffers live in the handle's arena (bm25f_search_batch)
+  bool owns_memory = true;      // false: buffers live in one of the handle's arenas (bm25f_search_batch)
+  int arena = -1;               // which one
+  bool submitted = false;       // bm25f_submit: bm25f_execute also brings the results to the arena's pinned h_out
   bool simple_kernel = false;   // k_score_topk instead of k_score_pipe (option, or a non-positive leaf weight)
 };
 
@@ -1326,8 +1339,14 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_pairs);
   cudaFree(h->d_norm);
   cudaFree(h->d_prof);
-  cudaFree(h->d_arena);
-  if (h->h_arena) cudaFreeHost(h->h_arena);
+  for (auto& A : h->arenas) {
+    cudaFree(A.d);
+    if (A.h) cudaFreeHost(A.h);
+    if (A.h_out) cudaFreeHost(A.h_out);
+    if (A.ev_ready) cudaEventDestroy(A.ev_ready);
+    if (A.ev_done) cudaEventDestroy(A.ev_done);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
@@ -1439,6 +1458,11 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
 
   CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& A : h->arenas) {
+    CUH(cudaEventCreateWithFlags(&A.ev_ready, cudaEventDisableTiming));
+    CUH(cudaEventCreateWithFlags(&A.ev_done, cudaEventDisableTiming));
+  }
   CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   h->stream = h->own_stream;
@@ -1738,20 +1762,24 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   std::vector<QueryRec> own_queries;
   LeafRec* leaves;
   QueryRec* queries;
+  const int slot = use_arena ? h->arena_next : 0;
+  bm25f_handle::Arena& A = h->arenas[slot];
   if (use_arena) {
+    if (A.submitted) return fail(BM25F_EINVAL, "two submitted batches are in flight: bm25f_collect the oldest one first");
+    h->arena_next ^= 1;
     // items are appended after planning; reserve generously (grown below if needed)
     const size_t want = hl_bytes + hq_bytes;
-    if (h->h_arena_cap < want + (1u << 20)) {
-      if (h->h_arena) cudaFreeHost(h->h_arena);
-      h->h_arena = nullptr;
-      h->h_arena_cap = 0;
+    if (A.h_cap < want + (1u << 20)) {
+      if (A.h) cudaFreeHost(A.h);
+      A.h = nullptr;
+      A.h_cap = 0;
       const size_t cap = align_up((want + (1u << 20)) * 2, 1u << 20);
-      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_arena), cap, cudaHostAllocDefault);
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&A.h), cap, cudaHostAllocDefault);
       if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e));
-      h->h_arena_cap = cap;
+      A.h_cap = cap;
     }
-    leaves = reinterpret_cast<LeafRec*>(h->h_arena);
-    queries = reinterpret_cast<QueryRec*>(h->h_arena + hl_bytes);
+    leaves = reinterpret_cast<LeafRec*>(A.h);
+    queries = reinterpret_cast<QueryRec*>(A.h + hl_bytes);
   } else {
     own_leaves.resize(NL);
     own_queries.resize(Q);
@@ -2084,6 +2112,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   for (int c = 0; c < 6; ++c) p->postings_cls[c] = cls_postings[c];
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
+  p->arena = use_arena ? slot : -1;
 
 #define RCP(x)                                    \
   do {                                            \
@@ -2106,19 +2135,19 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   if (use_arena) {
     // the sorted item records follow the leaf / query records in the pinned arena
     const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec));
-    if (need > h->h_arena_cap) {
+    if (need > A.h_cap) {
       unsigned char* bigger = nullptr;
       const size_t cap = align_up(need * 2, 1u << 20);
       cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&bigger), cap, cudaHostAllocDefault);
       if (e != cudaSuccess) { delete p; return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e)); }
-      memcpy(bigger, h->h_arena, hl_bytes + hq_bytes);
-      cudaFreeHost(h->h_arena);
-      h->h_arena = bigger;
-      h->h_arena_cap = cap;
-      leaves = reinterpret_cast<LeafRec*>(h->h_arena);
-      queries = reinterpret_cast<QueryRec*>(h->h_arena + hl_bytes);
+      memcpy(bigger, A.h, hl_bytes + hq_bytes);
+      cudaFreeHost(A.h);
+      A.h = bigger;
+      A.h_cap = cap;
+      leaves = reinterpret_cast<LeafRec*>(A.h);
+      queries = reinterpret_cast<QueryRec*>(A.h + hl_bytes);
     }
-    h_items = reinterpret_cast<ItemRec*>(h->h_arena + hl_bytes + hq_bytes);
+    h_items = reinterpret_cast<ItemRec*>(A.h + hl_bytes + hq_bytes);
   } else {
     own_items.resize(n_it);
     h_items = own_items.data();
@@ -2139,17 +2168,18 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
                  o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 5) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
                  o_taken = take((size_t)(taken_words + 1) * 4);
-    if (off > h->d_arena_cap) {
+    if (off > A.d_cap) {
       CUP(cudaStreamSynchronize(h->stream));
-      cudaFree(h->d_arena);
-      h->d_arena = nullptr;
-      h->d_arena_cap = 0;
+      CUP(cudaStreamSynchronize(h->copy_stream));
+      cudaFree(A.d);
+      A.d = nullptr;
+      A.d_cap = 0;
       const size_t cap = align_up(off + off / 2, 1u << 20);
-      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_arena), cap);
+      cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&A.d), cap);
       if (e != cudaSuccess) { delete p; return fail(BM25F_ENOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e)); }
-      h->d_arena_cap = cap;
+      A.d_cap = cap;
     }
-    unsigned char* d = h->d_arena;
+    unsigned char* d = A.d;
     p->d_leaves = reinterpret_cast<LeafRec*>(d + o_leaves);
     p->d_queries = reinterpret_cast<QueryRec*>(d + o_queries);
     p->d_items = reinterpret_cast<ItemRec*>(d + o_items);
@@ -2180,11 +2210,15 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->d_items_hs = p->d_items_is + p->n_is;
   p->d_items_o1 = p->d_items_hs + p->n_hs;
   auto t_c = now();
-  if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, h->stream));
-  if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, h->stream));
-  if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, h->stream));
-  // pageable sources must outlive the copy; the pinned arena is only rewritten by the next
-  // search_batch, which runs after this one has synchronised in bm25f_fetch
+  // Arena plans upload on the copy stream (bm25f_execute waits for ev_ready): the records of the next batch
+  // travel while the current one is still being scored.  Nothing else touches this arena: its previous
+  // batch was fetched / collected before it was handed out again.
+  cudaStream_t up = use_arena ? h->copy_stream : h->stream;
+  if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, up));
+  if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, up));
+  if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, up));
+  if (use_arena) CUP(cudaEventRecord(A.ev_ready, up));
+  // pageable sources must outlive the copy; a pinned arena is only rewritten two batches later
   if (!use_arena) CUP(cudaStreamSynchronize(h->stream));
   if (trace) {
     auto us = [](auto x, auto y) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count() / 1e3; };
@@ -2218,6 +2252,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     if (rc) return rc;
   }
   cudaEvent_t* ev = h->ev[h->ev_head];
+  if (p->arena >= 0) CU(cudaStreamWaitEvent(st, h->arenas[p->arena].ev_ready, 0));
   CU(cudaEventRecord(ev[0], st));
   CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 5) * 8, st));   // totals + the five work counters
   if (p->taken_words) CU(cudaMemsetAsync(p->d_taken, 0, (size_t)p->taken_words * 4, st));
@@ -2295,8 +2330,9 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
       const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
       CU(cudaEventRecord(ev[4], st));
-      if (p->k <= 32) k_score_stream<1><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
-      else k_score_stream<4><<<grid, h->st_warps * 32u, stream_smem_bytes(h->st_warps, h->st_slot_bytes), st>>>(stp);
+      const size_t smem = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
+      if (p->k <= 32) k_score_stream<1><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      else k_score_stream<4><<<grid, h->st_warps * 32u, smem, st>>>(stp);
       CU(cudaEventRecord(ev[5], st));
       CU(cudaGetLastError());
       ++launches;
@@ -2411,6 +2447,27 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   CU(cudaEventRecord(ev[3], st));
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
+  if (p->submitted) {
+    // results -> the arena's pinned landing zone, behind the kernels on the same stream
+    bm25f_handle::Arena& A = h->arenas[p->arena];
+    const size_t n = (size_t)p->Q * p->k;
+    const size_t o_doc = align_up(n * 4), o_cnt = o_doc + align_up(n * 4), o_tot = o_cnt + align_up((size_t)p->Q * 4),
+                 need = o_tot + align_up((size_t)p->Q * 8);
+    if (need > A.h_out_cap) {
+      if (A.h_out) cudaFreeHost(A.h_out);
+      A.h_out = nullptr;
+      A.h_out_cap = 0;
+      const size_t cap = align_up(need + need / 2, 1u << 20);
+      cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&A.h_out), cap, cudaHostAllocDefault);
+      if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e));
+      A.h_out_cap = cap;
+    }
+    if (n) CU(cudaMemcpyAsync(A.h_out, p->d_scores, n * 4, cudaMemcpyDeviceToHost, st));
+    if (n) CU(cudaMemcpyAsync(A.h_out + o_doc, p->d_docids, n * 4, cudaMemcpyDeviceToHost, st));
+    if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_cnt, p->d_counts, (size_t)p->Q * 4, cudaMemcpyDeviceToHost, st));
+    if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_tot, p->d_totals, (size_t)p->Q * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(A.ev_done, st));
+  }
   h->stats.postings_touched = p->postings;
   h->stats.postings_stream = p->postings_cls[0];
   h->stats.postings_team = p->postings_cls[1];
@@ -2482,6 +2539,43 @@ int bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* b, int k, float
   if (!rc) rc = bm25f_fetch(h, p, out_scores, out_docids, out_counts, out_totals);
   bm25f_plan_destroy(p);
   return rc;
+}
+
+int bm25f_submit(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
+  if (!out) return fail(BM25F_EINVAL, "null argument");
+  bm25f_plan* p = nullptr;
+  int rc = prepare_impl(h, b, k, &p, true);
+  if (rc) return rc;
+  p->submitted = true;
+  rc = bm25f_execute(h, p);
+  if (rc) { bm25f_plan_destroy(p); return rc; }
+  h->arenas[p->arena].submitted = p;
+  *out = p;
+  return 0;
+}
+
+int bm25f_collect(bm25f_handle* h, bm25f_plan* p, float* out_scores, uint32_t* out_docids, uint32_t* out_counts,
+                  uint64_t* out_totals) {
+  if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
+  if (!p->submitted || p->arena < 0 || h->arenas[p->arena].submitted != p) return fail(BM25F_EINVAL, "not a submitted plan");
+  CU(cudaSetDevice(h->device));
+  bm25f_handle::Arena& A = h->arenas[p->arena];
+  if (h->arenas[p->arena ^ 1].submitted && h->arena_next != p->arena)      // both in flight: the older one sits in arena_next
+    return fail(BM25F_EINVAL, "collect submitted batches in the order they were submitted");
+  cudaError_t e = cudaEventSynchronize(A.ev_done);
+  A.submitted = nullptr;
+  if (e != cudaSuccess) {
+    bm25f_plan_destroy(p);
+    return fail(BM25F_ECUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
+  }
+  const size_t n = (size_t)p->Q * p->k;
+  const size_t o_doc = align_up(n * 4), o_cnt = o_doc + align_up(n * 4), o_tot = o_cnt + align_up((size_t)p->Q * 4);
+  if (out_scores && n) memcpy(out_scores, A.h_out, n * 4);
+  if (out_docids && n) memcpy(out_docids, A.h_out + o_doc, n * 4);
+  if (out_counts && p->Q) memcpy(out_counts, A.h_out + o_cnt, (size_t)p->Q * 4);
+  if (out_totals && p->Q) memcpy(out_totals, A.h_out + o_tot, (size_t)p->Q * 8);
+  bm25f_plan_destroy(p);
+  return fold_events(h, 1);          // this batch's timings (batches finish in submission order)
 }
 
 int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,

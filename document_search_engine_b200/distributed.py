@@ -81,8 +81,8 @@ class ShardedSearcher:
     def pack(self, queries, after_keys=None):
         return self.local.pack(queries, after_keys)
 
-    def _buffers(self, Q: int, k: int):
-        key = (Q, k)
+    def _buffers(self, Q: int, k: int, slot: int = 0):
+        key = (Q, k, slot)
         b = self._bufs.get(key)
         if b is None:
             dev = "cuda:%d" % self.device
@@ -95,11 +95,12 @@ class ShardedSearcher:
             self._bufs[key] = b
         return b
 
-    def run_plan(self, plan: _ffi.Plan):
+    def run_plan(self, plan: _ffi.Plan, slot: int = 0):
         """Execute a prepared plan on this shard, exchange, merge.  Everything is enqueued on
-        torch's current stream; returns the device buffers (merged keys, totals, decoded)."""
+        torch's current stream; returns the device buffers (merged keys, totals, decoded).  ``slot``
+        picks one of the buffer sets (two batches can be in flight, see ``search_packed_stream``)."""
         Q, k = plan.n_queries, plan.k
-        b = self._buffers(Q, k)
+        b = self._buffers(Q, k, slot)
         plan.execute()
         d_keys, d_totals = plan.device_results()
         local_keys = device_view(d_keys, Q * k, self.device)
@@ -134,8 +135,54 @@ class ShardedSearcher:
             plan.close()
         return scores, docids, counts, totals
 
-    def _host_buffers(self, Q: int, k: int):
-        key = ("host", Q, k)
+    def search_packed_stream(self, batches, k: int):
+        """``search_packed`` over an iterable of packed batches, pipelined two deep: the host plans and
+        uploads batch i + 1 while the GPUs score, exchange and merge batch i.  Yields the result tuples in
+        order.  Every rank must iterate the same batches (the collectives pair up in order)."""
+        if self.world == 1:
+            yield from self.local.search_packed_stream(batches, k)
+            return
+        stream = torch.cuda.current_stream(self.device)
+        inflight = None
+        slot = 0
+
+        def finish(item):
+            plan, h, ev, Q = item
+            try:
+                ev.synchronize()
+                return (h["scores"].numpy().reshape(Q, k).copy(),
+                        h["docids"].numpy().view(np.uint32).reshape(Q, k).copy(),
+                        h["counts"].numpy().view(np.uint32).copy(),
+                        h["totals"].numpy().view(np.uint64).copy())
+            finally:
+                plan.close()
+
+        try:
+            for batch in batches:
+                plan = self.engine.prepare(batch, k, arena=True)
+                Q = batch.n_queries
+                b = self.run_plan(plan, slot)
+                h = self._host_buffers(Q, k, slot)
+                for name in ("scores", "docids", "counts", "totals"):
+                    h[name].copy_(b[name], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                cur = (plan, h, ev, Q)
+                slot ^= 1
+                if inflight is not None:
+                    prev, inflight = inflight, cur
+                    yield finish(prev)
+                else:
+                    inflight = cur
+            if inflight is not None:
+                prev, inflight = inflight, None
+                yield finish(prev)
+        finally:
+            if inflight is not None:
+                finish(inflight)
+
+    def _host_buffers(self, Q: int, k: int, slot: int = 0):
+        key = ("host", Q, k, slot)
         h = self._bufs.get(key)
         if h is None:
             h = dict(scores=torch.empty(Q * k, dtype=torch.float32).pin_memory(),

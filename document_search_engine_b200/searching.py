@@ -323,6 +323,37 @@ class Searcher:
             raise ValueError("limit must be 1..%d for search_packed" % _ffi.MAX_K)
         return self._run_packed(batch, limit)
 
+    def search_packed_stream(self, batches, limit: int = 10):
+        """``search_packed`` over an iterable of packed batches, pipelined two deep: while the GPU scores
+        batch i, the host plans and uploads batch i + 1 (``bm25f_submit`` / ``bm25f_collect``).  Yields the
+        result tuples in order.  This is the throughput form for a server that answers request batches
+        back to back; the latency of one batch is that of ``search_packed``."""
+        if limit < 1 or limit > _ffi.MAX_K:
+            raise ValueError("limit must be 1..%d for search_packed_stream" % _ffi.MAX_K)
+        T = max(1, -(-self.ix.n_docs_all // (self.engine.stats()["tile_docs"] or DEFAULT_TILE_DOCS)))
+        max_leaves = max(_ffi.MAX_LEAVES_PER_QUERY, BOUNDS_BYTES_PER_CALL // (4 * (T + 1)))
+        pending = None
+        try:
+            for batch in batches:
+                if batch.n_leaves > max_leaves:          # needs splitting: not pipelined
+                    if pending is not None:
+                        p, pending = pending, None
+                        yield p.collect()
+                    yield self._run_packed(batch, limit)
+                    continue
+                nxt = self.engine.submit(batch, limit)
+                if pending is not None:
+                    p, pending = pending, nxt
+                    yield p.collect()
+                else:
+                    pending = nxt
+            if pending is not None:
+                p, pending = pending, None
+                yield p.collect()
+        finally:
+            if pending is not None:                      # the consumer stopped early: free the workspace
+                pending.collect()
+
     def search_batch(self, queries: Sequence[Query], limit: Optional[int] = 10) -> List[Results]:
         """Batched ``search``: one GPU pass for all queries (several when ``limit`` is
         ``None`` or exceeds the kernel's top-k capacity: the next pass collects only hits

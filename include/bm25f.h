@@ -172,7 +172,8 @@ int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
 /* Host planning + upload of one batch.  The plan can be executed any number of times. */
 int  bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
 /* Same, but the plan's buffers live in the handle's reusable workspaces (no allocation): the plan is valid
- * until the next bm25f_prepare_arena / bm25f_search_batch on this handle.  This is what the sharded host layer
+ * until the second next bm25f_prepare_arena / bm25f_search_batch / bm25f_submit on this handle (there are two
+ * workspaces, used alternately).  This is what the sharded host layer
  * uses per batch (the per-GPU half of `Searcher.search`, reference my_flask.py:208, :211, :304). */
 int  bm25f_prepare_arena(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
 /* Launch the kernels of a plan on the handle's stream (asynchronous). */
@@ -194,6 +195,18 @@ void bm25f_plan_destroy(bm25f_plan* plan);
 /* prepare + execute + fetch */
 int  bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* batch, int k, float* out_scores,
                         uint32_t* out_docids, uint32_t* out_counts, uint64_t* out_totals);
+
+/* Pipelined form of bm25f_search_batch for a stream of batches (a server answering request batches back to
+ * back): bm25f_submit plans the batch on the host, uploads it on a copy stream, launches its kernels and the
+ * device-to-host copy of its results into pinned memory, and returns without waiting; bm25f_collect waits for
+ * that batch, copies the results to the caller's buffers (same layout as bm25f_fetch) and frees the plan.
+ * Two batches may be in flight (the handle has two workspaces), so the host side of batch i + 1 overlaps the
+ * GPU side of batch i; a third bm25f_submit before the oldest is collected is refused (BM25F_EINVAL), and
+ * batches are collected in submission order (a refused bm25f_collect leaves the batch in flight; any other
+ * outcome frees the plan).  The query arrays may be reused as soon as bm25f_submit returns. */
+int  bm25f_submit(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
+int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_t* out_docids,
+                   uint32_t* out_counts, uint64_t* out_totals);
 
 /* Merge n_lists device-resident top-k key lists per query (layout [n_lists][n_queries][k], as an
  * all-gather of per-shard results produces) into d_out_keys [n_queries][k].  Runs on `stream`

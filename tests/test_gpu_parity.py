@@ -271,3 +271,40 @@ def test_every_field_and_cli_harness():
         assert [h.docnum for h in r] == sorted(h.docnum for h in r) and all(h.score == 1.0 for h in r)
         live_with_title = int(((ix.len_bytes[0] != 0) & (ix.deleted == 0)).sum())
         assert len(r) == live_with_title == r.scored_length()
+
+
+def test_pipelined_stream_equals_serial(cfg1):
+    """bm25f_submit / bm25f_collect (two batches in flight) return what bm25f_search_batch returns, batch
+    by batch and in order; the workspace rules are enforced loudly."""
+    from document_search_engine_b200._ffi import EngineError
+    ix, o = cfg1
+    sets = [make_queries(n, 50_000, 500 + i, 2, 4, "mixed", skip_top=0).queries for i, n in enumerate((300, 7, 1200, 1, 450))]
+    with ix.searcher(weighting=BM25F) as s:
+        batches = [s.pack(q) for q in sets]
+        serial = [s.search_packed(b, 10) for b in batches]
+        piped = list(s.search_packed_stream(iter(batches), 10))
+        assert len(piped) == len(serial)
+        for a, b in zip(serial, piped):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y)
+        # a consumer that stops early leaves no batch behind
+        g = s.search_packed_stream(iter(batches), 10)
+        next(g)
+        g.close()
+        assert np.array_equal(s.search_packed(batches[0], 10)[1], serial[0][1])
+        # three in flight: refused; out of order: refused; then both collect fine
+        p0 = s.engine.submit(batches[0], 10)
+        p1 = s.engine.submit(batches[1], 10)
+        with pytest.raises(EngineError, match="in flight"):
+            s.engine.submit(batches[2], 10)
+        with pytest.raises(EngineError, match="order"):
+            p1.collect()
+        # a refused collect leaves the batch in flight
+        r0, r1 = p0.collect(), p1.collect()
+        assert np.array_equal(r0[1], serial[0][1]) and np.array_equal(r0[3], serial[0][3])
+        assert np.array_equal(r1[1], serial[1][1]) and np.array_equal(r1[0], serial[1][0])
+        with pytest.raises(RuntimeError, match="already collected"):
+            p1.collect()
+        # and the engine is usable again
+        r = s.search_packed(batches[3], 10)
+        assert np.array_equal(r[1], serial[3][1])

@@ -15,7 +15,7 @@ rep, kern = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 45
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 csrc = os.path.join(root, "document_search_engine_b200", "csrc")
-cubin = "/tmp/bm25f_lines.cubin"
+cubin = os.path.join(root, "gpurun_out", "bm25f_lines.cubin")
 subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-cubin",
                 "-o", cubin, os.path.join(csrc, "bm25f.cu")], check=True)
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
