@@ -7,8 +7,8 @@ parsed query terms over inverted-index posting lists plus top-k collection
 """
 from .index import FlatIndex, Schema
 from .query import And, Every, Not, NullQuery, Or, QueryParser, Term
-from .scoring import BM25F, WeightingModel
+from .scoring import AscDateBM25F, BM25F, DateBM25F, DescDateBM25F, WeightingModel
 
 __all__ = ["FlatIndex", "Schema", "And", "Or", "Term", "Every", "Not", "NullQuery", "QueryParser",
-           "BM25F", "WeightingModel"]
+           "BM25F", "DateBM25F", "DescDateBM25F", "AscDateBM25F", "WeightingModel"]
 __version__ = "0.1.0"

@@ -26,7 +26,7 @@ EXPORTS = (
     "bm25f_abi_version", "bm25f_last_error", "bm25f_create", "bm25f_destroy", "bm25f_set_weighting",
     "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
-    "bm25f_reset_stats", "bm25f_submit", "bm25f_collect",
+    "bm25f_reset_stats", "bm25f_submit", "bm25f_collect", "bm25f_set_final_date", "bm25f_fetch_final",
 )
 
 
@@ -106,6 +106,8 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_reset_stats.argtypes = [vp]
     lib.bm25f_submit.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, C.POINTER(vp)]
     lib.bm25f_collect.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.bm25f_set_final_date.argtypes = [vp, vp]
+    lib.bm25f_fetch_final.argtypes = [vp, vp, vp, vp, vp, vp]
     if lib.bm25f_abi_version() != ABI_VERSION:
         raise RuntimeError("libbm25f ABI %d != binding ABI %d" % (lib.bm25f_abi_version(), ABI_VERSION))
     if path == os.environ.get("BM25F_LIB", LIB_PATH):
@@ -176,6 +178,17 @@ class Plan:
                                                               _ptr(counts), _ptr(totals)))
         return scores, docids, counts, totals
 
+    def fetch_final(self):
+        """``fetch`` for a plan prepared under a final() weighting: float64 final values instead of scores."""
+        q, k = self.n_queries, self.k
+        final = np.empty((q, k), dtype=np.float64)
+        docids = np.empty((q, k), dtype=np.uint32)
+        counts = np.empty(q, dtype=np.uint32)
+        totals = np.empty(q, dtype=np.uint64)
+        _check(self.engine.lib, self.engine.lib.bm25f_fetch_final(self.engine._h, self._p, _ptr(final), _ptr(docids),
+                                                                    _ptr(counts), _ptr(totals)))
+        return final, docids, counts, totals
+
     def device_results(self) -> Tuple[int, int]:
         """Raw device pointers ``(keys [Q*k] u64, totals [Q] u64)``."""
         dk, dt = C.c_void_p(), C.c_void_p()
@@ -237,6 +250,8 @@ class Engine:
         h = C.c_void_p()
         _check(self.lib, self.lib.bm25f_create(C.byref(desc), device, C.byref(opts), C.byref(h)))
         self._h = h
+        self.n_docs_all = int(ix.n_docs_all)
+        self._final_key = None            # which final() step the handle currently applies (None: none)
         self.device = device
         self.n_fields = len(ix.field_names)
         self._weighting_key = None
@@ -247,6 +262,25 @@ class Engine:
             raise ValueError("norm tables must be [n_fields, 256]")
         _check(self.lib, self.lib.bm25f_set_weighting(self._h, _ptr(norm)))
         self._weighting_key = key
+
+    def set_final_date(self, date_add: Optional[np.ndarray]):
+        """Per-document date term of a DateBM25F-style final() step (NaN: no date); ``None`` switches it off."""
+        if date_add is None:
+            _check(self.lib, self.lib.bm25f_set_final_date(self._h, None))
+            return
+        a = np.ascontiguousarray(date_add, dtype=np.float64)
+        if a.shape != (self.n_docs_all,):
+            raise ValueError("date_add must have one entry per document (%d), got %r" % (self.n_docs_all, a.shape))
+        _check(self.lib, self.lib.bm25f_set_final_date(self._h, _ptr(a)))
+
+    def search_batch_final(self, batch: PackedBatch, k: int):
+        """prepare + execute + fetch_final with the handle's reusable workspaces."""
+        plan = self.prepare(batch, k, arena=True)
+        try:
+            plan.execute()
+            return plan.fetch_final()
+        finally:
+            plan.close()
 
     def prepare(self, batch: PackedBatch, k: int, arena: bool = False) -> Plan:
         """``arena=True``: the plan lives in the handle's reusable workspaces (no allocation) and is

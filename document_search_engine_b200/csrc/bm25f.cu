@@ -1069,6 +1069,58 @@ __global__ void k_merge_topk_warp(const unsigned long long* __restrict__ keys_in
   if (lane < k) keys_out[(size_t)q * k + lane] = best;
 }
 
+// Final mode: merge of a query's partial lists of 96-bit keys and decode in one pass, one warp per query,
+// four keys per lane (k <= 128).
+__global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, const unsigned int* __restrict__ part_lo,
+                              const QueryRec* __restrict__ queries, uint32_t Q, int k, double* __restrict__ out_final,
+                              uint32_t* __restrict__ out_docids, uint32_t* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  const QueryRec qr = queries[q];
+  const size_t start = (size_t)qr.part_begin * k;
+  unsigned long long top[4] = {0ull, 0ull, 0ull, 0ull};
+  uint32_t topl[4] = {0u, 0u, 0u, 0u};
+  unsigned long long thr_h = 0ull;
+  uint32_t thr_l = 0u;
+  for (uint32_t l = 0; l < qr.n_parts; ++l) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int idx = 32 * j + lane;
+      if (32 * j >= k) break;
+      unsigned long long kh = 0ull;
+      uint32_t kl = 0u;
+      if (idx < k) {
+        kh = part_hi[start + (size_t)l * k + idx];
+        kl = part_lo[start + (size_t)l * k + idx];
+      }
+      unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_h, thr_l));
+      while (pm) {
+        const int src = __ffs(pm) - 1;
+        pm &= pm - 1u;
+        const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
+        const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
+        if (key2_gt(bh, bl, thr_h, thr_l)) {
+          warp_topk2_insert_rows<4>(top, topl, bh, bl, lane);
+          warp_topk2_kth<4>(top, topl, k, thr_h, thr_l);
+        }
+      }
+    }
+  }
+  uint32_t n = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = 32 * j + lane;
+    const bool ok = idx < k && top[j] != 0ull;
+    if (idx < k) {
+      out_final[(size_t)q * k + idx] = ok ? orderable_f64_value(top[j]) : -INFINITY;
+      out_docids[(size_t)q * k + idx] = ok ? 0xFFFFFFFFu - topl[j] : 0xFFFFFFFFu;
+    }
+    n += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ok));
+  }
+  if (lane == 0) out_counts[q] = n;
+}
+
 __global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint32_t Q, int k,
                               float* __restrict__ scores, uint32_t* __restrict__ docids,
                               uint32_t* __restrict__ counts) {
@@ -1174,6 +1226,7 @@ struct bm25f_handle {
   uint8_t* d_lb = nullptr;
   uint2* d_pairs = nullptr;           // {docid, tf / (tf + norm[lb]) under the current weighting}: the stream kernel's store
   float* d_norm = nullptr;
+  double* d_final_add = nullptr;   // bm25f_set_final_date: per-document date term (NaN: no date); null = no final() step
   bool packed = true;
   bool have_weighting = false;
   uint32_t S = 8192, NT = 256, split = 1u << 16;
@@ -1247,6 +1300,9 @@ struct bm25f_plan {
   size_t smem_score = 0;
   bool owns_memory = true;      // false: buffers live in one of the handle's arenas (bm25f_search_batch)
   int arena = -1;               // which one
+  bool final_mode = false;      // planned with a final() step: 96-bit keys, float64 results (bm25f_fetch_final)
+  unsigned int* d_part_lo = nullptr;   // final mode: low halves of the partial lists' keys
+  double* d_final = nullptr;           // final mode: [Q * k] final values
   bool submitted = false;       // bm25f_submit: bm25f_execute also brings the results to the arena's pinned h_out
   bool simple_kernel = false;   // k_score_topk instead of k_score_pipe (option, or a non-positive leaf weight)
 };
@@ -1338,6 +1394,7 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_lb);
   cudaFree(h->d_pairs);
   cudaFree(h->d_norm);
+  cudaFree(h->d_final_add);
   cudaFree(h->d_prof);
   for (auto& A : h->arenas) {
     cudaFree(A.d);
@@ -1706,6 +1763,8 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_docids);
   cudaFree(p->d_counts);
   cudaFree(p->d_taken);
+  cudaFree(p->d_part_lo);
+  cudaFree(p->d_final);
   delete p;
 }
 
@@ -1824,6 +1883,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   auto dummy_leaves = [&](uint32_t a, uint32_t e) {
     for (uint32_t i = a; i < e; ++i) { leaves[i] = LeafRec{}; leaves[i].qleaf0 = i; leaves[i].qnl = 1; }
   };
+  const bool final_mode = h->d_final_add != nullptr;
   auto plan_range = [&](uint32_t q_begin, uint32_t q_end, PlanLocal& L) {
     for (uint32_t qi = q_begin; qi < q_end; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -1930,12 +1990,14 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     if (n_neg && !(k <= 128 && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
       PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 128, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
     const bool isect_ok = k <= 128 && nlq <= 32 && all_pos && qr.after_key == 0ull;
+    if (final_mode && !isect_ok)
+      PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 128, at most 32 leaves, positive weights and no paging bound", qi);
     // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
     // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
     uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
     bool use_or1 = false;
     bool use_hash = false;
-    if ((qr.flags & QF_SIMPLE_OR) && isect_ok && k <= 32 && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
+    if (!final_mode && (qr.flags & QF_SIMPLE_OR) && isect_ok && k <= 32 && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
       uint32_t imax = 0;
       for (uint32_t i = 1; i < nlq; ++i)
         if (leaves[out_leaf - nlq + i].df > leaves[out_leaf - nlq + imax].df) imax = i;
@@ -1960,7 +2022,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }
     // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
-    const bool use_isect = use_or1 || (!use_hash && isect_ok && (h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
+    const bool use_isect = use_or1 || (!use_hash && isect_ok && (final_mode || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
     const bool use_team = !use_isect && !use_hash && stream_ok && n_neg == 0 && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
@@ -2113,6 +2175,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
   p->arena = use_arena ? slot : -1;
+  p->final_mode = final_mode;
 
 #define RCP(x)                                    \
   do {                                            \
@@ -2167,7 +2230,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
                  o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 5) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
-                 o_taken = take((size_t)(taken_words + 1) * 4);
+                 o_taken = take((size_t)(taken_words + 1) * 4),
+                 o_plo = take(final_mode ? (size_t)n_parts * k * 4 : 0), o_fin = take(final_mode ? (size_t)Q * k * 8 : 0);
     if (off > A.d_cap) {
       CUP(cudaStreamSynchronize(h->stream));
       CUP(cudaStreamSynchronize(h->copy_stream));
@@ -2191,6 +2255,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
     p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
     p->d_taken = reinterpret_cast<unsigned int*>(d + o_taken);
+    if (final_mode) {
+      p->d_part_lo = reinterpret_cast<unsigned int*>(d + o_plo);
+      p->d_final = reinterpret_cast<double*>(d + o_fin);
+    }
   } else {
     RCP(dev_alloc(&p->d_leaves, out_leaf));
     RCP(dev_alloc(&p->d_queries, Q));
@@ -2203,6 +2271,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
     RCP(dev_alloc(&p->d_taken, (size_t)taken_words + 1));
+    if (final_mode) {
+      RCP(dev_alloc(&p->d_part_lo, (size_t)n_parts * k + 1));
+      RCP(dev_alloc(&p->d_final, (size_t)Q * k + 1));
+    }
   }
   p->d_items_w4 = p->d_items + p->n_items;
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
@@ -2351,14 +2423,16 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.n_items = p->n_o1;
       ip.doc_base = (uint32_t)h->doc_base;
       ip.k = p->k;
+      ip.final_add = nullptr;
+      ip.part_lo = nullptr;
       if (h->is_ctas_per_sm == 0) {
         int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1>, IS_WARPS * 32, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1, false>, IS_WARPS * 32, 0));
         h->is_ctas_per_sm = std::max(1, nb_);
       }
       const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_o1 + IS_WARPS - 1) / IS_WARPS);
-      if (p->k <= 32) k_score_isect<1><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
-      else k_score_isect<4><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      if (p->k <= 32) k_score_isect<1, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2375,14 +2449,21 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.n_items = p->n_is;
       ip.doc_base = (uint32_t)h->doc_base;
       ip.k = p->k;
+      ip.final_add = h->d_final_add;
+      ip.part_lo = p->d_part_lo;
       if (h->is_ctas_per_sm == 0) {
         int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1>, IS_WARPS * 32, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1, false>, IS_WARPS * 32, 0));
         h->is_ctas_per_sm = std::max(1, nb_);
       }
       const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_is + IS_WARPS - 1) / IS_WARPS);
-      if (p->k <= 32) k_score_isect<1><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
-      else k_score_isect<4><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      if (p->final_mode) {
+        // final() of every match before the top-k: 96-bit keys, more registers, 2 CTAs per SM at least
+        const unsigned gridf = std::min<unsigned>((unsigned)(h->n_sms * 2), (p->n_is + IS_WARPS - 1) / IS_WARPS);
+        if (p->k <= 32) k_score_isect<1, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
+        else k_score_isect<4, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
+      } else if (p->k <= 32) k_score_isect<1, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2436,7 +2517,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   }
   if (!p->n_w4) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventRecord(ev[5], st)); }
   CU(cudaEventRecord(ev[2], st));
-  if (p->Q) {
+  if (p->Q && p->final_mode) {
+    k_merge_final<<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
+    CU(cudaGetLastError());
+    ++launches;
+  } else if (p->Q) {
     if (p->k <= 32) k_merge_topk_warp<<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->d_keys);
     else k_merge_topk<<<p->Q, 128, (size_t)2 * p->kp * 8, st>>>(p->d_part_keys, p->d_queries, 0, 0, 0ull, p->Q, p->k, p->kp, p->d_keys);
     CU(cudaGetLastError());
@@ -2515,6 +2600,7 @@ int bm25f_fetch(bm25f_handle* h, bm25f_plan* p, float* out_scores, uint32_t* out
                 uint64_t* out_totals) {
   if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
   CU(cudaSetDevice(h->device));
+  if (p->final_mode) return fail(BM25F_EINVAL, "the plan was prepared with a final() step: use bm25f_fetch_final");
   const size_t n = (size_t)p->Q * p->k;
   if (out_scores && n) CU(cudaMemcpyAsync(out_scores, p->d_scores, n * 4, cudaMemcpyDeviceToHost, h->stream));
   if (out_docids && n) CU(cudaMemcpyAsync(out_docids, p->d_docids, n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -2523,8 +2609,44 @@ int bm25f_fetch(bm25f_handle* h, bm25f_plan* p, float* out_scores, uint32_t* out
   return bm25f_synchronize(h);
 }
 
+int bm25f_fetch_final(bm25f_handle* h, bm25f_plan* p, double* out_final, uint32_t* out_docids, uint32_t* out_counts,
+                      uint64_t* out_totals) {
+  if (!h || !p || p->h != h) return fail(BM25F_EINVAL, "plan does not belong to this handle");
+  if (!p->final_mode) return fail(BM25F_EINVAL, "the plan was prepared without a final() step: use bm25f_fetch");
+  CU(cudaSetDevice(h->device));
+  const size_t n = (size_t)p->Q * p->k;
+  if (out_final && n) CU(cudaMemcpyAsync(out_final, p->d_final, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  if (out_docids && n) CU(cudaMemcpyAsync(out_docids, p->d_docids, n * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_counts && p->Q) CU(cudaMemcpyAsync(out_counts, p->d_counts, (size_t)p->Q * 4, cudaMemcpyDeviceToHost, h->stream));
+  if (out_totals && p->Q) CU(cudaMemcpyAsync(out_totals, p->d_totals, (size_t)p->Q * 8, cudaMemcpyDeviceToHost, h->stream));
+  return bm25f_synchronize(h);
+}
+
+int bm25f_set_final_date(bm25f_handle* h, const double* date_add) {
+  if (!h) return fail(BM25F_EINVAL, "null handle");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  for (auto& A : h->arenas)
+    if (A.submitted) return fail(BM25F_EINVAL, "collect the submitted batches before changing the weighting");
+  if (!date_add) {
+    cudaFree(h->d_final_add);
+    h->d_final_add = nullptr;
+    return 0;
+  }
+  if (!h->d_final_add) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_final_add), std::max<uint64_t>(1, h->n_docs) * sizeof(double));
+    if (e != cudaSuccess) {
+      h->d_final_add = nullptr;
+      return fail(BM25F_ENOMEM, "cudaMalloc(%llu): %s", (unsigned long long)(h->n_docs * sizeof(double)), cudaGetErrorString(e));
+    }
+  }
+  if (h->n_docs) CU(cudaMemcpy(h->d_final_add, date_add, h->n_docs * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
 int bm25f_plan_device_results(bm25f_plan* p, uint64_t** d_keys, uint64_t** d_totals) {
   if (!p) return fail(BM25F_EINVAL, "null plan");
+  if (p->final_mode) return fail(BM25F_EINVAL, "plans with a final() step have no 64-bit key lists");
   if (d_keys) *d_keys = reinterpret_cast<uint64_t*>(p->d_keys);
   if (d_totals) *d_totals = reinterpret_cast<uint64_t*>(p->d_totals);
   return 0;
@@ -2532,6 +2654,7 @@ int bm25f_plan_device_results(bm25f_plan* p, uint64_t** d_keys, uint64_t** d_tot
 
 int bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* b, int k, float* out_scores, uint32_t* out_docids,
                        uint32_t* out_counts, uint64_t* out_totals) {
+  if (h && h->d_final_add) return fail(BM25F_EINVAL, "a final() weighting is set: use bm25f_prepare_arena / bm25f_execute / bm25f_fetch_final");
   bm25f_plan* p = nullptr;
   int rc = prepare_impl(h, b, k, &p, true);
   if (rc) return rc;
@@ -2543,6 +2666,7 @@ int bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* b, int k, float
 
 int bm25f_submit(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out) {
   if (!out) return fail(BM25F_EINVAL, "null argument");
+  if (h && h->d_final_add) return fail(BM25F_EINVAL, "a final() weighting is set: use bm25f_prepare_arena / bm25f_execute / bm25f_fetch_final");
   bm25f_plan* p = nullptr;
   int rc = prepare_impl(h, b, k, &p, true);
   if (rc) return rc;

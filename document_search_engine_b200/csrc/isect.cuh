@@ -41,14 +41,90 @@ struct IsectParams {
   uint32_t n_items;
   uint32_t doc_base;
   int k;
+  // FINAL instantiation only (a weighting with a final() step, reference my_whoosh.py:127-154):
+  const double* final_add;         // [n_docs] date term of the document (NaN: the document has no date)
+  unsigned int* part_lo;           // [n_parts * k] low halves of the keys (~global docnum); part_keys holds the high halves
 };
 
 constexpr int IS_WARPS = 8;
 
+// ---- DateBM25F.final (my_whoosh.py:129-146), applied to every match before the top-k (W14) -------
+//   s' = 1 - 1 / s;  a dated document:  s' = (s' + (date seconds + 1.0)) / 10**9   -- float64, IEEE division
+// `add` is (date seconds + 1.0), precomputed in float64 on the host.
+__device__ __forceinline__ double final_value(float score, double add) {
+  const double t = 1.0 - 1.0 / (double)score;
+  return isnan(add) ? t : (t + add) / 1e9;
+}
+__host__ __device__ __forceinline__ unsigned long long orderable_f64(double v) {
+#ifdef __CUDA_ARCH__
+  unsigned long long u = (unsigned long long)__double_as_longlong(v);
+#else
+  unsigned long long u;
+  memcpy(&u, &v, 8);
+#endif
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double orderable_f64_value(unsigned long long u) {
+  u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+#ifdef __CUDA_ARCH__
+  return __longlong_as_double((long long)u);
+#else
+  double v;
+  memcpy(&v, &u, 8);
+  return v;
+#endif
+}
+// 96-bit keys (high: orderable final value, low: ~global docnum), KR per lane, the same sorted list as
+// warp_topk_insert_rows keeps for 64-bit keys
+__device__ __forceinline__ bool key2_gt(unsigned long long ah, uint32_t al, unsigned long long bh, uint32_t bl) {
+  return ah > bh || (ah == bh && al > bl);
+}
+template <int KR>
+__device__ __forceinline__ void warp_topk2_insert_rows(unsigned long long (&th)[KR], uint32_t (&tl)[KR], unsigned long long kh,
+                                                       uint32_t kl, int lane) {
+  bool inserted = false;
+  unsigned long long ch = 0ull;
+  uint32_t cl = 0u;
+#pragma unroll
+  for (int j = 0; j < KR; ++j) {
+    const unsigned long long last_h = __shfl_sync(0xFFFFFFFFu, th[j], 31);
+    const uint32_t last_l = __shfl_sync(0xFFFFFFFFu, tl[j], 31);
+    const unsigned long long up_h = __shfl_up_sync(0xFFFFFFFFu, th[j], 1);
+    const uint32_t up_l = __shfl_up_sync(0xFFFFFFFFu, tl[j], 1);
+    if (!inserted) {
+      const int pos = __popc(__ballot_sync(0xFFFFFFFFu, key2_gt(th[j], tl[j], kh, kl)));
+      if (pos < 32) {
+        if (lane > pos) { th[j] = up_h; tl[j] = up_l; }
+        if (lane == pos) { th[j] = kh; tl[j] = kl; }
+        ch = last_h;
+        cl = last_l;
+        inserted = true;
+      }
+    } else {
+      th[j] = (lane == 0) ? ch : up_h;
+      tl[j] = (lane == 0) ? cl : up_l;
+      ch = last_h;
+      cl = last_l;
+    }
+  }
+}
+template <int KR>
+__device__ __forceinline__ void warp_topk2_kth(const unsigned long long (&th)[KR], const uint32_t (&tl)[KR], int k,
+                                               unsigned long long& vh, uint32_t& vl) {
+  vh = 0ull;
+  vl = 0u;
+#pragma unroll
+  for (int j = 0; j < KR; ++j) {
+    const unsigned long long h = __shfl_sync(0xFFFFFFFFu, th[j], (k - 1) & 31);
+    const uint32_t l = __shfl_sync(0xFFFFFFFFu, tl[j], (k - 1) & 31);
+    if (j == ((k - 1) >> 5)) { vh = h; vl = l; }
+  }
+}
+
 // Requires: k <= 32 * KR, <= 32 leaves, <= 32 groups, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store.
-template <int KR>
-__global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
+template <int KR, bool FINAL>
+__global__ void __launch_bounds__(IS_WARPS * 32, FINAL ? 2 : KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
   const int lane = threadIdx.x & 31;
   const uint2* __restrict__ store = ip.pairs;
 
@@ -93,6 +169,10 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
     unsigned long long thr_key = 0ull;
     float thr = 0.0f;
     unsigned int tot = 0;
+    uint32_t topl[FINAL ? KR : 1];            // FINAL: the low halves of the keys; thr_key / thr_lo = the k-th best
+    uint32_t thr_lo = 0u;
+#pragma unroll
+    for (int j = 0; j < (FINAL ? KR : 1); ++j) topl[j] = 0u;
 
     for (unsigned cm = cand_mask; cm; cm &= cm - 1u) {
       const int c = __ffs(cm) - 1;
@@ -148,6 +228,26 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
         }
         const bool alive = !dead && sat == full;
         tot += alive ? 1u : 0u;
+        if constexpr (FINAL) {
+          // final() of every match, then the same insertion with 96-bit keys
+          unsigned long long kh = 0ull;
+          uint32_t kl = 0u;
+          if (alive) {
+            kh = orderable_f64(final_value(score, __ldg(ip.final_add + doc)));
+            kl = 0xFFFFFFFFu - (ip.doc_base + doc);
+          }
+          unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_key, thr_lo));
+          while (pm) {
+            const int src = __ffs(pm) - 1;
+            pm &= pm - 1u;
+            const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
+            const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
+            if (key2_gt(bh, bl, thr_key, thr_lo)) {
+              warp_topk2_insert_rows<KR>(top, topl, bh, bl, lane);
+              warp_topk2_kth<KR>(top, topl, ip.k, thr_key, thr_lo);
+            }
+          }
+        } else {
         unsigned long long key = 0ull;
         if (alive && score >= thr) key = make_key(score, ip.doc_base + doc);
         unsigned pm = __ballot_sync(0xFFFFFFFFu, key > thr_key);
@@ -161,10 +261,11 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
           }
         }
         if (thr_key != 0ull) thr = key_score(thr_key);
+        }
       }
     }
 
-    if (stream_last) {
+    if (!FINAL && stream_last) {
       // ---- the dense leaf: no accumulators, no lookups --------------------------------------------
       __threadfence();                                  // the bitmap words written above, read below by other lanes
       const int dl = L - 1;
@@ -234,6 +335,12 @@ __global__ void __launch_bounds__(IS_WARPS * 32, KR == 1 ? 5 : 3) k_score_isect(
 #pragma unroll
     for (int j = 0; j < KR; ++j)
       if (32 * j + lane < ip.k) out[32 * j + lane] = top[j];
+    if constexpr (FINAL) {
+      unsigned int* out_lo = ip.part_lo + (size_t)item.part * ip.k;
+#pragma unroll
+      for (int j = 0; j < KR; ++j)
+        if (32 * j + lane < ip.k) out_lo[32 * j + lane] = topl[j];
+    }
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
     if (lane == 0 && tot) atomicAdd(ip.totals + item.q, (unsigned long long)tot);
   }

@@ -74,6 +74,9 @@ class ShardedSearcher:
         self.shard_ix = shard_ix
         # corpus-wide statistics come from ``full_ix`` (only its df / totals / dictionary are used)
         self.local = Searcher(self.shard_ix, weighting=weighting, device=self.device, stats_ix=full_ix, **engine_opts)
+        if self.local.weighting.use_final and self.world > 1:
+            raise NotImplementedError("final() weightings (DateBM25F) are served on one GPU: the cross-shard merge "
+                                      "exchanges 64-bit keys, final() needs 96-bit ones")
         self.engine = self.local.engine
         self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._bufs = {}

@@ -13,6 +13,8 @@ so that the per-posting work on the device is ``w * tf / (tf + norm[lb])``.
 """
 from __future__ import annotations
 
+import re
+from datetime import datetime, timedelta
 from math import log
 
 import numpy as np
@@ -65,6 +67,64 @@ class BM25F(WeightingModel):
 
     def key(self):
         return ("BM25F", self.B, self.K1, tuple(sorted(self._field_B.items())))
+
+
+class DateBM25F(BM25F):
+    """BM25F whose ``final`` step orders hits by date first (reference ``my_whoosh.py:127-154``, chosen at
+    ``my_flask.py:183`` for two of the UI's three hit orders).  Whoosh calls ``final`` for every match
+    before the top-k collector (W14), so the device has to apply it: the per-document part (the date, plus
+    the chapter number found in the stored heading, as seconds) is computed once on the host by
+    ``doc_final_terms`` and uploaded; the kernels evaluate, in float64,
+
+        v = 1 - 1/score                           (document without a date)
+        v = ((1 - 1/score) + (date_s + 1.0)) / 10**9   (dated document)
+
+    ``final`` below is the same arithmetic for one document (what the oracle calls)."""
+    use_final = True
+    #: seconds are counted up from this instant (newest first) or down to it (oldest first)
+    descending = True
+    _EPOCH_DESC = datetime(1800, 1, 1)
+    _EPOCH_ASC = datetime(2200, 1, 1)
+    _CHAPTER = re.compile(r"chapter\W*(\d+)", re.IGNORECASE)
+
+    def date_seconds(self, fields):
+        """Date score of a document's stored fields, or ``None`` when it has no date."""
+        if "date" not in fields:
+            return None
+        m = self._CHAPTER.search(fields.get("heading") or "")
+        when = fields["date"] + timedelta(seconds=int(m.group(1)) if m else 0)
+        if self.descending:
+            return (when - self._EPOCH_DESC).total_seconds()
+        return (self._EPOCH_ASC - when).total_seconds()
+
+    def final(self, searcher, docnum, score):
+        v = 1 - 1 / score
+        ds = self.date_seconds(searcher.stored_fields(docnum))
+        if ds is not None:
+            v += ds + 1.0
+            v /= 10 ** 9
+        return v
+
+    def doc_final_terms(self, ix) -> np.ndarray:
+        """float64 ``[n_docs_all]``: ``date_s + 1.0`` per document of ``ix``, NaN where there is no date."""
+        out = np.full(ix.n_docs_all, np.nan, dtype=np.float64)
+        if ix.stored is not None:
+            for i, fields in enumerate(ix.stored):
+                ds = self.date_seconds(fields)
+                if ds is not None:
+                    out[i] = ds + 1.0
+        return out
+
+    def key(self):
+        return (type(self).__name__,) + super().key()[1:]
+
+
+class DescDateBM25F(DateBM25F):
+    descending = True
+
+
+class AscDateBM25F(DateBM25F):
+    descending = False
 
 
 def bm25(idf, tf, fl, avgfl, B, K1):

@@ -30,6 +30,8 @@ from .scoring import BM25F, instantiate
 #: bound on the per-call tile-boundary table (bytes); larger batches are split
 BOUNDS_BYTES_PER_CALL = 1 << 30
 DEFAULT_TILE_DOCS = 8192
+#: largest limit the device serves under a final() weighting (the candidate kernel keeps 4 keys per lane)
+FINAL_MAX_K = 128
 
 
 def make_keys(scores: np.ndarray, docids: np.ndarray) -> np.ndarray:
@@ -215,6 +217,17 @@ class Searcher:
         wkey = self.weighting.key() + (self.stats_ix.doc_count_all(),)
         if eng._weighting_key != wkey:
             eng.set_weighting(self.weighting.norm_tables(self.stats_ix), key=wkey)
+        # a final() step (DateBM25F: my_whoosh.py:127-154) runs on the device, over every match (W14)
+        fkey = None
+        if self.weighting.use_final:
+            if not hasattr(self.weighting, "doc_final_terms"):
+                raise NotImplementedError(
+                    "a weighting with use_final=True must provide doc_final_terms(ix) (see scoring.DateBM25F): "
+                    "final() is applied to every match before the top-k (W14), which only the device can do")
+            fkey = self.weighting.key()
+        if eng._final_key != fkey:
+            eng.set_final_date(None if fkey is None else self.weighting.doc_final_terms(ix))
+            eng._final_key = fkey
         self._idf_cache = {}
         self.closed = False
 
@@ -318,9 +331,14 @@ class Searcher:
         return tuple(np.concatenate([o[i] for o in outs]) for i in range(4))
 
     def search_packed(self, batch: _ffi.PackedBatch, limit: int = 10):
-        """``(scores [Q,k] f32, docids [Q,k] u32, counts [Q], totals [Q])`` for a packed batch."""
+        """``(scores [Q,k] f32, docids [Q,k] u32, counts [Q], totals [Q])`` for a packed batch (float64 final
+        values instead of scores under a final() weighting)."""
         if limit < 1 or limit > _ffi.MAX_K:
             raise ValueError("limit must be 1..%d for search_packed" % _ffi.MAX_K)
+        if self.weighting.use_final:
+            if limit > FINAL_MAX_K:
+                raise NotImplementedError("a final() weighting is served for limit <= %d" % FINAL_MAX_K)
+            return self.engine.search_batch_final(batch, limit)
         return self._run_packed(batch, limit)
 
     def search_packed_stream(self, batches, limit: int = 10):
@@ -358,13 +376,17 @@ class Searcher:
         """Batched ``search``: one GPU pass for all queries (several when ``limit`` is
         ``None`` or exceeds the kernel's top-k capacity: the next pass collects only hits
         ordered strictly after the last one already returned)."""
-        if self.weighting.use_final:
-            raise NotImplementedError(
-                "weightings with use_final=True (DescDateBM25F/AscDateBM25F, my_whoosh.py:127-154) apply "
-                "final() to every match before top-k (W14); the device path for it is SURVEY.md §8 f1")
         t_start = time.perf_counter()
         queries = list(queries)
         nq = len(queries)
+        if self.weighting.use_final:
+            # final values (float64) come straight from the device, one pass
+            if limit is None or limit > FINAL_MAX_K:
+                raise NotImplementedError("a final() weighting is served for limit <= %d" % FINAL_MAX_K)
+            final, docids, counts, tot = self.engine.search_batch_final(self.pack(queries), limit)
+            dt = time.perf_counter() - t_start
+            return [Results(self, queries[i], list(zip(final[i, :int(counts[i])].tolist(), docids[i, :int(counts[i])].tolist())),
+                            int(tot[i]), runtime=dt) for i in range(nq)]
         want = [limit if limit is not None else None] * nq
         tops: List[list] = [[] for _ in range(nq)]
         totals = np.zeros(nq, dtype=np.uint64)

@@ -169,6 +169,17 @@ void bm25f_destroy(bm25f_handle* h);
 /* norm: [n_fields * 256] float32, norm[f][b] = K1 * ((1 - B_f) + B_f * fl(b) / avgfl_f). */
 int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
 
+/* A weighting with a final() step (reference my_whoosh.py:127-154, DescDateBM25F / AscDateBM25F, selected at
+ * my_flask.py:183): Whoosh applies final(searcher, docnum, score) to EVERY match before the top-k collector.
+ * date_add: [n_docs_all] float64, for a dated document (its date score in seconds + 1.0), NaN for a document
+ * without a date.  While set, a match with BM25F score s ranks by the float64 value
+ *     v = 1 - 1/s                      (no date)
+ *     v = ((1 - 1/s) + date_add) / 1e9 (dated)
+ * descending, docnum ascending; plans are fetched with bm25f_fetch_final (which returns v), k <= 128, at most
+ * 32 leaves per query, and bm25f_search_batch / bm25f_submit / bm25f_fetch are refused.  NULL switches the
+ * step off again. */
+int  bm25f_set_final_date(bm25f_handle* h, const double* date_add);
+
 /* Host planning + upload of one batch.  The plan can be executed any number of times. */
 int  bm25f_prepare(bm25f_handle* h, const bm25f_query_batch* batch, int k, bm25f_plan** out);
 /* Same, but the plan's buffers live in the handle's reusable workspaces (no allocation): the plan is valid
@@ -183,6 +194,10 @@ int  bm25f_execute(bm25f_handle* h, bm25f_plan* plan);
  * out_counts [n_queries] hits written, out_totals [n_queries] exact number of matching documents. */
 int  bm25f_fetch(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_t* out_docids,
                  uint32_t* out_counts, uint64_t* out_totals);
+/* bm25f_fetch for a plan prepared while a final() step was set: out_final [n_queries * k] float64 final
+ * values (unused slots: -inf); the other outputs as bm25f_fetch. */
+int  bm25f_fetch_final(bm25f_handle* h, bm25f_plan* plan, double* out_final, uint32_t* out_docids,
+                       uint32_t* out_counts, uint64_t* out_totals);
 /* Device-resident results of a plan: keys [n_queries * k] (0 = empty slot), totals [n_queries]. */
 int  bm25f_plan_device_results(bm25f_plan* plan, uint64_t** d_keys, uint64_t** d_totals);
 int  bm25f_synchronize(bm25f_handle* h);

@@ -57,8 +57,12 @@ def lower_query(q):
 
 
 class NumpyOracle:
-    def __init__(self, ix, B=0.75, K1=1.2, field_B=None, shards=None):
+    def __init__(self, ix, B=0.75, K1=1.2, field_B=None, shards=None, final_add=None):
         self.ix = ix
+        #: W14 with the reference's DateBM25F.final (my_whoosh.py:129-146), vectorised: per global docnum
+        #: ``date seconds + 1.0`` or NaN (no date); every match's score s becomes 1 - 1/s, and
+        #: ((1 - 1/s) + final_add) / 10**9 for a dated document, before ranking
+        self.final_add = None if final_add is None else np.asarray(final_add, dtype=np.float64)
         self.B, self.K1 = B, K1
         self.field_B = dict(field_B or {})
         self.shards = list(shards) if shards is not None else [ix]
@@ -128,7 +132,13 @@ class NumpyOracle:
             ss.append(acc[d])
         if not ds:
             return np.zeros(0, np.int64), np.zeros(0, np.float64)
-        return np.concatenate(ds), np.concatenate(ss)
+        d, s = np.concatenate(ds), np.concatenate(ss)
+        if self.final_add is not None and d.size:
+            t = 1 - 1 / s
+            add = self.final_add[d]
+            dated = ~np.isnan(add)
+            s = np.where(dated, (t + np.where(dated, add, 0.0)) / 10 ** 9, t)
+        return d, s
 
     def search(self, q, limit=10):
         """``(top, total)`` with ``top`` = list of ``(score, docnum)`` in W11 order."""
