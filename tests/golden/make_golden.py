@@ -54,6 +54,10 @@ def main():
     cases.append(dict(name="deleted_ties", n_docs=2500, vocab=300, seed=99, fields=["body"], qseed=11, n_queries=80,
                       min_terms=1, max_terms=4, mode="mixed", skip_top=0, k=10, deleted_frac=0.2, zero_len_frac=0.1,
                       unit_tf=True, B=0.75, K1=1.2, field_B={}))
+    # 5: NOT clauses (Whoosh's AndNotMatcher): every second AND / OR query excludes one or two dense terms
+    cases.append(dict(name="not_clauses", n_docs=3000, vocab=4000, seed=20260001, fields=["body"], qseed=20261007,
+                      n_queries=100, min_terms=2, max_terms=4, mode="mixed", skip_top=0, k=10, nots=True, B=0.75, K1=1.2,
+                      field_B={}))
     for c in cases:
         ix, queries = build_case(c)
         o = OracleSearcher(ix, B=c["B"], K1=c["K1"], field_B=c["field_B"])
@@ -83,7 +87,17 @@ def build_case(c):
     qs = make_queries(c["n_queries"], c["vocab"], c["qseed"], c["min_terms"], c["max_terms"], c["mode"],
                       fields=tuple(c["fields"]), field_boosts=tuple(c.get("field_boosts", [1.0] * len(c["fields"]))),
                       variants=c.get("variants", False), skip_top=c["skip_top"])
-    return ix, qs.queries
+    queries = qs.queries
+    if c.get("nots"):
+        from document_search_engine_b200.query import And, Not, Or, Term
+        out = []
+        for i, q in enumerate(queries):
+            if i % 2 == 0 and isinstance(q, (And, Or)):
+                neg = [Term(c["fields"][0], (i * 7) % 150)] + ([Term(c["fields"][0], (i * 13) % 400)] if i % 4 == 0 else [])
+                q = type(q)(list(q.subqueries) + [Not(neg[0] if len(neg) == 1 else Or(neg))])
+            out.append(q)
+        queries = out
+    return ix, queries
 
 
 if __name__ == "__main__":
