@@ -2323,6 +2323,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     int rc = fold_events(h, 1);
     if (rc) return rc;
   }
+  if (p->final_mode && !h->d_final_add) return fail(BM25F_EINVAL, "the plan was prepared with a final() step that has since been switched off");
   cudaEvent_t* ev = h->ev[h->ev_head];
   if (p->arena >= 0) CU(cudaStreamWaitEvent(st, h->arenas[p->arena].ev_ready, 0));
   CU(cudaEventRecord(ev[0], st));

@@ -375,7 +375,6 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
           const uint32_t idx = cur + (uint32_t)lane;
           r = make_uint2(0xFFFFFFFFu, 0u);
           if (idx < end) r = ldg_pair(pairs + idx);
-          if (lane < 2 && idx + 32u < end) prefetch_l1(pairs + cur + 32u + (uint32_t)lane * 16u);   // the row after it
         }
         if (dirty) sts_v2(tail, r.x, r.y);
         const uint32_t nd = __shfl_sync(0xFFFFFFFFu, r.x, cur & 31u);
