@@ -986,6 +986,7 @@ __device__ __forceinline__ unsigned long long warp_topk_kth(const unsigned long 
   return v;
 }
 
+#include "final.cuh"
 #include "stream.cuh"
 #include "team.cuh"
 #include "isect.cuh"
@@ -1227,6 +1228,7 @@ struct bm25f_handle {
   uint2* d_pairs = nullptr;           // {docid, tf / (tf + norm[lb]) under the current weighting}: the stream kernel's store
   float* d_norm = nullptr;
   double* d_final_add = nullptr;   // bm25f_set_final_date: per-document date term (NaN: no date); null = no final() step
+  double* d_final_blk = nullptr;   // ... and the largest one of every aligned block of 32 documents
   bool packed = true;
   bool have_weighting = false;
   uint32_t S = 8192, NT = 256, split = 1u << 16;
@@ -1395,6 +1397,7 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_pairs);
   cudaFree(h->d_norm);
   cudaFree(h->d_final_add);
+  cudaFree(h->d_final_blk);
   cudaFree(h->d_prof);
   for (auto& A : h->arenas) {
     cudaFree(A.d);
@@ -1689,7 +1692,8 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[3] = {(const void*)k_score_stream<1>, (const void*)k_score_stream<4>, (const void*)k_score_team};
+    const void* wfns[5] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
+                           (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1990,7 +1994,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     if (n_neg && !(k <= 128 && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
       PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 128, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
     const bool isect_ok = k <= 128 && nlq <= 32 && all_pos && qr.after_key == 0ull;
-    if (final_mode && !isect_ok)
+    if (final_mode && !isect_ok && !stream_ok)
       PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 128, at most 32 leaves, positive weights and no paging bound", qi);
     // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
     // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
@@ -2022,10 +2026,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }
     // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
-    const bool use_isect = use_or1 || (!use_hash && isect_ok && (final_mode || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
+    const bool use_isect = use_or1 || (!use_hash && isect_ok && ((final_mode && !stream_ok) || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
-    const bool use_team = !use_isect && !use_hash && stream_ok && n_neg == 0 && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const bool use_team = !use_isect && !use_hash && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_hash ? 4 : use_or1 ? 5 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
     if (use_hash) {
@@ -2400,12 +2404,18 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       stp.items = p->d_items_w4;
       stp.n_items = p->n_w4;
       stp.slot_bytes = h->st_slot_bytes;
+      stp.final_add = h->d_final_add;
+      stp.final_blk = h->d_final_blk;
+      stp.part_lo = p->d_part_lo;
       stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
       const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
       CU(cudaEventRecord(ev[4], st));
       const size_t smem = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
-      if (p->k <= 32) k_score_stream<1><<<grid, h->st_warps * 32u, smem, st>>>(stp);
-      else k_score_stream<4><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      if (p->final_mode) {
+        if (p->k <= 32) k_score_stream<1, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+        else k_score_stream<4, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      } else if (p->k <= 32) k_score_stream<1, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      else k_score_stream<4, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
       CU(cudaEventRecord(ev[5], st));
       CU(cudaGetLastError());
       ++launches;
@@ -2567,7 +2577,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     if (p->n_w8 && !p->n_w4) {
       nb_ = h->tl_ctas_per_sm;
     } else if (p->n_w4) {
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream<1>, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream<1, false>, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
     } else if (!p->simple_kernel) {
       if (h->packed) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<true>, (int)h->NT + 32, p->smem_score);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_pipe<false>, (int)h->NT + 32, p->smem_score);
@@ -2631,8 +2641,24 @@ int bm25f_set_final_date(bm25f_handle* h, const double* date_add) {
     if (A.submitted) return fail(BM25F_EINVAL, "collect the submitted batches before changing the weighting");
   if (!date_add) {
     cudaFree(h->d_final_add);
+    cudaFree(h->d_final_blk);
     h->d_final_add = nullptr;
+    h->d_final_blk = nullptr;
     return 0;
+  }
+  const size_t nblk = (size_t)(h->n_docs / 32 + 2);
+  if (!h->d_final_blk) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_final_blk), nblk * sizeof(double));
+    if (e != cudaSuccess) {
+      h->d_final_blk = nullptr;
+      return fail(BM25F_ENOMEM, "cudaMalloc(%zu): %s", nblk * sizeof(double), cudaGetErrorString(e));
+    }
+  }
+  {
+    std::vector<double> blk(nblk, -INFINITY);
+    for (uint64_t d = 0; d < h->n_docs; ++d)
+      if (date_add[d] > blk[d >> 5]) blk[d >> 5] = date_add[d];      // NaN (no date) never compares greater
+    CU(cudaMemcpy(h->d_final_blk, blk.data(), nblk * sizeof(double), cudaMemcpyHostToDevice));
   }
   if (!h->d_final_add) {
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&h->d_final_add), std::max<uint64_t>(1, h->n_docs) * sizeof(double));

@@ -48,6 +48,10 @@ struct StreamParams {
   uint32_t doc_base;
   uint32_t pf_dist;                // L2 prefetch distance in postings (0: off)
   int k;
+  // FINAL instantiation only (a weighting with a final() step, final.cuh):
+  const double* final_add;         // [n_docs] date term of the document (NaN: no date)
+  const double* final_blk;         // [n_docs / 32 + 2] largest date term of each aligned block of 32 documents (-inf: none)
+  unsigned int* part_lo;           // [n_parts * k] low halves of the keys; part_keys holds the high halves
 };
 
 __device__ __forceinline__ void bulk_prefetch_l2(const void* p, uint32_t bytes) {
@@ -206,7 +210,7 @@ __device__ __forceinline__ void and_four(const SubCtx& cx, float w, uint32_t g, 
 
 // Requires: k <= 32 * KR, <= ST_MAX_LEAVES leaves, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store (bm25f_create compacts them away).
-template <int KR>
+template <int KR, bool FINAL>
 __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -279,8 +283,15 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
 #pragma unroll
     for (int j = 0; j < KR; ++j) top[j] = 0ull;
     unsigned long long thr_key = 0ull;
-    cx.thr = 1.17549435e-38f;                 // FLT_MIN until k hits exist: every first hit is hot
+    // FLT_MIN until k hits exist: every first hit is hot.  FINAL: final() can lift any match over the k-th
+    // best, so nothing is ever hot and every sub-range with a match is scanned (below).
+    cx.thr = FINAL ? __int_as_float(0x7f800000) : 1.17549435e-38f;
     unsigned int tot = 0;
+    uint32_t topl[FINAL ? KR : 1];            // FINAL: low halves of the keys (thr_key / thr_lo: the k-th best)
+#pragma unroll
+    for (int j = 0; j < (FINAL ? KR : 1); ++j) topl[j] = 0u;
+    uint32_t thr_lo = 0u;
+    double thr_v = -INFINITY, add_min = -INFINITY;   // FINAL: the k-th best final value; the least date term that can beat it
 
     uint32_t sub_lo = d_lo;
     while (sub_lo < d_hi) {
@@ -294,6 +305,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
         continue;
       }
       cx.sbase = cx.slots_addr - (sub_lo << shift);
+      const unsigned int tot_sub = tot;
 
       while (todo) {
         const int l = __ffs(todo) - 1;          // ascending leaf order = ascending group rank
@@ -383,6 +395,66 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
 
       // ---- sub-range epilogue ------------------------------------------------------------------
       __syncwarp();
+      if constexpr (FINAL) {
+        if (__any_sync(0xFFFFFFFFu, tot != tot_sub)) {          // the sub-range has matches: final() of each
+          // ... of each that can still beat the k-th best.  A dated document's value is below (1 + add) / 1e9,
+          // an undated one's below 1: blocks of 32 documents whose largest date term is too small are skipped
+          // with one coalesced load per 32 blocks, the others pay one gather per match.
+          const uint32_t n = cx.sub_hi - sub_lo;
+          const uint32_t n_it = (n + 31u) >> 5;
+          for (uint32_t c0 = 0; c0 < n_it; c0 += 32u) {
+            const uint32_t it = c0 + (uint32_t)lane;
+            bool pass = false;
+            if (it < n_it) {
+              const uint32_t d0 = sub_lo + (it << 5);
+              pass = (thr_v < 1.0) || (__ldg(sp.final_blk + (d0 >> 5)) >= add_min) ||
+                     ((d0 & 31u) != 0u && __ldg(sp.final_blk + (d0 >> 5) + 1) >= add_min);
+            }
+            unsigned im = __ballot_sync(0xFFFFFFFFu, pass);
+            while (im) {
+              const uint32_t j = ((c0 + (uint32_t)(__ffs(im) - 1)) << 5) + (uint32_t)lane;
+              im &= im - 1u;
+              unsigned long long kh = 0ull;
+              uint32_t kl = 0u;
+              if (j < n) {
+                float sc;
+                bool ok;
+                if (simple_or) {
+                  sc = lds_f32(cx.slots_addr + (j << 2));
+                  ok = sc != 0.0f;
+                } else {
+                  const uint2 v = lds_v2(cx.slots_addr + (j << 3));
+                  sc = __uint_as_float(v.y);
+                  ok = v.x == G;
+                }
+                if (ok) {
+                  const double add = __ldg(sp.final_add + sub_lo + j);
+                  if (isnan(add) ? (thr_v < 1.0) : (add >= add_min)) {
+                    kh = orderable_f64(final_value(sc, add));
+                    kl = 0xFFFFFFFFu - (sp.doc_base + sub_lo + j);
+                  }
+                }
+              }
+              unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_key, thr_lo));
+              while (pm) {
+                const int src = __ffs(pm) - 1;
+                pm &= pm - 1u;
+                const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
+                const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
+                if (key2_gt(bh, bl, thr_key, thr_lo)) {
+                  warp_topk2_insert_rows<KR>(top, topl, bh, bl, lane);
+                  warp_topk2_kth<KR>(top, topl, sp.k, thr_key, thr_lo);
+                  if (thr_key != 0ull) {
+                    thr_v = orderable_f64_value(thr_key);
+                    add_min = thr_v * 1e9 - 2.0;
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      if constexpr (!FINAL) {
       const uint32_t nhot = lds_u32(cx.cnt_addr);
       if (nhot) {
         const bool overflow = nhot > (uint32_t)ST_HOT;
@@ -418,6 +490,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
         if (thr_key != 0ull) cx.thr = key_score(thr_key);
         if (lane == 0) sts_u32(cx.cnt_addr, 0u);
       }
+      }
       for (uint32_t o = (uint32_t)lane * 16u; o < slot_bytes; o += 512u) sts_zero16(cx.slots_addr + o);
       __syncwarp();
       sub_lo += SW;
@@ -428,6 +501,12 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
 #pragma unroll
     for (int j = 0; j < KR; ++j)
       if (32 * j + lane < sp.k) out[32 * j + lane] = top[j];
+    if constexpr (FINAL) {
+      unsigned int* out_lo = sp.part_lo + (size_t)item.part * sp.k;
+#pragma unroll
+      for (int j = 0; j < KR; ++j)
+        if (32 * j + lane < sp.k) out_lo[32 * j + lane] = topl[j];
+    }
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xFFFFFFFFu, tot, o);
     if (lane == 0 && tot) atomicAdd(sp.totals + item.q, (unsigned long long)tot);
   }

@@ -25,13 +25,14 @@ t_plain = (time.perf_counter() - t0) / 10
 eng.set_final_date(add)
 for _ in range(2):
     out = eng.search_batch_final(batch, 10)
+eng.reset_stats()
 t0 = time.perf_counter()
 for _ in range(5):
     out = eng.search_batch_final(batch, 10)
 t_final = (time.perf_counter() - t0) / 5
 st = eng.stats()
 print("plain BM25F: %.3f ms per 10k-query batch (%.2f M q/s); date final: %.3f ms (%.2f M q/s); kernels %s"
-      % (t_plain * 1e3, 1e-2 / t_plain, t_final * 1e3, 1e-2 / t_final, {k: st[k] for k in ("ms_score", "n_executes")}))
+      % (t_plain * 1e3, 1e-2 / t_plain, t_final * 1e3, 1e-2 / t_final, {k: st[k] for k in ("ms_score", "ms_stream", "n_executes", "postings_stream", "postings_lookup")}))
 final, docids, counts, totals = out
 # sanity: dated documents first, values descending
 ok = all(np.all(np.diff(final[i, :counts[i]]) <= 0) for i in range(0, 10000, 97))
