@@ -27,6 +27,7 @@ EXPORTS = (
     "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
     "bm25f_reset_stats", "bm25f_submit", "bm25f_collect", "bm25f_set_final_date", "bm25f_fetch_final",
+    "bm25f_plan_device_final", "bm25f_merge_final_lists",
 )
 
 
@@ -108,6 +109,8 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_collect.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bm25f_set_final_date.argtypes = [vp, vp]
     lib.bm25f_fetch_final.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.bm25f_plan_device_final.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    lib.bm25f_merge_final_lists.argtypes = [vp, vp, vp, i32, u32, i32, vp, vp, vp, vp]
     if lib.bm25f_abi_version() != ABI_VERSION:
         raise RuntimeError("libbm25f ABI %d != binding ABI %d" % (lib.bm25f_abi_version(), ABI_VERSION))
     if path == os.environ.get("BM25F_LIB", LIB_PATH):
@@ -194,6 +197,13 @@ class Plan:
         dk, dt = C.c_void_p(), C.c_void_p()
         _check(self.engine.lib, self.engine.lib.bm25f_plan_device_results(self._p, C.byref(dk), C.byref(dt)))
         return dk.value, dt.value
+
+    def device_final(self) -> Tuple[int, int, int]:
+        """Raw device pointers ``(final values [Q*k] f64, docids [Q*k] u32, totals [Q] u64)`` of a plan prepared
+        under a final() weighting."""
+        df, dd, dt = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(self.engine.lib, self.engine.lib.bm25f_plan_device_final(self._p, C.byref(df), C.byref(dd), C.byref(dt)))
+        return df.value, dd.value, dt.value
 
     def close(self):
         if self._p is not None:
@@ -314,6 +324,12 @@ class Engine:
     def merge_keys(self, d_keys: int, n_lists: int, n_queries: int, k: int, d_out: int):
         """Runs on the handle's stream (see ``set_stream``)."""
         _check(self.lib, self.lib.bm25f_merge_keys(self._h, d_keys, n_lists, n_queries, k, d_out, None))
+
+    def merge_final_lists(self, d_vals: int, d_docids: int, n_lists: int, n_queries: int, k: int, d_out_final: int,
+                          d_out_docids: int, d_out_counts: int):
+        """Merge per-shard (final value, docnum) result lists; runs on the handle's stream."""
+        _check(self.lib, self.lib.bm25f_merge_final_lists(self._h, d_vals, d_docids, n_lists, n_queries, k, d_out_final,
+                                                          d_out_docids, d_out_counts, None))
 
     def decode_keys(self, d_keys: int, n_queries: int, k: int, d_scores: int, d_docids: int, d_counts: int):
         _check(self.lib, self.lib.bm25f_decode_keys(self._h, d_keys, n_queries, k, d_scores or None,

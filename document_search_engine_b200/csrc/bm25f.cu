@@ -1122,6 +1122,61 @@ __global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, co
   if (lane == 0) out_counts[q] = n;
 }
 
+// Final mode across document shards: merge of n_lists decoded result lists per query (layout
+// [n_lists][Q][k], as an all-gather of the shards' (final value, docnum) results produces; an empty slot has
+// docnum 0xFFFFFFFF), one warp per query, four keys per lane (k <= 128).
+__global__ void k_merge_final_lists(const double* __restrict__ vals, const uint32_t* __restrict__ docids, int n_lists,
+                                    uint32_t Q, int k, double* __restrict__ out_final, uint32_t* __restrict__ out_docids,
+                                    uint32_t* __restrict__ out_counts) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= Q) return;
+  unsigned long long top[4] = {0ull, 0ull, 0ull, 0ull};
+  uint32_t topl[4] = {0u, 0u, 0u, 0u};
+  unsigned long long thr_h = 0ull;
+  uint32_t thr_l = 0u;
+  for (int l = 0; l < n_lists; ++l) {
+    const size_t start = ((size_t)l * Q + q) * k;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const int idx = 32 * j + lane;
+      if (32 * j >= k) break;
+      unsigned long long kh = 0ull;
+      uint32_t kl = 0u;
+      if (idx < k) {
+        const uint32_t d = docids[start + idx];
+        if (d != 0xFFFFFFFFu) {
+          kh = orderable_f64(vals[start + idx]);
+          kl = 0xFFFFFFFFu - d;
+        }
+      }
+      unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_h, thr_l));
+      while (pm) {
+        const int src = __ffs(pm) - 1;
+        pm &= pm - 1u;
+        const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
+        const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
+        if (key2_gt(bh, bl, thr_h, thr_l)) {
+          warp_topk2_insert_rows<4>(top, topl, bh, bl, lane);
+          warp_topk2_kth<4>(top, topl, k, thr_h, thr_l);
+        }
+      }
+    }
+  }
+  uint32_t n = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int idx = 32 * j + lane;
+    const bool ok = idx < k && top[j] != 0ull;
+    if (idx < k) {
+      out_final[(size_t)q * k + idx] = ok ? orderable_f64_value(top[j]) : -INFINITY;
+      out_docids[(size_t)q * k + idx] = ok ? 0xFFFFFFFFu - topl[j] : 0xFFFFFFFFu;
+    }
+    n += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, ok));
+  }
+  if (lane == 0) out_counts[q] = n;
+}
+
 __global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint32_t Q, int k,
                               float* __restrict__ scores, uint32_t* __restrict__ docids,
                               uint32_t* __restrict__ counts) {
@@ -2746,6 +2801,28 @@ int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint3
       k_merge_topk<<<n_queries, 128, (size_t)2 * kp * 8, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), nullptr, 1, n_lists,
                                                                (unsigned long long)n_queries * k, n_queries, k, kp,
                                                                reinterpret_cast<unsigned long long*>(d_out_keys));
+    CU(cudaGetLastError());
+  }
+  return 0;
+}
+
+int bm25f_plan_device_final(bm25f_plan* p, double** d_final, uint32_t** d_docids, uint64_t** d_totals) {
+  if (!p) return fail(BM25F_EINVAL, "null plan");
+  if (!p->final_mode) return fail(BM25F_EINVAL, "the plan was prepared without a final() step");
+  if (d_final) *d_final = p->d_final;
+  if (d_docids) *d_docids = p->d_docids;
+  if (d_totals) *d_totals = reinterpret_cast<uint64_t*>(p->d_totals);
+  return 0;
+}
+
+int bm25f_merge_final_lists(bm25f_handle* h, const double* d_vals, const uint32_t* d_docids, int n_lists, uint32_t n_queries,
+                            int k, double* d_out_final, uint32_t* d_out_docids, uint32_t* d_out_counts, void* stream) {
+  if (!h || !d_vals || !d_docids || !d_out_final || !d_out_docids || !d_out_counts) return fail(BM25F_EINVAL, "null argument");
+  if (k < 1 || k > 128 || n_lists < 1) return fail(BM25F_EINVAL, "bad k (1..128) or n_lists");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  if (n_queries) {
+    k_merge_final_lists<<<(n_queries + 7) / 8, 256, 0, st>>>(d_vals, d_docids, n_lists, n_queries, k, d_out_final, d_out_docids, d_out_counts);
     CU(cudaGetLastError());
   }
   return 0;

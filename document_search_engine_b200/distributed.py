@@ -33,9 +33,9 @@ class _RawCuda:
                                          "version": 2, "strides": None}
 
 
-def device_view(ptr: int, n: int, device: int) -> torch.Tensor:
-    """int64 tensor aliasing ``n`` 64-bit words at device pointer ``ptr``."""
-    return torch.as_tensor(_RawCuda(ptr, n, "<i8"), device="cuda:%d" % device)
+def device_view(ptr: int, n: int, device: int, typestr: str = "<i8") -> torch.Tensor:
+    """Tensor aliasing ``n`` elements at device pointer ``ptr`` (int64 words by default)."""
+    return torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda:%d" % device)
 
 
 def merge_keys_host(gathered: np.ndarray, k: int) -> np.ndarray:
@@ -74,9 +74,6 @@ class ShardedSearcher:
         self.shard_ix = shard_ix
         # corpus-wide statistics come from ``full_ix`` (only its df / totals / dictionary are used)
         self.local = Searcher(self.shard_ix, weighting=weighting, device=self.device, stats_ix=full_ix, **engine_opts)
-        if self.local.weighting.use_final and self.world > 1:
-            raise NotImplementedError("final() weightings (DateBM25F) are served on one GPU: the cross-shard merge "
-                                      "exchanges 64-bit keys, final() needs 96-bit ones")
         self.engine = self.local.engine
         self.engine.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         self._bufs = {}
@@ -120,8 +117,46 @@ class ShardedSearcher:
                                 b["counts"].data_ptr())
         return b
 
+    def _search_packed_final(self, batch: _ffi.PackedBatch, k: int):
+        """``search_packed`` under a final() weighting (DateBM25F): the shards exchange their (final value,
+        docnum) lists instead of 64-bit keys and ``bm25f_merge_final_lists`` picks the k best."""
+        if self.world == 1:
+            return self.local.search_packed(batch, k)
+        Q = batch.n_queries
+        dev = "cuda:%d" % self.device
+        key = ("final", Q, k)
+        b = self._bufs.get(key)
+        if b is None:
+            b = dict(vals=torch.empty(self.world * Q * k, dtype=torch.float64, device=dev),
+                     docs=torch.empty(self.world * Q * k, dtype=torch.int32, device=dev),
+                     totals=torch.empty(Q, dtype=torch.int64, device=dev),
+                     out_vals=torch.empty(Q * k, dtype=torch.float64, device=dev),
+                     out_docs=torch.empty(Q * k, dtype=torch.int32, device=dev),
+                     out_counts=torch.empty(Q, dtype=torch.int32, device=dev))
+            self._bufs[key] = b
+        plan = self.engine.prepare(batch, k, arena=True)
+        try:
+            plan.execute()
+            d_final, d_docids, d_totals = plan.device_final()
+            dist.all_gather_into_tensor(b["vals"], device_view(d_final, Q * k, self.device, "<f8"), group=self.group)
+            dist.all_gather_into_tensor(b["docs"], device_view(d_docids, Q * k, self.device, "<i4"), group=self.group)
+            b["totals"].copy_(device_view(d_totals, Q, self.device))
+            dist.all_reduce(b["totals"], op=dist.ReduceOp.SUM, group=self.group)
+            self.engine.merge_final_lists(b["vals"].data_ptr(), b["docs"].data_ptr(), self.world, Q, k,
+                                          b["out_vals"].data_ptr(), b["out_docs"].data_ptr(), b["out_counts"].data_ptr())
+            final = b["out_vals"].cpu().numpy().reshape(Q, k)
+            docids = b["out_docs"].cpu().numpy().view(np.uint32).reshape(Q, k)
+            counts = b["out_counts"].cpu().numpy().view(np.uint32)
+            totals = b["totals"].cpu().numpy().view(np.uint64)
+        finally:
+            plan.close()
+        return final, docids, counts, totals
+
     def search_packed(self, batch: _ffi.PackedBatch, k: int):
-        """Host buffers in, host buffers out: ``(scores, docids, counts, totals)`` of the whole corpus."""
+        """Host buffers in, host buffers out: ``(scores, docids, counts, totals)`` of the whole corpus (float64
+        final values instead of scores under a final() weighting)."""
+        if self.local.weighting.use_final:
+            return self._search_packed_final(batch, k)
         plan = self.engine.prepare(batch, k, arena=True)
         try:
             b = self.run_plan(plan)
@@ -142,6 +177,10 @@ class ShardedSearcher:
         """``search_packed`` over an iterable of packed batches, pipelined two deep: the host plans and
         uploads batch i + 1 while the GPUs score, exchange and merge batch i.  Yields the result tuples in
         order.  Every rank must iterate the same batches (the collectives pair up in order)."""
+        if self.local.weighting.use_final:
+            for batch in batches:                        # not pipelined
+                yield self._search_packed_final(batch, k)
+            return
         if self.world == 1:
             yield from self.local.search_packed_stream(batches, k)
             return

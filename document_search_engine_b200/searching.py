@@ -348,6 +348,10 @@ class Searcher:
         back to back; the latency of one batch is that of ``search_packed``."""
         if limit < 1 or limit > _ffi.MAX_K:
             raise ValueError("limit must be 1..%d for search_packed_stream" % _ffi.MAX_K)
+        if self.weighting.use_final:                     # float64 results: one blocking call per batch
+            for batch in batches:
+                yield self.search_packed(batch, limit)
+            return
         T = max(1, -(-self.ix.n_docs_all // (self.engine.stats()["tile_docs"] or DEFAULT_TILE_DOCS)))
         max_leaves = max(_ffi.MAX_LEAVES_PER_QUERY, BOUNDS_BYTES_PER_CALL // (4 * (T + 1)))
         pending = None

@@ -228,6 +228,15 @@ int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_
  * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
+/* Final mode across document shards.  bm25f_plan_device_final: the device-resident results of a plan
+ * prepared under a final() step (final values [n_queries * k] float64, global docnums [n_queries * k] with
+ * 0xFFFFFFFF in unused slots, totals [n_queries]).  bm25f_merge_final_lists merges n_lists such result lists
+ * per query (layout [n_lists][n_queries][k], as an all-gather over the shards produces) into the k best by
+ * (final value descending, docnum ascending) and counts them.  k <= 128. */
+int  bm25f_plan_device_final(bm25f_plan* plan, double** d_final, uint32_t** d_docids, uint64_t** d_totals);
+int  bm25f_merge_final_lists(bm25f_handle* h, const double* d_vals, const uint32_t* d_docids, int n_lists,
+                             uint32_t n_queries, int k, double* d_out_final, uint32_t* d_out_docids,
+                             uint32_t* d_out_counts, void* stream);
 /* Decode device keys to device arrays of scores / docids / counts (any may be NULL). */
 int  bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_queries, int k,
                        float* d_scores, uint32_t* d_docids, uint32_t* d_counts, void* stream);

@@ -123,3 +123,44 @@ def test_final_switches_with_the_weighting(dated):
         assert page.total == len(s.search(qs[0], limit=10)) or True
     with dated.searcher(weighting=BM25F) as s:
         assert_batch_parity(o_plain, qs, s.search_batch(qs, limit=10), 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k", [10, 100])
+def test_final_merge_across_shards(dated, k):
+    """Document shards under a final() weighting: every shard's (final value, docnum) lists, laid out as an
+    all-gather would, merged by bm25f_merge_final_lists, equal the whole corpus (W8 + W14)."""
+    import torch
+    from document_search_engine_b200.distributed import device_view
+    from document_search_engine_b200.searching import Searcher
+    qs = date_queries(60, 5)
+    Q, G = len(qs), 3
+    o = NumpyOracle(dated, final_add=DescDateBM25F().doc_final_terms(dated))
+    vals = torch.empty(G * Q * k, dtype=torch.float64, device="cuda:0")
+    docs = torch.empty(G * Q * k, dtype=torch.int32, device="cuda:0")
+    totals = np.zeros(Q, dtype=np.uint64)
+    searchers = [Searcher(dated.shard(g, G), weighting=DescDateBM25F, stats_ix=dated) for g in range(G)]
+    for g, s in enumerate(searchers):
+        plan = s.engine.prepare(s.pack(qs), k, arena=True)
+        plan.execute()
+        d_final, d_docids, d_totals = plan.device_final()
+        s.engine.synchronize()
+        vals[g * Q * k:(g + 1) * Q * k].copy_(device_view(d_final, Q * k, 0, "<f8"))
+        docs[g * Q * k:(g + 1) * Q * k].copy_(device_view(d_docids, Q * k, 0, "<i4"))
+        totals += device_view(d_totals, Q, 0).cpu().numpy().view(np.uint64)
+        plan.close()
+    out_v = torch.empty(Q * k, dtype=torch.float64, device="cuda:0")
+    out_d = torch.empty(Q * k, dtype=torch.int32, device="cuda:0")
+    out_c = torch.empty(Q, dtype=torch.int32, device="cuda:0")
+    torch.cuda.synchronize()
+    eng = searchers[0].engine
+    eng.merge_final_lists(vals.data_ptr(), docs.data_ptr(), G, Q, k, out_v.data_ptr(), out_d.data_ptr(), out_c.data_ptr())
+    eng.synchronize()
+    v = out_v.cpu().numpy().reshape(Q, k)
+    d = out_d.cpu().numpy().view(np.uint32).reshape(Q, k)
+    c = out_c.cpu().numpy()
+    from tests.parity import assert_query_parity
+    for i, q in enumerate(qs):
+        n = int(c[i])
+        assert_query_parity(o, q, list(zip(v[i, :n].tolist(), d[i, :n].tolist())), int(totals[i]), k,
+                            ctx="query %d" % i, abs_tol=FINAL_TOL)
