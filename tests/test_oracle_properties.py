@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from document_search_engine_b200 import And, FlatIndex, Or, Term
+from document_search_engine_b200 import And, FlatIndex, Not, Or, Term
 from document_search_engine_b200.variants import expand_with_map
 from oracle.numpy_oracle import NumpyOracle
 from oracle.whoosh_port import OracleSearcher
@@ -16,6 +16,11 @@ term_st = st.builds(lambda w, b: Term("f", w, boost=b), st.sampled_from(WORDS + 
 or_st = st.builds(Or, st.lists(term_st, min_size=1, max_size=3))
 # the normal form the engine scores (SURVEY.md §8 b): a term, an OR of terms, or an AND of those
 query_st = st.one_of(term_st, or_st, st.builds(And, st.lists(st.one_of(term_st, or_st), min_size=1, max_size=3)))
+# ... plus NOT clauses inside AND / OR (Whoosh's AndNotMatcher)
+not_st = st.builds(Not, st.one_of(term_st, or_st))
+not_query_st = st.one_of(
+    st.builds(lambda pos, neg: And(pos + neg), st.lists(st.one_of(term_st, or_st), min_size=1, max_size=3), st.lists(not_st, min_size=1, max_size=2)),
+    st.builds(lambda pos, neg: Or(pos + neg), st.lists(term_st, min_size=1, max_size=3), st.lists(not_st, min_size=1, max_size=2)))
 
 
 def build(docs, deleted_mask):
@@ -83,3 +88,27 @@ def test_variant_expansion_only_adds_matches(docs, q):
     t0, n0 = o.search(q, limit=None)
     t1, n1 = o.search(expand_with_map(q, lambda w: partner.get(w)), limit=None)
     assert n0 <= n1 and {d for _, d in t0} <= {d for _, d in t1}
+
+
+@settings(max_examples=120, deadline=None)
+@given(docs_st, st.lists(st.booleans(), min_size=24, max_size=24), not_query_st, st.sampled_from([1, 3, None]))
+def test_not_clauses(docs, dele, q, limit):
+    """AndNot: the two oracles agree, and the matches are exactly the matches of the positive part that are
+    in none of the negated queries, with the positive part's scores."""
+    ix = build(docs, dele)
+    a_top, a_tot = OracleSearcher(ix).search(q, limit=limit)
+    b_top, b_tot = NumpyOracle(ix).search(q, limit=limit)
+    assert a_tot == b_tot
+    assert [d for _, d in a_top] == [d for _, d in b_top]
+    assert [s for s, _ in a_top] == pytest.approx([s for s, _ in b_top], rel=1e-12)
+    o = NumpyOracle(ix)
+    pos = type(q)([s for s in q.subqueries if not isinstance(s, Not)])
+    d_pos, s_pos = o.match_all(pos)
+    excluded = set()
+    for s in q.subqueries:
+        if isinstance(s, Not):
+            excluded |= set(o.match_all(s.query)[0].tolist())
+    d_q, s_q = o.match_all(q)
+    want = [(d, sc) for d, sc in zip(d_pos.tolist(), s_pos.tolist()) if d not in excluded]
+    assert d_q.tolist() == [d for d, _ in want]
+    assert s_q.tolist() == pytest.approx([sc for _, sc in want], rel=1e-12)
