@@ -1388,7 +1388,8 @@ size_t pipe_smem_bytes(const bm25f_handle* h, int cap) {
 size_t team_smem_bytes(const bm25f_handle* h) { return (size_t)h->tl_warps * h->tl_slot_bytes + sizeof(TeamShared); }
 
 size_t stream_smem_bytes(uint32_t warps, uint32_t slot_bytes) {
-  return (size_t)warps * (slot_bytes + ST_MAX_LEAVES * 256 + ST_HOT * 2 + 4);
+  // slots, tails, hot list, hot counter, and (16-byte aligned) the leaf records
+  return (size_t)warps * (slot_bytes + ST_MAX_LEAVES * 256 + ST_HOT * 2 + 4) + 16 + (size_t)warps * ST_MAX_LEAVES * 32;
 }
 
 int pipe_prune_at(int k) { return std::max(2 * k, 256); }

@@ -14,9 +14,10 @@
 //    documents it is sweeping: 4-byte score slots for a flat OR, 8-byte {groups matched, score}
 //    slots for AND / AND-of-OR.  Slots are cleared with 128-bit stores after a sub-range that
 //    touched them.
-//  * The state of leaf l (cursor, end, weight, group, docid at the cursor) lives in LANE l of the
-//    warp, so "which leaves have a posting in this sub-range" is one compare + ballot and a leaf
-//    that has none costs nothing.  The partially consumed row of every leaf (its TAIL) is parked
+//  * The docid at the cursor of leaf l lives in LANE l of the warp, so "which leaves have a posting in
+//    this sub-range" is one compare + ballot and a leaf that has none costs nothing; the rest of the
+//    leaf's record (list origin, cursor, end, weight, group) sits in shared memory and is read with one
+//    broadcast load per visit.  The partially consumed row of every leaf (its TAIL) is parked
 //    in shared memory between visits; a visit that runs past its tail streams SUPER-ROWS (128
 //    postings, four loads in flight per lane, the next super-row requested before the current one
 //    is processed) straight into registers, with bulk L2 prefetches (cp.async.bulk.prefetch.L2,
@@ -91,6 +92,14 @@ __device__ __forceinline__ uint32_t atoms_inc(uint32_t addr) {
   uint32_t v;
   asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(addr) : "memory");
   return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ void sts_zero16(uint32_t addr) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
@@ -217,13 +226,17 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const uint32_t slot_bytes = sp.slot_bytes;
-  // shared memory: [nwarps][slot_bytes] slots | [nwarps][ST_MAX_LEAVES][32] tails (8 B) | [nwarps][ST_HOT] hot (2 B) | [nwarps] hot counters
+  // shared memory: [nwarps][slot_bytes] slots | [nwarps][ST_MAX_LEAVES][32] tails (8 B) | [nwarps][ST_HOT] hot (2 B) | [nwarps] hot counters |
+  // [nwarps][ST_MAX_LEAVES] leaf records (32 B, 16-byte aligned)
   SubCtx cx;
   const uint32_t smem0 = smem_u32(smem_raw);
   cx.slots_addr = smem0 + (uint32_t)warp * slot_bytes;
   const uint32_t tails_addr = smem0 + (uint32_t)nwarps * slot_bytes + (uint32_t)warp * (ST_MAX_LEAVES * 256u) + (uint32_t)lane * 8u;
   cx.hot_addr = smem0 + (uint32_t)nwarps * (slot_bytes + ST_MAX_LEAVES * 256u) + (uint32_t)warp * (ST_HOT * 2);
   cx.cnt_addr = smem0 + (uint32_t)nwarps * (slot_bytes + ST_MAX_LEAVES * 256u + ST_HOT * 2) + (uint32_t)warp * 4u;
+  // leaf records of the warp's item: {base lo, base hi, cursor, end | weight, group}, 32 bytes per leaf
+  const uint32_t state_addr = ((smem0 + (uint32_t)nwarps * (slot_bytes + ST_MAX_LEAVES * 256u + ST_HOT * 2 + 4u) + 15u) & ~15u) +
+                              (uint32_t)warp * (ST_MAX_LEAVES * 32u);
 
   for (uint32_t o = (uint32_t)lane * 16u; o < slot_bytes; o += 512u) sts_zero16(cx.slots_addr + o);
   if (lane == 0) sts_u32(cx.cnt_addr, 0u);
@@ -244,25 +257,25 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
     const uint32_t SW = slot_bytes >> shift;            // documents per sub-range
     const uint32_t d_lo = item.tile_begin, d_hi = item.tile_end;
 
-    // ---- leaf state: lane l holds leaf l ------------------------------------------------------
-    // Index space of a leaf: absolute posting index minus s_base, where s_base = off & ~31, so every
+    // ---- leaf state ------------------------------------------------------------------------------
+    // Index space of a leaf: absolute posting index minus its base, where base = off & ~31, so every
     // row is 256-byte aligned.  The list occupies [off & 31, s_end).
-    unsigned long long s_base = 0ull;
-    uint32_t s_cur = 0u, s_end = 0u, s_grp = 0u, s_next = 0xFFFFFFFFu;
-    float s_w = 0.0f;
+    // The records live in shared memory (one broadcast load per visit instead of six shuffles); the docid at
+    // the cursor of leaf l stays in lane l, so "which leaves have a posting in this sub-range" is one ballot.
+    uint32_t s_next = 0xFFFFFFFFu;
     if (lane < L) {
       const LeafRec lf = sp.leaves[q.leaf_begin + lane];
       const uint32_t a = (uint32_t)(lf.off & 31ull);
-      s_base = lf.off - a;
-      s_cur = a;
-      s_end = a + lf.df;
-      s_w = lf.w;
-      s_grp = lf.group;
+      const unsigned long long base = lf.off - a;
+      sts_v4(state_addr + (uint32_t)lane * 32u, (uint32_t)base, (uint32_t)(base >> 32), a, a + lf.df);
+      sts_v2(state_addr + (uint32_t)lane * 32u + 16u, __float_as_uint(lf.w), lf.group);
     }
+    __syncwarp();
     for (int l = 0; l < L; ++l) {
-      const unsigned long long base = __shfl_sync(0xFFFFFFFFu, s_base, l);
-      const uint32_t end = __shfl_sync(0xFFFFFFFFu, s_end, l);
-      uint32_t cur = __shfl_sync(0xFFFFFFFFu, s_cur, l);
+      const uint4 st4 = lds_v4(state_addr + (uint32_t)l * 32u);
+      const unsigned long long base = (unsigned long long)st4.x | ((unsigned long long)st4.y << 32);
+      const uint32_t end = st4.w;
+      uint32_t cur = st4.z;
       const uint2* __restrict__ pairs = sp.pairs + base;
       if (d_lo > 0u) cur += warp_lower_bound(pairs + cur, end - cur, d_lo, lane);
       // park the row that holds the cursor; remember the docid at the cursor
@@ -271,7 +284,8 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
       if (idx < end) t = ldg_pair(pairs + idx);
       sts_v2(tails_addr + (uint32_t)l * 256u, t.x, t.y);
       const uint32_t nd = __shfl_sync(0xFFFFFFFFu, t.x, cur & 31u);
-      if (lane == l) { s_cur = cur; s_next = (cur < end) ? nd : 0xFFFFFFFFu; }
+      if (lane == 0) sts_u32(state_addr + (uint32_t)l * 32u + 8u, cur);
+      if (lane == l) s_next = (cur < end) ? nd : 0xFFFFFFFFu;
       if (sp.pf_dist) {
         // chunks [cur, cur + pf_dist + chunk), one per lane
         const uint32_t c0 = (cur & ~(ST_PF_CHUNK - 1u)) + (uint32_t)lane * ST_PF_CHUNK;
@@ -279,6 +293,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
       }
     }
 
+    __syncwarp();
     unsigned long long top[KR];               // lane i, row j: the (32 j + i)-th best key of this item so far
 #pragma unroll
     for (int j = 0; j < KR; ++j) top[j] = 0ull;
@@ -310,11 +325,13 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
       while (todo) {
         const int l = __ffs(todo) - 1;          // ascending leaf order = ascending group rank
         todo &= todo - 1u;
-        const unsigned long long base = __shfl_sync(0xFFFFFFFFu, s_base, l);
-        const uint32_t end = __shfl_sync(0xFFFFFFFFu, s_end, l);
-        uint32_t cur = __shfl_sync(0xFFFFFFFFu, s_cur, l);
-        const float w = __shfl_sync(0xFFFFFFFFu, s_w, l);
-        const uint32_t g = __shfl_sync(0xFFFFFFFFu, s_grp, l);
+        const uint4 st4 = lds_v4(state_addr + (uint32_t)l * 32u);
+        const uint2 wg = lds_v2(state_addr + (uint32_t)l * 32u + 16u);
+        const unsigned long long base = (unsigned long long)st4.x | ((unsigned long long)st4.y << 32);
+        const uint32_t end = st4.w;
+        uint32_t cur = st4.z;
+        const float w = __uint_as_float(wg.x);
+        const uint32_t g = wg.y;
         const bool lastg = (g + 1u == G);
         const uint2* __restrict__ pairs = sp.pairs + base;
         const uint32_t tail = tails_addr + (uint32_t)l * 256u;
@@ -390,7 +407,8 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
         }
         if (dirty) sts_v2(tail, r.x, r.y);
         const uint32_t nd = __shfl_sync(0xFFFFFFFFu, r.x, cur & 31u);
-        if (lane == l) { s_cur = cur; s_next = (cur < end) ? nd : 0xFFFFFFFFu; }
+        if (lane == 0) sts_u32(state_addr + (uint32_t)l * 32u + 8u, cur);
+        if (lane == l) s_next = (cur < end) ? nd : 0xFFFFFFFFu;
       }
 
       // ---- sub-range epilogue ------------------------------------------------------------------

@@ -74,7 +74,7 @@ def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
 
 
 @pytest.mark.parametrize("subtile,wsplit,warps,pf", [(128, 2048, 16, 512), (512, 0, 4, 0xFFFFFFFF), (1024, 1 << 14, 8, 0),
-                                                      (3072, 1 << 20, 16, 4096), (12288, 1 << 12, 4, 1024)])
+                                                      (2816, 1 << 20, 16, 4096), (12288, 1 << 12, 4, 1024)])
 @pytest.mark.parametrize("mode", ["mixed", "variants"])
 def test_stream_kernel(cfg1, subtile, wsplit, warps, pf, mode):
     """Stream kernel: sub-range sizes, many small items per query (document ranges that start
