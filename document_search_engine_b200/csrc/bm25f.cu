@@ -1859,6 +1859,23 @@ void order_items(const std::vector<ItemRec>& items, const std::vector<uint64_t>&
   for (size_t i = 0; i < items.size(); ++i) out[count[NB - 1 - bucket(w[i])]++] = items[i];
 }
 
+// Planner threads of this process: BM25F_PLAN_THREADS, else the host's cores shared out between the ranks of
+// the box (torchrun exports LOCAL_WORLD_SIZE; one process per GPU, and all of them plan at the same time
+// because the collectives keep them in step), at most 8.
+unsigned plan_thread_budget() {
+  static const unsigned budget = [] {
+    if (const char* e = getenv("BM25F_PLAN_THREADS")) {
+      const int v = atoi(e);
+      if (v >= 1) return (unsigned)std::min(v, 8);
+    }
+    unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    unsigned local = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) local = (unsigned)std::max(1, atoi(e));
+    return std::min(8u, std::max(1u, hw / local));
+  }();
+  return budget;
+}
+
 // Host planning + upload.  With use_arena the plan's buffers live in the handle's grow-only
 // workspaces (pinned host staging, one device arena): no allocation on the hot path.
 int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out, bool use_arena) {
@@ -2166,7 +2183,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto t_a = now();
   unsigned n_thr = 1;
-  if (Q >= 2048) n_thr = std::min<unsigned>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), Q / 1024);
+  if (Q >= 2048) n_thr = std::min<unsigned>(plan_thread_budget(), Q / 1024);
   std::vector<PlanLocal> locals(n_thr);
   if (n_thr == 1) {
     plan_range(0, Q, locals[0]);

@@ -33,9 +33,20 @@ class _RawCuda:
                                          "version": 2, "strides": None}
 
 
+_VIEWS = {}
+
+
 def device_view(ptr: int, n: int, device: int, typestr: str = "<i8") -> torch.Tensor:
-    """Tensor aliasing ``n`` elements at device pointer ``ptr`` (int64 words by default)."""
-    return torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda:%d" % device)
+    """Tensor aliasing ``n`` elements at device pointer ``ptr`` (int64 words by default).  Views are cached:
+    the library's result buffers live in two grow-only workspaces, so the same few pointers recur."""
+    key = (ptr, n, device, typestr)
+    v = _VIEWS.get(key)
+    if v is None:
+        if len(_VIEWS) > 64:
+            _VIEWS.clear()
+        v = torch.as_tensor(_RawCuda(ptr, n, typestr), device="cuda:%d" % device)
+        _VIEWS[key] = v
+    return v
 
 
 def merge_keys_host(gathered: np.ndarray, k: int) -> np.ndarray:
