@@ -12,7 +12,7 @@
 //   k_score_isect     (isect.cuh)         ANDs: candidate-driven lookups (IntersectionMatcher + skip_to)
 //   k_score_team      (team.cuh)          symmetric ANDs: CTA-built bounds table, private slices
 //   k_score_hash      (hash.cuh)          experimental one-dense OR
-//   k_tile_bounds, k_score_pipe, k_score_topk   general fallback (k > 128, many leaves, paging, odd weights)
+//   k_tile_bounds, k_score_pipe, k_score_topk   general fallback (k > 256, many leaves, paging, odd weights)
 //   k_merge_topk_warp / k_merge_topk      merge of per-item (or per-GPU) top-k lists
 //   k_decode_keys                         keys -> (score, docid, count)
 #include "../../include/bm25f.h"
@@ -90,6 +90,7 @@ constexpr uint32_t QF_SIMPLE_OR = 1u;
 constexpr uint32_t QF_STREAM_LAST = 2u;   // one-dense OR: the last leaf is streamed accumulator-free
 constexpr uint32_t QF_TAKEN = 4u;         // ... by k_score_isect: after_key is the word offset of its "taken" bitmap
 constexpr int MAXL = BM25F_MAX_LEAVES_PER_QUERY;
+constexpr int FAST_MAX_K = 256;           // largest k of the warp kernels: 8 keys per lane (the reference's listing page asks for 150)
 
 // W11 order as one unsigned 64-bit key: score descending, docnum ascending.  All keys of
 // distinct documents are distinct, so "top-k by key" is exactly the reference collector.
@@ -1071,7 +1072,8 @@ __global__ void k_merge_topk_warp(const unsigned long long* __restrict__ keys_in
 }
 
 // Final mode: merge of a query's partial lists of 96-bit keys and decode in one pass, one warp per query,
-// four keys per lane (k <= 128).
+// KR keys per lane (k <= 32 * KR).
+template <int KR>
 __global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, const unsigned int* __restrict__ part_lo,
                               const QueryRec* __restrict__ queries, uint32_t Q, int k, double* __restrict__ out_final,
                               uint32_t* __restrict__ out_docids, uint32_t* __restrict__ out_counts) {
@@ -1080,13 +1082,15 @@ __global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, co
   if (q >= Q) return;
   const QueryRec qr = queries[q];
   const size_t start = (size_t)qr.part_begin * k;
-  unsigned long long top[4] = {0ull, 0ull, 0ull, 0ull};
-  uint32_t topl[4] = {0u, 0u, 0u, 0u};
+  unsigned long long top[KR];
+  uint32_t topl[KR];
+#pragma unroll
+  for (int j = 0; j < KR; ++j) { top[j] = 0ull; topl[j] = 0u; }
   unsigned long long thr_h = 0ull;
   uint32_t thr_l = 0u;
   for (uint32_t l = 0; l < qr.n_parts; ++l) {
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < KR; ++j) {
       const int idx = 32 * j + lane;
       if (32 * j >= k) break;
       unsigned long long kh = 0ull;
@@ -1102,15 +1106,15 @@ __global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, co
         const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
         const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
         if (key2_gt(bh, bl, thr_h, thr_l)) {
-          warp_topk2_insert_rows<4>(top, topl, bh, bl, lane);
-          warp_topk2_kth<4>(top, topl, k, thr_h, thr_l);
+          warp_topk2_insert_rows<KR>(top, topl, bh, bl, lane);
+          warp_topk2_kth<KR>(top, topl, k, thr_h, thr_l);
         }
       }
     }
   }
   uint32_t n = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < KR; ++j) {
     const int idx = 32 * j + lane;
     const bool ok = idx < k && top[j] != 0ull;
     if (idx < k) {
@@ -1124,21 +1128,24 @@ __global__ void k_merge_final(const unsigned long long* __restrict__ part_hi, co
 
 // Final mode across document shards: merge of n_lists decoded result lists per query (layout
 // [n_lists][Q][k], as an all-gather of the shards' (final value, docnum) results produces; an empty slot has
-// docnum 0xFFFFFFFF), one warp per query, four keys per lane (k <= 128).
+// docnum 0xFFFFFFFF), one warp per query, KR keys per lane (k <= 32 * KR).
+template <int KR>
 __global__ void k_merge_final_lists(const double* __restrict__ vals, const uint32_t* __restrict__ docids, int n_lists,
                                     uint32_t Q, int k, double* __restrict__ out_final, uint32_t* __restrict__ out_docids,
                                     uint32_t* __restrict__ out_counts) {
   const int lane = threadIdx.x & 31;
   const uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (q >= Q) return;
-  unsigned long long top[4] = {0ull, 0ull, 0ull, 0ull};
-  uint32_t topl[4] = {0u, 0u, 0u, 0u};
+  unsigned long long top[KR];
+  uint32_t topl[KR];
+#pragma unroll
+  for (int j = 0; j < KR; ++j) { top[j] = 0ull; topl[j] = 0u; }
   unsigned long long thr_h = 0ull;
   uint32_t thr_l = 0u;
   for (int l = 0; l < n_lists; ++l) {
     const size_t start = ((size_t)l * Q + q) * k;
 #pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < KR; ++j) {
       const int idx = 32 * j + lane;
       if (32 * j >= k) break;
       unsigned long long kh = 0ull;
@@ -1157,15 +1164,15 @@ __global__ void k_merge_final_lists(const double* __restrict__ vals, const uint3
         const unsigned long long bh = __shfl_sync(0xFFFFFFFFu, kh, src);
         const uint32_t bl = __shfl_sync(0xFFFFFFFFu, kl, src);
         if (key2_gt(bh, bl, thr_h, thr_l)) {
-          warp_topk2_insert_rows<4>(top, topl, bh, bl, lane);
-          warp_topk2_kth<4>(top, topl, k, thr_h, thr_l);
+          warp_topk2_insert_rows<KR>(top, topl, bh, bl, lane);
+          warp_topk2_kth<KR>(top, topl, k, thr_h, thr_l);
         }
       }
     }
   }
   uint32_t n = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < KR; ++j) {
     const int idx = 32 * j + lane;
     const bool ok = idx < k && top[j] != 0ull;
     if (idx < k) {
@@ -1748,8 +1755,9 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[5] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
-                           (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>};
+    const void* wfns[7] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
+                           (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>,
+                           (const void*)k_score_stream<8, false>, (const void*)k_score_stream<8, true>};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -2058,17 +2066,17 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= 128 && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= FAST_MAX_K && nlq <= 8 && all_pos && qr.after_key == 0ull;
     // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
     // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
     // ... unless its smallest group is so much sparser than the rest that looking its documents up in
     // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
     const uint64_t g0 = gsize[order[0]];
-    if (n_neg && !(k <= 128 && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
-      PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 128, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
-    const bool isect_ok = k <= 128 && nlq <= 32 && all_pos && qr.after_key == 0ull;
+    if (n_neg && !(k <= FAST_MAX_K && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
+      PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 256, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
+    const bool isect_ok = k <= FAST_MAX_K && nlq <= 32 && all_pos && qr.after_key == 0ull;
     if (final_mode && !isect_ok && !stream_ok)
-      PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 128, at most 32 leaves, positive weights and no paging bound", qi);
+      PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 256, at most 32 leaves, positive weights and no paging bound", qi);
     // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
     // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
     uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
@@ -2486,9 +2494,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       const size_t smem = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
       if (p->final_mode) {
         if (p->k <= 32) k_score_stream<1, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
-        else k_score_stream<4, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+        else if (p->k <= 128) k_score_stream<4, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+        else k_score_stream<8, true><<<grid, h->st_warps * 32u, smem, st>>>(stp);
       } else if (p->k <= 32) k_score_stream<1, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
-      else k_score_stream<4, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      else if (p->k <= 128) k_score_stream<4, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
+      else k_score_stream<8, false><<<grid, h->st_warps * 32u, smem, st>>>(stp);
       CU(cudaEventRecord(ev[5], st));
       CU(cudaGetLastError());
       ++launches;
@@ -2516,7 +2526,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       }
       const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_o1 + IS_WARPS - 1) / IS_WARPS);
       if (p->k <= 32) k_score_isect<1, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
-      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);      // one-dense ORs are planned for k <= 32 only
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2545,9 +2555,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
         // final() of every match before the top-k: 96-bit keys, more registers, 2 CTAs per SM at least
         const unsigned gridf = std::min<unsigned>((unsigned)(h->n_sms * 2), (p->n_is + IS_WARPS - 1) / IS_WARPS);
         if (p->k <= 32) k_score_isect<1, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
-        else k_score_isect<4, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
+        else if (p->k <= 128) k_score_isect<4, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
+        else k_score_isect<8, true><<<gridf, IS_WARPS * 32, 0, ax>>>(ip);
       } else if (p->k <= 32) k_score_isect<1, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
-      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else if (p->k <= 128) k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
+      else k_score_isect<8, false><<<std::min<unsigned>(grid, (unsigned)(h->n_sms * 2)), IS_WARPS * 32, 0, ax>>>(ip);
       CU(cudaGetLastError());
       ++launches;
     }
@@ -2602,7 +2614,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   if (!p->n_w4) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventRecord(ev[5], st)); }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q && p->final_mode) {
-    k_merge_final<<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
+    if (p->k <= 128) k_merge_final<4><<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
+    else k_merge_final<8><<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
     CU(cudaGetLastError());
     ++launches;
   } else if (p->Q) {
@@ -2836,11 +2849,12 @@ int bm25f_plan_device_final(bm25f_plan* p, double** d_final, uint32_t** d_docids
 int bm25f_merge_final_lists(bm25f_handle* h, const double* d_vals, const uint32_t* d_docids, int n_lists, uint32_t n_queries,
                             int k, double* d_out_final, uint32_t* d_out_docids, uint32_t* d_out_counts, void* stream) {
   if (!h || !d_vals || !d_docids || !d_out_final || !d_out_docids || !d_out_counts) return fail(BM25F_EINVAL, "null argument");
-  if (k < 1 || k > 128 || n_lists < 1) return fail(BM25F_EINVAL, "bad k (1..128) or n_lists");
+  if (k < 1 || k > FAST_MAX_K || n_lists < 1) return fail(BM25F_EINVAL, "bad k (1..256) or n_lists");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
   if (n_queries) {
-    k_merge_final_lists<<<(n_queries + 7) / 8, 256, 0, st>>>(d_vals, d_docids, n_lists, n_queries, k, d_out_final, d_out_docids, d_out_counts);
+    if (k <= 128) k_merge_final_lists<4><<<(n_queries + 7) / 8, 256, 0, st>>>(d_vals, d_docids, n_lists, n_queries, k, d_out_final, d_out_docids, d_out_counts);
+    else k_merge_final_lists<8><<<(n_queries + 7) / 8, 256, 0, st>>>(d_vals, d_docids, n_lists, n_queries, k, d_out_final, d_out_docids, d_out_counts);
     CU(cudaGetLastError());
   }
   return 0;

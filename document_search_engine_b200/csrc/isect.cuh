@@ -49,7 +49,7 @@ struct IsectParams {
 constexpr int IS_WARPS = 8;
 
 template <int KR, bool FINAL>
-__global__ void __launch_bounds__(IS_WARPS * 32, FINAL ? 2 : KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
+__global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
   const int lane = threadIdx.x & 31;
   const uint2* __restrict__ store = ip.pairs;
 

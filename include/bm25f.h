@@ -85,7 +85,7 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 128, <= 8 leaves, positive
+  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 256, <= 8 leaves, positive
                                     weights, no paging bound - flat ORs on warp streams, ANDs whose smallest
                                     group is far sparser than the rest by candidate-driven lookups, other
                                     ANDs on warp teams; else the bulk-copy pipeline),
@@ -175,7 +175,7 @@ int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
  * without a date.  While set, a match with BM25F score s ranks by the float64 value
  *     v = 1 - 1/s                      (no date)
  *     v = ((1 - 1/s) + date_add) / 1e9 (dated)
- * descending, docnum ascending; plans are fetched with bm25f_fetch_final (which returns v), k <= 128, at most
+ * descending, docnum ascending; plans are fetched with bm25f_fetch_final (which returns v), k <= 256, at most
  * 32 leaves per query, and bm25f_search_batch / bm25f_submit / bm25f_fetch are refused.  NULL switches the
  * step off again. */
 int  bm25f_set_final_date(bm25f_handle* h, const double* date_add);
@@ -232,7 +232,7 @@ int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint
  * prepared under a final() step (final values [n_queries * k] float64, global docnums [n_queries * k] with
  * 0xFFFFFFFF in unused slots, totals [n_queries]).  bm25f_merge_final_lists merges n_lists such result lists
  * per query (layout [n_lists][n_queries][k], as an all-gather over the shards produces) into the k best by
- * (final value descending, docnum ascending) and counts them.  k <= 128. */
+ * (final value descending, docnum ascending) and counts them.  k <= 256. */
 int  bm25f_plan_device_final(bm25f_plan* plan, double** d_final, uint32_t** d_docids, uint64_t** d_totals);
 int  bm25f_merge_final_lists(bm25f_handle* h, const double* d_vals, const uint32_t* d_docids, int n_lists,
                              uint32_t n_queries, int k, double* d_out_final, uint32_t* d_out_docids,

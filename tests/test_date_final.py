@@ -93,7 +93,7 @@ def test_oracles_agree_on_final(dated, cls):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("cls", [DescDateBM25F, AscDateBM25F])
-@pytest.mark.parametrize("k", [10, 3, 100])
+@pytest.mark.parametrize("k", [10, 3, 100, 150])
 def test_final_on_device(dated, cls, k):
     w = cls()
     o = NumpyOracle(dated, final_add=w.doc_final_terms(dated))
@@ -126,7 +126,7 @@ def test_final_switches_with_the_weighting(dated):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [10, 100])
+@pytest.mark.parametrize("k", [10, 100, 150])
 def test_final_merge_across_shards(dated, k):
     """Document shards under a final() weighting: every shard's (final value, docnum) lists, laid out as an
     all-gather would, merged by bm25f_merge_final_lists, equal the whole corpus (W8 + W14)."""

@@ -161,7 +161,7 @@ def test_limits(cfg1, k):
 
 
 @pytest.mark.parametrize("variant", [0, 3, 5])
-@pytest.mark.parametrize("k", [33, 64, 100, 128])
+@pytest.mark.parametrize("k", [33, 64, 100, 128, 150, 256])
 def test_four_keys_per_lane(cfg1, k, variant):
     """32 < k <= 128 on the stream and candidate-driven kernels (four keys per lane): ORs with thousands
     of matches, ANDs with fewer than k, AND-of-OR groups, many partial lists to merge."""

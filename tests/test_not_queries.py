@@ -115,7 +115,7 @@ def test_not_all_routes(cfg1, variant, kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [1, 32, 100])
+@pytest.mark.parametrize("k", [1, 32, 100, 150])
 def test_not_limits(cfg1, k):
     ix, o = cfg1
     qs = not_queries(100, 50_000, 17)
