@@ -211,8 +211,8 @@ void bm25f_plan_destroy(bm25f_plan* plan);
 int  bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* batch, int k, float* out_scores,
                         uint32_t* out_docids, uint32_t* out_counts, uint64_t* out_totals);
 
-/* Pipelined form of bm25f_search_batch for a stream of batches (a server answering request batches back to
- * back): bm25f_submit plans the batch on the host, uploads it on a copy stream, launches its kernels and the
+/* Pipelined form of bm25f_search_batch (same reference call sites: my_flask.py:208, :211, :304) for a stream of
+ * batches (a server answering request batches back to back): bm25f_submit plans the batch on the host, uploads it on a copy stream, launches its kernels and the
  * device-to-host copy of its results into pinned memory, and returns without waiting; bm25f_collect waits for
  * that batch, copies the results to the caller's buffers (same layout as bm25f_fetch) and frees the plan.
  * Two batches may be in flight (the handle has two workspaces), so the host side of batch i + 1 overlaps the
@@ -228,7 +228,8 @@ int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_
  * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
-/* Final mode across document shards.  bm25f_plan_device_final: the device-resident results of a plan
+/* Final mode (my_whoosh.py:127-154) across document shards (Whoosh segments with doc offsets, W8).
+ * bm25f_plan_device_final: the device-resident results of a plan
  * prepared under a final() step (final values [n_queries * k] float64, global docnums [n_queries * k] with
  * 0xFFFFFFFF in unused slots, totals [n_queries]).  bm25f_merge_final_lists merges n_lists such result lists
  * per query (layout [n_lists][n_queries][k], as an all-gather over the shards produces) into the k best by
