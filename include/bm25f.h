@@ -212,8 +212,8 @@ int  bm25f_search_batch(bm25f_handle* h, const bm25f_query_batch* batch, int k, 
                         uint32_t* out_docids, uint32_t* out_counts, uint64_t* out_totals);
 
 /* Pipelined form of bm25f_search_batch (same reference call sites: my_flask.py:208, :211, :304) for a stream of
- * batches (a server answering request batches back to back): bm25f_submit plans the batch on the host, uploads it on a copy stream, launches its kernels and the
- * device-to-host copy of its results into pinned memory, and returns without waiting; bm25f_collect waits for
+ * batches (a server answering request batches back to back): bm25f_submit plans the batch on the host, uploads
+ * it on a copy stream, launches its kernels and the device-to-host copy of its results into pinned memory, and returns without waiting; bm25f_collect waits for
  * that batch, copies the results to the caller's buffers (same layout as bm25f_fetch) and frees the plan.
  * Two batches may be in flight (the handle has two workspaces), so the host side of batch i + 1 overlaps the
  * GPU side of batch i; a third bm25f_submit before the oldest is collected is refused (BM25F_EINVAL), and
