@@ -11,10 +11,13 @@ all-gather, so total work is fixed (``"scaling": "strong"``).
 
 * ``value``   queries/s with the packed query batch and the plan already resident in HBM;
               timed with CUDA events on the launching stream, max over ranks.
-* ``e2e``     the same metric through the C-ABI entry ``bm25f_search_batch`` (N = 1) /
-              ``ShardedSearcher.search_packed`` (N > 1) with HOST buffers: host planning, H2D of
-              the batch, kernels, (all-gather + merge), D2H of the results, all inside the timed
-              region.
+* ``e2e``     the same metric with HOST buffers: host planning, H2D of the batch, kernels,
+              (all-gather + merge), D2H of the results, every step, all inside the timed region.
+              ``e2e.value`` goes through the pipelined entry (``bm25f_submit`` / ``bm25f_collect``
+              at N = 1, ``ShardedSearcher.search_packed_stream`` at N > 1: two batches in flight,
+              the host side of step i + 1 overlaps the GPU side of step i); ``e2e.serial_value``
+              is one blocking ``bm25f_search_batch`` / ``search_packed`` per step.  Wall clock,
+              max over ranks, median of three repetitions of ``--steps`` steps.
 * ``roofline`` achieved algorithmic posting bytes/s of the scoring kernel (9 B per posting
               touched, SURVEY.md §8 d) from the library's CUDA events around that kernel, over the
               same timed steps, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
@@ -359,44 +362,48 @@ def main():
     d2h = batch.n_queries * (k * 8 + 4 + 8)
     for _ in range(min(2, args.warmup)):
         ss.search_packed(batch, k) if world > 1 else eng.search_batch(batch, k)
-    barrier()
-    eng.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        if world > 1:
-            ss.search_packed(batch, k)
-        else:
-            eng.search_batch(batch, k)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = c["n_queries"] * args.steps / float(t.item())
-    e2e_extra = {"pipeline_depth": 1}
-    if True:
-        # The same steps through the pipelined entry (N = 1: bm25f_submit / bm25f_collect; N > 1:
-        # ShardedSearcher.search_packed_stream), two batches in flight: every step still plans its batch
-        # from the host arrays, uploads it, and reads its results back into host arrays; the host side of
-        # step i + 1 overlaps the GPU side of step i.
-        for _ in ss.search_packed_stream((batch for _ in range(min(2, args.warmup))), k):
-            pass
-        barrier()
-        eng.synchronize()
-        t0 = time.perf_counter()
+
+    def median_of_three(run_steps):
+        """Wall time of ``run_steps()`` (exactly ``--steps`` steps), max over ranks, median of three
+        repetitions: the region is tens of milliseconds of host + GPU work, one host hiccup would
+        otherwise move the figure by 10 %."""
+        times = []
+        for _ in range(3):
+            barrier()
+            eng.synchronize()
+            t0 = time.perf_counter()
+            run_steps()
+            barrier()
+            t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        return sorted(times)[1]
+
+    def serial_steps():
+        for _ in range(args.steps):
+            if world > 1:
+                ss.search_packed(batch, k)
+            else:
+                eng.search_batch(batch, k)
+
+    def pipelined_steps():
         n_out = 0
         for res in ss.search_packed_stream((batch for _ in range(args.steps)), k):
             n_out += res[0].shape[0]
-        barrier()
-        pipe_s = time.perf_counter() - t0
         assert n_out == c["n_queries"] * args.steps
-        t = torch.tensor([pipe_s], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_extra = {"pipeline_depth": 2, "serial_value": e2e_value,
-                     "note": "value: search_packed_stream (N = 1: bm25f_submit / bm25f_collect), the host side of batch "
-                             "i+1 overlaps the GPU side of batch i; serial_value: one blocking search per step"}
-        e2e_value = c["n_queries"] * args.steps / float(t.item())
+
+    serial_value = c["n_queries"] * args.steps / median_of_three(serial_steps)
+    # The same steps through the pipelined entry (N = 1: bm25f_submit / bm25f_collect; N > 1:
+    # ShardedSearcher.search_packed_stream), two batches in flight: every step still plans its batch
+    # from the host arrays, uploads it, and reads its results back into host arrays; the host side of
+    # step i + 1 overlaps the GPU side of step i.
+    for _ in ss.search_packed_stream((batch for _ in range(min(2, args.warmup))), k):
+        pass
+    e2e_value = c["n_queries"] * args.steps / median_of_three(pipelined_steps)
+    e2e_extra = {"pipeline_depth": 2, "serial_value": serial_value, "timing": "median of 3 repetitions of --steps steps",
+                 "note": "value: search_packed_stream (N = 1: bm25f_submit / bm25f_collect), the host side of batch "
+                         "i+1 overlaps the GPU side of batch i; serial_value: one blocking search per step"}
     plan.close()
 
     if rank == 0:
