@@ -58,6 +58,26 @@ def merge_keys_host(gathered: np.ndarray, k: int) -> np.ndarray:
     return np.ascontiguousarray(allk[:, :k])
 
 
+def merge_final_host(vals: np.ndarray, docids: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Host restatement of ``bm25f_merge_final_lists`` for CPU (gloo) tests: ``vals`` / ``docids`` are
+    ``[G, Q, k]`` (float64 final values, uint32 global docnums, 0xFFFFFFFF = empty slot); returns the k best
+    per query by (value descending, docnum ascending) as ``(vals [Q, k], docids [Q, k], counts [Q])``."""
+    G, Q, _ = vals.shape
+    v = np.transpose(vals, (1, 0, 2)).reshape(Q, G * k)
+    d = np.transpose(docids, (1, 0, 2)).reshape(Q, G * k).astype(np.int64)
+    out_v = np.full((Q, k), -np.inf)
+    out_d = np.full((Q, k), 0xFFFFFFFF, dtype=np.uint32)
+    counts = np.zeros(Q, dtype=np.uint32)
+    for q in range(Q):
+        ok = d[q] != 0xFFFFFFFF
+        order = np.lexsort((d[q][ok], -v[q][ok]))[:k]
+        n = order.size
+        out_v[q, :n] = v[q][ok][order]
+        out_d[q, :n] = d[q][ok][order]
+        counts[q] = n
+    return out_v, out_d, counts
+
+
 def decode_keys_host(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     """``(scores f32, docids u32, counts)`` from uint64 keys (host mirror of ``bm25f_decode_keys``)."""
     u = (keys >> np.uint64(32)).astype(np.uint32)

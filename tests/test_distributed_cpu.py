@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from document_search_engine_b200.corpus import make_corpus, make_queries
-from document_search_engine_b200.distributed import decode_keys_host, merge_keys_host
+from document_search_engine_b200.distributed import decode_keys_host, merge_final_host, merge_keys_host
 from document_search_engine_b200.searching import make_keys
 from oracle.numpy_oracle import NumpyOracle
 
@@ -101,3 +101,59 @@ def test_key_roundtrip_and_order():
     assert order.tolist() == [4, 1, 0, 2, 3]          # score desc, docnum asc (W11)
     sc, dc, cnt = decode_keys_host(keys[None, :])
     assert sc[0].tolist() == s.tolist() and dc[0].tolist() == d.tolist() and cnt[0] == 5
+
+
+# ---- the same exchange under a date-ordered weighting: (final value, docnum) lists instead of keys ------------
+
+def _dated(ix):
+    from tests.test_date_final import dated_corpus
+    return dated_corpus(ix, seed=11)
+
+
+def _worker_final(rank, world, port, out):
+    from document_search_engine_b200 import DescDateBM25F
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ix = _dated(make_corpus(4000, 3000, 7, device="cpu"))
+        qs = make_queries(60, 3000, 8, 1, 4, "mixed", skip_top=0).queries
+        shard = ix.shard(rank, world)
+        # what a rank's device produces: its shard's k best by final value, global docnums, local totals
+        o = NumpyOracle(ix, shards=[shard], final_add=DescDateBM25F().doc_final_terms(ix))
+        vals = np.full((len(qs), K), -np.inf)
+        docs = np.full((len(qs), K), 0xFFFFFFFF, dtype=np.uint32)
+        totals = np.zeros(len(qs), dtype=np.int64)
+        for i, q in enumerate(qs):
+            top, totals[i] = o.search(q, limit=K)
+            vals[i, :len(top)] = [t[0] for t in top]
+            docs[i, :len(top)] = [t[1] for t in top]
+        g_vals = torch.empty(world * vals.size, dtype=torch.float64)
+        g_docs = torch.empty(world * docs.size, dtype=torch.int32)
+        dist.all_gather_into_tensor(g_vals, torch.from_numpy(vals.reshape(-1)))
+        dist.all_gather_into_tensor(g_docs, torch.from_numpy(docs.view(np.int32).reshape(-1)))
+        tot = torch.from_numpy(totals.copy())
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        mv, md, mc = merge_final_host(g_vals.numpy().reshape(world, len(qs), K),
+                                      g_docs.numpy().view(np.uint32).reshape(world, len(qs), K), K)
+        if rank == 0:
+            np.savez(out, vals=mv, docids=md, counts=mc, totals=tot.numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_final_exchange_equals_whole(tmp_path):
+    from document_search_engine_b200 import DescDateBM25F
+    out = str(tmp_path / "merged_final.npz")
+    mp.spawn(_worker_final, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    ix = _dated(make_corpus(4000, 3000, 7, device="cpu"))
+    qs = make_queries(60, 3000, 8, 1, 4, "mixed", skip_top=0).queries
+    o = NumpyOracle(ix, final_add=DescDateBM25F().doc_final_terms(ix))
+    for i, q in enumerate(qs):
+        top, total = o.search(q, limit=K)
+        assert int(got["totals"][i]) == total
+        n = int(got["counts"][i])
+        assert n == len(top)
+        assert got["docids"][i, :n].tolist() == [d for _, d in top]
+        assert got["vals"][i, :n].tolist() == [v for v, _ in top]
