@@ -8,11 +8,12 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_K = 1024
 MAX_LEAVES_PER_QUERY = 64
 TERM_UNKNOWN = 0xFFFFFFFF
@@ -50,7 +51,13 @@ class Options(C.Structure):
                 ("subtile_docs", C.c_uint32), ("warp_split", C.c_uint32), ("stream_warps", C.c_uint32),
                 ("prefetch_postings", C.c_uint32), ("cta_warps", C.c_uint32), ("cta_prefetch", C.c_uint32),
                 ("cta_split", C.c_uint32), ("cta_slice_docs", C.c_uint32), ("isect_ratio", C.c_uint32),
-                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("or1_ratio", C.c_uint32), ("hash_split", C.c_uint32)]
+                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("coop_warps", C.c_uint32),
+                ("coop_tile_docs", C.c_uint32), ("coop_chunk", C.c_uint32), ("coop_stages", C.c_uint32),
+                ("coop_split", C.c_uint32), ("serial_streams", C.c_uint32)]
+
+
+#: engine options a caller may pass (``bm25f_options`` field names; 0 = library default)
+OPTION_NAMES = tuple(n for n, _ in Options._fields_)
 
 
 class QueryBatchDesc(C.Structure):
@@ -65,7 +72,7 @@ class Stats(C.Structure):
                 ("tile_docs", C.c_uint32), ("threads", C.c_uint32), ("ctas_per_sm", C.c_uint32),
                 ("packed_payload", C.c_uint32), ("device_bytes", C.c_uint64), ("postings_stream", C.c_uint64),
                 ("postings_team", C.c_uint64), ("postings_cta", C.c_uint64), ("postings_lookup", C.c_uint64),
-                ("postings_hash", C.c_uint64), ("ms_stream", C.c_float), ("reserved", C.c_uint32)]
+                ("postings_tile", C.c_uint64), ("ms_stream", C.c_float), ("ms_tile", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -246,17 +253,19 @@ class Pending:
 class Engine:
     """One uploaded index shard on one GPU."""
 
-    def __init__(self, ix, device: int = 0, tile_docs: int = 0, threads: int = 0, split_postings: int = 0,
-                 variant: int = 0, chunk_postings: int = 0, stages: int = 0, subtile_docs: int = 0,
-                 warp_split: int = 0, stream_warps: int = 0, prefetch_postings: int = 0, cta_warps: int = 0,
-                 cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0, or1_ratio: int = 0, hash_split: int = 0):
+    def __init__(self, ix, device: int = 0, **options):
+        """``options``: ``bm25f_options`` fields by name (``OPTION_NAMES``); anything left out is the library default."""
+        unknown = sorted(set(options) - set(OPTION_NAMES))
+        if unknown:
+            raise TypeError("unknown engine option(s): %s" % ", ".join(unknown))
         self.lib = load_library()
+        #: a handle serves one call at a time (include/bm25f.h); host layers that share an engine take this lock
+        self.lock = threading.RLock()
         self._h = None
         desc = IndexDesc(ABI_VERSION, len(ix.field_names), ix.n_docs_all, ix.n_terms, ix.n_postings, ix.doc_base,
                          _ptr(ix.term_offsets), _ptr(ix.term_field), _ptr(ix.docids), _ptr(ix.tfs),
                          _ptr(ix.len_bytes), _ptr(ix.deleted))
-        opts = Options(tile_docs, threads, split_postings, variant, chunk_postings, stages, subtile_docs,
-                       warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit, or1_ratio, hash_split)
+        opts = Options(**{n: int(v) for n, v in options.items()})
         h = C.c_void_p()
         _check(self.lib, self.lib.bm25f_create(C.byref(desc), device, C.byref(opts), C.byref(h)))
         self._h = h

@@ -11,7 +11,7 @@
 //   k_score_stream    (stream.cuh)        flat ORs: independent warps, accumulators in shared memory
 //   k_score_isect     (isect.cuh)         ANDs: candidate-driven lookups (IntersectionMatcher + skip_to)
 //   k_score_team      (team.cuh)          symmetric ANDs: CTA-built bounds table, private slices
-//   k_score_hash      (hash.cuh)          experimental one-dense OR
+//   k_tile_item_bounds / k_score_tile (tile.cuh)   flat ORs: one CTA per query, TMA-staged posting chunks, tagged slots
 //   k_tile_bounds, k_score_pipe, k_score_topk   general fallback (k > 256, many leaves, paging, odd weights)
 //   k_merge_topk_warp / k_merge_topk      merge of per-item (or per-GPU) top-k lists
 //   k_decode_keys                         keys -> (score, docid, count)
@@ -87,8 +87,6 @@ struct ItemRec {            // 16 B
 };
 
 constexpr uint32_t QF_SIMPLE_OR = 1u;
-constexpr uint32_t QF_STREAM_LAST = 2u;   // one-dense OR: the last leaf is streamed accumulator-free
-constexpr uint32_t QF_TAKEN = 4u;         // ... by k_score_isect: after_key is the word offset of its "taken" bitmap
 constexpr int MAXL = BM25F_MAX_LEAVES_PER_QUERY;
 constexpr int FAST_MAX_K = 256;           // largest k of the warp kernels: 8 keys per lane (the reference's listing page asks for 150)
 
@@ -989,9 +987,9 @@ __device__ __forceinline__ unsigned long long warp_topk_kth(const unsigned long 
 
 #include "final.cuh"
 #include "stream.cuh"
+#include "tile.cuh"
 #include "team.cuh"
 #include "isect.cuh"
-#include "hash.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -1305,11 +1303,14 @@ struct bm25f_handle {
   int ctas_per_sm = 0;
   int tl_ctas_per_sm = 0;
   int is_ctas_per_sm = 0;
-  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000, is_or1_ratio = 0, is_or1_lookup = 1;
-  uint32_t hs_split = 1u << 16;   // hash OR: target work (posting-equivalents) per item
-  int hs_ctas_per_sm = 0;   // candidate-driven AND: cost of a lookup in postings, candidates per item
+  bool serial_streams = false;          // option: never run the second-stream kernels beside the first-stream ones
+  uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000;   // candidate-driven AND: cost of a lookup in postings, candidates per item
+  // cooperative tile kernel (flat ORs): consumer warps per CTA, documents per tile, postings per stage, ring depth,
+  // target work per item
+  uint32_t ct_warps = 16, ct_tile_docs = 9216, ct_chunk = 1024, ct_stages = 3, ct_split = 1u << 22;
+  int ct_ctas_per_sm = 0;
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
-  cudaEvent_t ev[EV_RING][6] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone
+  cudaEvent_t ev[EV_RING][8] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone; [6], [7] the tile kernel (boundary table included)
   int ev_head = 0;                     // next slot to use
   int ev_pending = 0;                  // slots recorded but not yet folded into the stats
   bm25f_stats stats{};
@@ -1340,17 +1341,16 @@ struct bm25f_plan {
   uint32_t n_w4 = 0, n_w8 = 0;            // stream-kernel items / team-kernel items; the rest are CTA items
   ItemRec* d_items_w4 = nullptr;
   ItemRec* d_items_w8 = nullptr;
-  uint32_t n_hs = 0;                      // hash OR items
-  ItemRec* d_items_hs = nullptr;
-  uint32_t n_o1 = 0;                      // one-dense OR (lookups) items
-  ItemRec* d_items_o1 = nullptr;
+  uint32_t n_ct = 0;                      // cooperative tile kernel items
+  ItemRec* d_items_ct = nullptr;
+  uint32_t* d_ct_boff = nullptr;          // [n_ct] first boundary-table entry of each item
+  uint32_t* d_ct_bounds = nullptr;
+  uint64_t n_ct_bounds = 0;
   uint32_t n_is = 0;                      // candidate-driven items
-  unsigned int* d_taken = nullptr;        // one-dense ORs: bitmaps over the dense leaves' postings
-  uint64_t taken_words = 0;
   ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
-  uint64_t postings_cls[6] = {0, 0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, hash, one-dense OR
+  uint64_t postings_cls[5] = {0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, cooperative tiles
   LeafRec* d_leaves = nullptr;
   QueryRec* d_queries = nullptr;
   ItemRec* d_items = nullptr;
@@ -1430,9 +1430,11 @@ int fold_events(bm25f_handle* h, int n) {
     CU(cudaEventElapsedTime(&b, e[1], e[2]));
     CU(cudaEventElapsedTime(&c, e[2], e[3]));
     CU(cudaEventElapsedTime(&d, e[0], e[3]));
-    float f = 0;
+    float f = 0, g = 0;
     CU(cudaEventElapsedTime(&f, e[4], e[5]));
+    CU(cudaEventElapsedTime(&g, e[6], e[7]));
     h->stats.ms_stream += f;
+    h->stats.ms_tile += g;
     h->stats.ms_bounds += a;
     h->stats.ms_score += b;
     h->stats.ms_merge += c;
@@ -1537,11 +1539,26 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   if (opts) {
     if (opts->isect_ratio) h->is_ratio = opts->isect_ratio;
     if (opts->isect_split) h->is_split = opts->isect_split;
-    if (opts->or1_ratio) h->is_or1_ratio = opts->or1_ratio;
-    if (opts->hash_split) h->hs_split = opts->hash_split;
     if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
   }
-  if (h->variant > 7) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams), 5 (candidate-driven), 6 (one-dense OR by lookups) or 7 (one-dense OR by hashing)"); }
+  if (opts) {
+    if (opts->coop_warps) h->ct_warps = opts->coop_warps;
+    if (opts->coop_tile_docs) h->ct_tile_docs = opts->coop_tile_docs;
+    if (opts->coop_chunk) h->ct_chunk = opts->coop_chunk;
+    if (opts->coop_stages) h->ct_stages = opts->coop_stages;
+    if (opts->coop_split) h->ct_split = opts->coop_split;
+    h->serial_streams = opts->serial_streams != 0;
+  }
+  if (h->variant > 6) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams), 5 (candidate-driven) or 6 (cooperative tiles for every eligible flat OR)"); }
+  if (h->ct_warps < 1 || h->ct_warps > (uint32_t)TL_MAX_CWARPS) { delete h; return fail(BM25F_EINVAL, "coop_warps must be 1..%d", TL_MAX_CWARPS); }
+  if (h->ct_tile_docs < 256 || h->ct_tile_docs > 65536 || (h->ct_tile_docs & 1)) { delete h; return fail(BM25F_EINVAL, "coop_tile_docs must be even, in 256..65536"); }
+  if (h->ct_chunk < 32 || (h->ct_chunk & 31) || h->ct_chunk > 8192) { delete h; return fail(BM25F_EINVAL, "coop_chunk must be a multiple of 32 in 32..8192"); }
+  if (h->ct_stages < 2 || h->ct_stages > (uint32_t)TL_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "coop_stages must be 2..%d", TL_MAX_STAGES); }
+  if ((h->variant == 0 || h->variant == 6) && tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps) + 2048 > (size_t)prop.sharedMemPerBlockOptin) {
+    const size_t need = tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps) + 2048;
+    delete h;
+    return fail(BM25F_EINVAL, "coop_tile_docs x coop_chunk x coop_stages needs %zu bytes of shared memory (> %zu)", need, (size_t)prop.sharedMemPerBlockOptin);
+  }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
   if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
@@ -1755,9 +1772,10 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[7] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
-                           (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>,
-                           (const void*)k_score_stream<8, false>, (const void*)k_score_stream<8, true>};
+    const void* wfns[10] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
+                            (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>,
+                            (const void*)k_score_stream<8, false>, (const void*)k_score_stream<8, true>,
+                            (const void*)k_score_tile<1>, (const void*)k_score_tile<4>, (const void*)k_score_tile<8>};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1830,7 +1848,8 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_scores);
   cudaFree(p->d_docids);
   cudaFree(p->d_counts);
-  cudaFree(p->d_taken);
+  cudaFree(p->d_ct_boff);
+  cudaFree(p->d_ct_bounds);
   cudaFree(p->d_part_lo);
   cudaFree(p->d_final);
   delete p;
@@ -1933,7 +1952,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
   // A small batch (a single interactive query is the reference's use) would be a handful of items on
   // a handful of warps: cut its items finer so that the whole GPU works on it.
-  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
+  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split, ct_split = h->ct_split;
   if (Q <= 1024) {
     uint64_t total = 0;
     for (uint32_t i = 0; i < NL; ++i) {
@@ -1941,6 +1960,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
     const uint64_t per_item = std::max<uint64_t>(4096, total / ((uint64_t)h->n_sms * 32));   // ~2 items per stream-kernel warp
+    ct_split = (uint32_t)std::min<uint64_t>(ct_split, std::max<uint64_t>(32768, total / ((uint64_t)h->n_sms * 2)));   // ~2 items per SM
     if (per_item < wsplit) {
       is_split = (uint32_t)std::max<uint64_t>(128, (uint64_t)is_split * per_item / wsplit);
       tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
@@ -1951,9 +1971,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   // into its own item lists and counters), then stitched together.  A query's leaf records live at
   // the positions of its input leaves, so no thread needs another's running totals.
   struct PlanLocal {
-    std::vector<ItemRec> items[6];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: hash OR; 5: one-dense OR by lookups
-    std::vector<uint64_t> item_w[6];
-    uint64_t postings = 0, taken_words = 0, cls_postings[6] = {0, 0, 0, 0, 0, 0};
+    std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: cooperative tiles
+    std::vector<uint64_t> item_w[5];
+    uint64_t postings = 0, cls_postings[5] = {0, 0, 0, 0, 0};
     uint32_t n_parts = 0;
     bool any_nonpos = false;
     int rc = 0;
@@ -2061,7 +2081,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     qr.n_groups = G;
     qr.flags = (G == 1 && all_pos && n_neg == 0) ? QF_SIMPLE_OR : 0u;
     if (!all_pos) L.any_nonpos = true;
-    const uint32_t out_leaf = a + nlq;   // one past the query's last leaf record
     L.postings += P;
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
@@ -2077,53 +2096,34 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     const bool isect_ok = k <= FAST_MAX_K && nlq <= 32 && all_pos && qr.after_key == 0ull;
     if (final_mode && !isect_ok && !stream_ok)
       PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 256, at most 32 leaves, positive weights and no paging bound", qi);
-    // One-dense OR: a flat OR whose densest leaf outweighs all the others together by or1_ratio is
-    // scored by k_score_isect with that leaf streamed accumulator-free (QF_STREAM_LAST).
-    uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
-    bool use_or1 = false;
-    bool use_hash = false;
-    if (!final_mode && (qr.flags & QF_SIMPLE_OR) && isect_ok && k <= 32 && (h->variant == 0 || h->variant == 6 || h->variant == 7)) {
-      uint32_t imax = 0;
-      for (uint32_t i = 1; i < nlq; ++i)
-        if (leaves[out_leaf - nlq + i].df > leaves[out_leaf - nlq + imax].df) imax = i;
-      const uint64_t dmax = leaves[out_leaf - nlq + imax].df;
-      const uint64_t rest = P - dmax;
-      if (h->variant == 6 || h->variant == 7 || (h->is_or1_ratio && rest * h->is_or1_ratio < P)) {
-        std::swap(leaves[out_leaf - nlq + imax], leaves[out_leaf - 1]);     // the dense leaf goes last
-        qr.flags |= QF_STREAM_LAST;
-        if (h->variant == 6 || (h->variant == 0 && h->is_or1_lookup)) {
-          // lookups + "taken" bitmap (k_score_isect)
-          use_or1 = true;
-          qr.flags |= QF_TAKEN;
-          qr.after_key = L.taken_words;               // word offset of this query's bitmap
-          L.taken_words += (dmax + 31) / 32 + 1;
-          n_cand = rest * (uint64_t)(nlq > 1 ? nlq - 1 : 1) + dmax / 16;   // work, in candidate lookups
-        } else {
-          // per-warp hash table for the other leaves' documents (k_score_hash)
-          use_hash = true;
-          n_cand = rest * 4 + dmax / 2;             // work, in posting-equivalents
-        }
-      }
-    }
+    const uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
     // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
-    const bool use_isect = use_or1 || (!use_hash && isect_ok && ((final_mode && !stream_ok) || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
-        ((qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) < (uint64_t)h->is_or_limit
-                                   : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P))));
-    const bool use_team = !use_isect && !use_hash && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
-    const int cls = use_hash ? 4 : use_or1 ? 5 : use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
+    const bool use_isect = isect_ok && ((final_mode && !stream_ok) || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
+        ((qr.flags & QF_SIMPLE_OR) ? n_cand < (uint64_t)h->is_or_limit
+                                   : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
+    // every other flat OR: one CTA per (query, range of tiles), k_score_tile
+    const bool use_tile = !use_isect && !final_mode && (h->variant == 0 || h->variant == 6) && (qr.flags & QF_SIMPLE_OR) && k <= FAST_MAX_K &&
+                          nlq <= (uint32_t)TL_MAX_LEAVES && qr.after_key == 0ull;
+    const bool use_team = !use_isect && !use_tile && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const int cls = use_isect ? 3 : use_tile ? 4 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
-    if (use_hash) {
-      nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 4096), std::max<uint64_t>(1, (n_cand + h->hs_split / 2) / h->hs_split));
+    if (use_tile) {
+      // an item is a run of whole tiles; its boundary table (tiles + 1 rows of nlq entries) must fit TL_BCAP
+      const uint64_t Tt = h->ct_tile_docs;
+      const uint64_t ntiles = std::max<uint64_t>(1, (h->n_docs + Tt - 1) / Tt);
+      const uint64_t nt_cap = (uint64_t)TL_BCAP / nlq - 1;
+      const uint64_t work = P + ntiles * (32ull * nlq + 64ull);      // posting-equivalents: every (tile, leaf) phase has a fixed cost
+      nsplit = (uint32_t)std::min<uint64_t>(ntiles, std::max<uint64_t>((ntiles + nt_cap - 1) / nt_cap, (work + ct_split / 2) / ct_split));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
         ItemRec it;
         it.q = qi;
-        it.tile_begin = (uint32_t)(h->n_docs * s / nsplit);          // document range [lo, hi)
-        it.tile_end = (uint32_t)(h->n_docs * (s + 1) / nsplit);
+        it.tile_begin = (uint32_t)((ntiles * s / nsplit) * Tt);                    // document range [lo, hi), tile-aligned
+        it.tile_end = (uint32_t)std::min<uint64_t>(h->n_docs, (ntiles * (s + 1) / nsplit) * Tt);
         it.part = L.n_parts + s;
         L.items[cls].push_back(it);
-        L.item_w[cls].push_back(n_cand / nsplit + 64);
+        L.item_w[cls].push_back(work / nsplit);
       }
     } else if (use_isect) {
       nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + is_split) / (2ull * is_split)));
@@ -2207,29 +2207,25 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   for (auto& L : locals)
     if (L.rc) return fail(L.rc, "%s", L.err);
   // stitch: partial-list indices and bitmap offsets become global
-  std::vector<ItemRec> items[6];
-  std::vector<uint64_t> item_w[6];
-  uint64_t postings = 0, taken_words = 0, cls_postings[6] = {0, 0, 0, 0, 0, 0};
+  std::vector<ItemRec> items[5];
+  std::vector<uint64_t> item_w[5];
+  uint64_t postings = 0, cls_postings[5] = {0, 0, 0, 0, 0};
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   for (unsigned t = 0; t < n_thr; ++t) {
     PlanLocal& L = locals[t];
-    if (t > 0 && (n_parts || taken_words)) {
+    if (t > 0 && n_parts) {
       const uint32_t q0 = (uint32_t)((uint64_t)Q * t / n_thr), q1 = (uint32_t)((uint64_t)Q * (t + 1) / n_thr);
-      for (uint32_t qi = q0; qi < q1; ++qi) {
-        queries[qi].part_begin += n_parts;
-        if (queries[qi].flags & QF_TAKEN) queries[qi].after_key += taken_words;
-      }
-      for (int c = 0; c < 6; ++c)
+      for (uint32_t qi = q0; qi < q1; ++qi) queries[qi].part_begin += n_parts;
+      for (int c = 0; c < 5; ++c)
         for (auto& it : L.items[c]) it.part += n_parts;
     }
-    for (int c = 0; c < 6; ++c) {
+    for (int c = 0; c < 5; ++c) {
       items[c].insert(items[c].end(), L.items[c].begin(), L.items[c].end());
       item_w[c].insert(item_w[c].end(), L.item_w[c].begin(), L.item_w[c].end());
       cls_postings[c] += L.cls_postings[c];
     }
     postings += L.postings;
-    taken_words += L.taken_words;
     n_parts += L.n_parts;
     any_nonpos = any_nonpos || L.any_nonpos;
   }
@@ -2250,13 +2246,11 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_w4 = (uint32_t)items[0].size();
   p->n_w8 = (uint32_t)items[1].size();
   p->n_is = (uint32_t)items[3].size();
-  p->n_hs = (uint32_t)items[4].size();
-  p->n_o1 = (uint32_t)items[5].size();
-  p->taken_words = taken_words;
+  p->n_ct = (uint32_t)items[4].size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
-  for (int c = 0; c < 6; ++c) p->postings_cls[c] = cls_postings[c];
+  for (int c = 0; c < 5; ++c) p->postings_cls[c] = cls_postings[c];
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
   p->arena = use_arena ? slot : -1;
@@ -2277,12 +2271,13 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }                                                                   \
   } while (0)
   const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
-  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs + p->n_o1;
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_ct;
+  const size_t boff_bytes = align_up((size_t)p->n_ct * 4);
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
   if (use_arena) {
     // the sorted item records follow the leaf / query records in the pinned arena
-    const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec));
+    const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec)) + boff_bytes;
     if (need > A.h_cap) {
       unsigned char* bigger = nullptr;
       const size_t cap = align_up(need * 2, 1u << 20);
@@ -2300,22 +2295,41 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     own_items.resize(n_it);
     h_items = own_items.data();
   }
+  std::vector<uint32_t> own_boff;
+  uint32_t* h_boff;
+  if (use_arena) {
+    h_boff = reinterpret_cast<uint32_t*>(A.h + hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec)));
+  } else {
+    own_boff.resize(p->n_ct);
+    h_boff = own_boff.data();
+  }
   // layout of the item array: [CTA items][warp streams][warp teams][candidate-driven AND]
   order_items(items[2], item_w[2], h_items);
   order_items(items[0], item_w[0], h_items + p->n_items);
   order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
   order_items(items[3], item_w[3], h_items + p->n_items + p->n_w4 + p->n_w8);
   order_items(items[4], item_w[4], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is);
-  order_items(items[5], item_w[5], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs);
+  {
+    // boundary tables of the tile items, in launch order
+    const ItemRec* ct = h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is;
+    uint64_t nb = 0;
+    for (uint32_t i = 0; i < p->n_ct; ++i) {
+      const uint64_t nt = ((uint64_t)ct[i].tile_end - ct[i].tile_begin + h->ct_tile_docs - 1) / h->ct_tile_docs;
+      h_boff[i] = (uint32_t)nb;
+      nb += (nt + 1) * queries[ct[i].q].n_leaves;
+    }
+    if (nb > 0xFFFFFFF0ull) { delete p; return fail(BM25F_EINVAL, "batch too large: %llu tile-boundary entries (split the batch)", (unsigned long long)nb); }
+    p->n_ct_bounds = nb;
+  }
 
   if (use_arena) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
     const size_t o_leaves = take((size_t)out_leaf * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
-                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 5) * 8),
+                 o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 8) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
-                 o_taken = take((size_t)(taken_words + 1) * 4),
+                 o_ctboff = take((size_t)p->n_ct * 4), o_ctbounds = take((size_t)p->n_ct_bounds * 4),
                  o_plo = take(final_mode ? (size_t)n_parts * k * 4 : 0), o_fin = take(final_mode ? (size_t)Q * k * 8 : 0);
     if (off > A.d_cap) {
       CUP(cudaStreamSynchronize(h->stream));
@@ -2339,7 +2353,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     p->d_scores = reinterpret_cast<float*>(d + o_sc);
     p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
     p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
-    p->d_taken = reinterpret_cast<unsigned int*>(d + o_taken);
+    p->d_ct_boff = reinterpret_cast<uint32_t*>(d + o_ctboff);
+    p->d_ct_bounds = reinterpret_cast<uint32_t*>(d + o_ctbounds);
     if (final_mode) {
       p->d_part_lo = reinterpret_cast<unsigned int*>(d + o_plo);
       p->d_final = reinterpret_cast<double*>(d + o_fin);
@@ -2351,11 +2366,12 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
     RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, (size_t)Q + 5));
+    RCP(dev_alloc(&p->d_totals, (size_t)Q + 8));
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
-    RCP(dev_alloc(&p->d_taken, (size_t)taken_words + 1));
+    RCP(dev_alloc(&p->d_ct_boff, p->n_ct));
+    RCP(dev_alloc(&p->d_ct_bounds, p->n_ct_bounds));
     if (final_mode) {
       RCP(dev_alloc(&p->d_part_lo, (size_t)n_parts * k + 1));
       RCP(dev_alloc(&p->d_final, (size_t)Q * k + 1));
@@ -2364,8 +2380,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->d_items_w4 = p->d_items + p->n_items;
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
   p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
-  p->d_items_hs = p->d_items_is + p->n_is;
-  p->d_items_o1 = p->d_items_hs + p->n_hs;
+  p->d_items_ct = p->d_items_is + p->n_is;
   auto t_c = now();
   // Arena plans upload on the copy stream (bm25f_execute waits for ev_ready): the records of the next batch
   // travel while the current one is still being scored.  Nothing else touches this arena: its previous
@@ -2374,6 +2389,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, up));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, up));
   if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, up));
+  if (p->n_ct) CUP(cudaMemcpyAsync(p->d_ct_boff, h_boff, (size_t)p->n_ct * 4, cudaMemcpyHostToDevice, up));
   if (use_arena) CUP(cudaEventRecord(A.ev_ready, up));
   // pageable sources must outlive the copy; a pinned arena is only rewritten two batches later
   if (!use_arena) CUP(cudaStreamSynchronize(h->stream));
@@ -2412,8 +2428,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   cudaEvent_t* ev = h->ev[h->ev_head];
   if (p->arena >= 0) CU(cudaStreamWaitEvent(st, h->arenas[p->arena].ev_ready, 0));
   CU(cudaEventRecord(ev[0], st));
-  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 5) * 8, st));   // totals + the five work counters
-  if (p->taken_words) CU(cudaMemsetAsync(p->d_taken, 0, (size_t)p->taken_words * 4, st));
+  CU(cudaMemsetAsync(p->d_totals, 0, ((size_t)p->Q + 8) * 8, st));   // totals + the work counters
   const unsigned long long nb = p->n_items ? (unsigned long long)p->n_leaves * (p->T + 1) : 0ull;
   if (nb) {
     k_tile_bounds<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(p->d_leaves, p->n_leaves, p->T, h->S, h->d_docids, p->d_bounds);
@@ -2421,7 +2436,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_hs || p->n_o1) {
+  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_ct) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -2443,34 +2458,47 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.prof = h->d_prof;
     // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
     // registers) fit on an SM together and stall on different things: launch them side by side.
-    const bool side = (p->n_w4 || p->n_hs) && (p->n_is || p->n_w8 || p->n_o1);
+    const bool side = (p->n_w4 || p->n_ct) && (p->n_is || p->n_w8) && !h->serial_streams;
     cudaStream_t ax = side ? h->aux_stream : st;
     if (side) {
       CU(cudaEventRecord(h->ev_fork, st));
       CU(cudaStreamWaitEvent(ax, h->ev_fork, 0));
     }
-    if (p->n_hs) {
-      HashParams hp;
-      hp.pairs = h->d_pairs;
-      hp.leaves = p->d_leaves;
-      hp.queries = p->d_queries;
-      hp.items = p->d_items_hs;
-      hp.part_keys = p->d_part_keys;
-      hp.totals = p->d_totals;
-      hp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 3);
-      hp.n_items = p->n_hs;
-      hp.doc_base = (uint32_t)h->doc_base;
-      hp.n_docs = (uint32_t)h->n_docs;
-      hp.k = p->k;
-      if (h->hs_ctas_per_sm == 0) {
+    if (p->n_ct) {
+      TileParams tp;
+      tp.pairs = h->d_pairs;
+      tp.leaves = p->d_leaves;
+      tp.queries = p->d_queries;
+      tp.items = p->d_items_ct;
+      tp.item_boff = p->d_ct_boff;
+      tp.bounds = p->d_ct_bounds;
+      tp.part_keys = p->d_part_keys;
+      tp.totals = p->d_totals;
+      tp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 5);
+      tp.n_items = p->n_ct;
+      tp.tile_docs = h->ct_tile_docs;
+      tp.chunk = h->ct_chunk;
+      tp.stages = h->ct_stages;
+      tp.doc_base = (uint32_t)h->doc_base;
+      tp.k = p->k;
+      const unsigned threads = (h->ct_warps + 1u) * 32u;
+      const size_t smem = tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps);
+      if (h->ct_ctas_per_sm == 0) {
         int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_hash, HS_WARPS * 32, 0));
-        h->hs_ctas_per_sm = std::max(1, nb_);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_tile<1>, (int)threads, smem));
+        if (nb_ < 1) return fail(BM25F_EINVAL, "k_score_tile does not fit an SM with %u threads and %zu bytes of shared memory", threads, smem);
+        h->ct_ctas_per_sm = nb_;
       }
-      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->hs_ctas_per_sm), (p->n_hs + HS_WARPS - 1) / HS_WARPS);
-      k_score_hash<<<grid, HS_WARPS * 32, 0, st>>>(hp);
+      CU(cudaEventRecord(ev[6], st));
+      k_tile_item_bounds<<<(p->n_ct + 3) / 4, 128, 0, st>>>(tp);
       CU(cudaGetLastError());
-      ++launches;
+      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->ct_ctas_per_sm), p->n_ct);
+      if (p->k <= 32) k_score_tile<1><<<grid, threads, smem, st>>>(tp);
+      else if (p->k <= 128) k_score_tile<4><<<grid, threads, smem, st>>>(tp);
+      else k_score_tile<8><<<grid, threads, smem, st>>>(tp);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(ev[7], st));
+      launches += 2;
     }
     if (p->n_w4) {
       StreamParams stp;
@@ -2503,33 +2531,6 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       CU(cudaGetLastError());
       ++launches;
     }
-    if (p->n_o1) {
-      // one-dense ORs (experimental, or1_ratio): same kernel as the candidate-driven ANDs, on the second stream
-      IsectParams ip;
-      ip.pairs = h->d_pairs;
-      ip.leaves = p->d_leaves;
-      ip.queries = p->d_queries;
-      ip.items = p->d_items_o1;
-      ip.part_keys = p->d_part_keys;
-      ip.totals = p->d_totals;
-      ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 4);
-      ip.taken = p->d_taken;
-      ip.n_items = p->n_o1;
-      ip.doc_base = (uint32_t)h->doc_base;
-      ip.k = p->k;
-      ip.final_add = nullptr;
-      ip.part_lo = nullptr;
-      if (h->is_ctas_per_sm == 0) {
-        int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1, false>, IS_WARPS * 32, 0));
-        h->is_ctas_per_sm = std::max(1, nb_);
-      }
-      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_o1 + IS_WARPS - 1) / IS_WARPS);
-      if (p->k <= 32) k_score_isect<1, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);
-      else k_score_isect<4, false><<<grid, IS_WARPS * 32, 0, ax>>>(ip);      // one-dense ORs are planned for k <= 32 only
-      CU(cudaGetLastError());
-      ++launches;
-    }
     if (p->n_is) {
       IsectParams ip;
       ip.pairs = h->d_pairs;
@@ -2539,7 +2540,6 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.part_keys = p->d_part_keys;
       ip.totals = p->d_totals;
       ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 2);
-      ip.taken = p->d_taken;
       ip.n_items = p->n_is;
       ip.doc_base = (uint32_t)h->doc_base;
       ip.k = p->k;
@@ -2612,6 +2612,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     }
   }
   if (!p->n_w4) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventRecord(ev[5], st)); }
+  if (!p->n_ct) { CU(cudaEventRecord(ev[6], st)); CU(cudaEventRecord(ev[7], st)); }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q && p->final_mode) {
     if (p->k <= 128) k_merge_final<4><<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
@@ -2655,12 +2656,14 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->stats.postings_team = p->postings_cls[1];
   h->stats.postings_cta = p->postings_cls[2];
   h->stats.postings_lookup = p->postings_cls[3];
-  h->stats.postings_hash = p->postings_cls[4] + p->postings_cls[5];
-  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_hs + p->n_o1;
+  h->stats.postings_tile = p->postings_cls[4];
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_ct;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
-    if (p->n_w8 && !p->n_w4) {
+    if (p->n_ct) {
+      nb_ = h->ct_ctas_per_sm;
+    } else if (p->n_w8 && !p->n_w4) {
       nb_ = h->tl_ctas_per_sm;
     } else if (p->n_w4) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream<1, false>, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
@@ -2893,7 +2896,7 @@ int bm25f_reset_stats(bm25f_handle* h) {
     cudaMemset(h->d_prof, 0, sizeof v);
   }
 #endif
-  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = h->stats.ms_stream = 0.0f;
+  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = h->stats.ms_stream = h->stats.ms_tile = 0.0f;
   h->stats.n_executes = 0;
   return 0;
 }

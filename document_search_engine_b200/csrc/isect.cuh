@@ -16,14 +16,6 @@
 //  * a candidate that collected every group is a match: counted, and offered to the warp's top-k
 //    (KR 64-bit keys per lane, k <= 32 * KR) if its score reaches the current k-th best.
 //
-// One-dense OR (QF_STREAM_LAST): a flat OR whose last leaf D is far denser than all the others
-// together.  Documents that occur only in D need no accumulator - their score is w * impact - so the
-// other leaves' postings are the candidates (looked up in each other and in D, the D postings found
-// are marked in a per-query "taken" bitmap over D's posting indices) and D is then streamed once,
-// rows of 128 postings, straight from global memory through registers: multiply, compare with the
-// k-th best score, skip the taken ones.  Every posting is still read exactly once; matches =
-// |union of candidates| + |D| - |taken|.
-//
 // Results are identical to the streaming kernels: same impacts, same FMA chain per document (own
 // leaf first, then the other leaves in leaf order), same keys.
 #pragma once
@@ -36,8 +28,6 @@ struct IsectParams {
   unsigned long long* part_keys;   // [n_parts * k]
   unsigned long long* totals;      // [Q]
   unsigned int* queue;             // work counter, zeroed before the launch
-  unsigned int* taken;             // one-dense OR: bitmaps over the dense leaf's postings (zeroed before the launch);
-                                   // a query's bitmap starts at word QueryRec::after_key
   uint32_t n_items;
   uint32_t doc_base;
   int k;
@@ -63,8 +53,6 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
     const QueryRec q = ip.queries[item.q];
     const int L = (int)q.n_leaves;
     const uint32_t full = (q.n_groups >= 32u) ? 0xFFFFFFFFu : ((1u << q.n_groups) - 1u);
-    const bool stream_last = (q.flags & QF_STREAM_LAST) != 0;      // leaf L-1 is looked up, then streamed
-    unsigned int* __restrict__ taken = ip.taken + (stream_last ? q.after_key : 0ull);
     const uint32_t d_lo = item.tile_begin, d_hi = item.tile_end;
 
     // lane l keeps leaf l: list origin, length, cursor (first posting not yet passed), weight, group
@@ -84,9 +72,8 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
         if (lane == l) s_start = st;
       }
     }
-    // candidate leaves: the leaves of the smallest group (rank 0; leaves of NOT clauses precede them); all but
-    // the dense one for a one-dense OR
-    const unsigned cand_mask = __ballot_sync(0xFFFFFFFFu, stream_last ? (lane < L - 1) : (s_grp == 0u));
+    // candidate leaves: the leaves of the smallest group (rank 0; leaves of NOT clauses precede them)
+    const unsigned cand_mask = __ballot_sync(0xFFFFFFFFu, s_grp == 0u);
 
     unsigned long long top[KR];               // lane i, row j: the (32 j + i)-th best key of this item so far
 #pragma unroll
@@ -162,7 +149,6 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
               score = fmaf(wl, __uint_as_float(h.y), score);
               sat |= 1u << g;                      // a leaf of a NOT clause sets bit NEG_GROUP, which `full` never has
               if (g == 0u && l < c) dead = true;   // already a candidate of an earlier leaf of the group
-              if (stream_last && l == L - 1 && !dead) atomicOr(taken + (lo >> 5), 1u << (lo & 31u));
             }
           }
           __syncwarp();
@@ -204,72 +190,6 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
         }
         if (thr_key != 0ull) thr = key_score(thr_key);
         }
-      }
-    }
-
-    if (!FINAL && stream_last) {
-      // ---- the dense leaf: no accumulators, no lookups --------------------------------------------
-      __threadfence();                                  // the bitmap words written above, read below by other lanes
-      const int dl = L - 1;
-      const uint2* __restrict__ dp = store + __shfl_sync(0xFFFFFFFFu, s_off, dl);
-      const uint32_t d_df = __shfl_sync(0xFFFFFFFFu, s_df, dl);
-      const float d_w = __shfl_sync(0xFFFFFFFFu, s_w, dl);
-      uint32_t i0 = __shfl_sync(0xFFFFFFFFu, s_start, dl) & ~31u;    // bitmap words are aligned to 32 postings
-      const uint32_t first = __shfl_sync(0xFFFFFFFFu, s_start, dl);
-      bool more = i0 < d_df;
-      if (more) {                                                   // the first 4 KB of the range
-        const uint32_t c0 = i0 + (uint32_t)lane * 16u;
-        if (c0 < d_df) prefetch_l2(dp + c0);
-      }
-      while (more) {
-        if ((i0 & 511u) < 128u) {
-          // one 128-byte line per lane: the 4 KB chunk 2048 postings ahead (the loads below then hit L2)
-          const uint32_t c0 = (i0 & ~511u) + 2048u + (uint32_t)lane * 16u;
-          if (c0 < d_df) prefetch_l2(dp + c0);
-        }
-        uint2 r[4];
-        uint32_t tk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t i = i0 + 32u * e + (uint32_t)lane;
-          r[e] = make_uint2(0xFFFFFFFFu, 0u);
-          tk[e] = 0u;
-          if (i0 + 32u * e < d_df) tk[e] = __ldcg(taken + ((i0 >> 5) + e));
-          if (i < d_df) r[e] = ldg_pair(dp + i);
-        }
-        bool hot[4];
-        bool any_hot = false;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const uint32_t i = i0 + 32u * e + (uint32_t)lane;
-          const bool valid = (i >= first) && (r[e].x < d_hi);       // past the end: docid 0xFFFFFFFF
-          const bool fresh = valid && !((tk[e] >> lane) & 1u);      // not already counted as a candidate
-          tot += fresh ? 1u : 0u;
-          hot[e] = fresh && (d_w * __uint_as_float(r[e].y) >= thr);
-          any_hot = any_hot || hot[e];
-        }
-        if (__any_sync(0xFFFFFFFFu, any_hot)) {                     // rare once k hits exist
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            unsigned long long key = 0ull;
-            if (hot[e]) key = make_key(d_w * __uint_as_float(r[e].y), ip.doc_base + r[e].x);
-            unsigned pm = __ballot_sync(0xFFFFFFFFu, key > thr_key);
-            while (pm) {
-              const int src = __ffs(pm) - 1;
-              pm &= pm - 1u;
-              const unsigned long long bk = __shfl_sync(0xFFFFFFFFu, key, src);
-              if (bk > thr_key) {
-                warp_topk_insert_rows<KR>(top, bk, lane);
-                thr_key = warp_topk_kth<KR>(top, ip.k);
-              }
-            }
-          }
-          if (thr_key != 0ull) thr = key_score(thr_key);
-        }
-        // docids ascend: done when the last posting loaded is past the range (or the list ended)
-        const uint32_t dl_last = __shfl_sync(0xFFFFFFFFu, r[3].x, 31);
-        i0 += 128u;
-        more = (dl_last < d_hi) && (i0 < d_df);
       }
     }
 

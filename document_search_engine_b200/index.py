@@ -22,6 +22,8 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
+import threading
+
 import numpy as np
 
 from .numeric import lengths_to_bytes
@@ -116,6 +118,7 @@ class FlatIndex:
         self.term_weight_total = term_weight_total
         self.schema = Schema(self.field_names, stored=self._stored_names())
         self._engine_cache = {}
+        self._engine_cache_lock = threading.Lock()
 
     # ---- Whoosh Index surface -------------------------------------------------
     def doc_count_all(self) -> int:

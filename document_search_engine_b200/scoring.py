@@ -65,8 +65,12 @@ class BM25F(WeightingModel):
             out[f] = norm_table(self.field_B(name), self.K1, ix.avg_field_length(name)).astype(np.float32)
         return out
 
+    def norm_key(self):
+        """What the per-posting impacts depend on (not the class: ``DescDateBM25F`` has ``BM25F``'s norms)."""
+        return (self.B, self.K1, tuple(sorted(self._field_B.items())))
+
     def key(self):
-        return ("BM25F", self.B, self.K1, tuple(sorted(self._field_B.items())))
+        return ("BM25F",) + self.norm_key()
 
 
 class DateBM25F(BM25F):

@@ -190,47 +190,47 @@ class ResultsPage:
 class Searcher:
     """Whoosh-shaped searcher over a ``FlatIndex`` whose postings live in HBM."""
 
-    def __init__(self, ix, weighting=None, device: int = 0, tile_docs: int = 0, threads: int = 0,
-                 split_postings: int = 0, stats_ix=None, variant: int = 0, chunk_postings: int = 0,
-                 stages: int = 0, subtile_docs: int = 0, warp_split: int = 0, stream_warps: int = 0,
-                 prefetch_postings: int = 0, cta_warps: int = 0, cta_prefetch: int = 0, cta_split: int = 0, cta_slice_docs: int = 0, isect_ratio: int = 0, isect_split: int = 0, isect_or_limit: int = 0, or1_ratio: int = 0, hash_split: int = 0):
+    def __init__(self, ix, weighting=None, device: int = 0, stats_ix=None, **engine_options):
+        """``engine_options``: ``bm25f_options`` fields by name (``_ffi.OPTION_NAMES``), e.g. ``variant=3``."""
         self.ix = ix
         #: index the corpus statistics come from (the whole corpus when ``ix`` is a shard, W8)
         self.stats_ix = stats_ix or ix
         self.weighting = instantiate(weighting)
         if not isinstance(self.weighting, BM25F):
             raise NotImplementedError("only BM25F weightings run on the GPU path")
+        if self.weighting.use_final and not hasattr(self.weighting, "doc_final_terms"):
+            raise NotImplementedError(
+                "a weighting with use_final=True must provide doc_final_terms(ix) (see scoring.DateBM25F): "
+                "final() is applied to every match before the top-k (W14), which only the device can do")
         self.device = device
         self.ixreader = self.stats_ix.reader()
-        key = (device, tile_docs, threads, split_postings, variant, chunk_postings, stages, subtile_docs,
-               warp_split, stream_warps, prefetch_postings, cta_warps, cta_prefetch, cta_split, cta_slice_docs, isect_ratio, isect_split, isect_or_limit, or1_ratio, hash_split)
-        eng = ix._engine_cache.get(key)
-        if eng is None:
-            eng = _ffi.Engine(ix, device=device, tile_docs=tile_docs, threads=threads,
-                              split_postings=split_postings, variant=variant,
-                              chunk_postings=chunk_postings, stages=stages, subtile_docs=subtile_docs,
-                              warp_split=warp_split, stream_warps=stream_warps,
-                              prefetch_postings=prefetch_postings, cta_warps=cta_warps,
-                              cta_prefetch=cta_prefetch, cta_split=cta_split, cta_slice_docs=cta_slice_docs, isect_ratio=isect_ratio,
-                              isect_split=isect_split, isect_or_limit=isect_or_limit, or1_ratio=or1_ratio, hash_split=hash_split)
-            ix._engine_cache[key] = eng
+        engine_options = {n: int(v) for n, v in engine_options.items() if v}
+        key = (device,) + tuple(sorted(engine_options.items()))
+        with ix._engine_cache_lock:
+            eng = ix._engine_cache.get(key)
+            if eng is None:
+                eng = _ffi.Engine(ix, device=device, **engine_options)
+                ix._engine_cache[key] = eng
         self.engine = eng
-        wkey = self.weighting.key() + (self.stats_ix.doc_count_all(),)
-        if eng._weighting_key != wkey:
-            eng.set_weighting(self.weighting.norm_tables(self.stats_ix), key=wkey)
-        # a final() step (DateBM25F: my_whoosh.py:127-154) runs on the device, over every match (W14)
-        fkey = None
-        if self.weighting.use_final:
-            if not hasattr(self.weighting, "doc_final_terms"):
-                raise NotImplementedError(
-                    "a weighting with use_final=True must provide doc_final_terms(ix) (see scoring.DateBM25F): "
-                    "final() is applied to every match before the top-k (W14), which only the device can do")
-            fkey = self.weighting.key()
-        if eng._final_key != fkey:
-            eng.set_final_date(None if fkey is None else self.weighting.doc_final_terms(ix))
-            eng._final_key = fkey
+        # The engine (the uploaded index) is shared by every searcher of this index, but its weighting (impact
+        # pairs) and final() table are handle state: every search call re-binds them under the engine's lock
+        # (the reference opens a searcher per request with the weighting of the requested hit order, my_flask.py:183-184).
+        self._wkey = self.weighting.norm_key() + (self.stats_ix.doc_count_all(),)
+        self._fkey = self.weighting.key() if self.weighting.use_final else None
+        with eng.lock:
+            self._bind()
         self._idf_cache = {}
         self.closed = False
+
+    def _bind(self):
+        """Make the shared engine score with this searcher's weighting (call with ``engine.lock`` held)."""
+        eng = self.engine
+        if eng._weighting_key != self._wkey:
+            eng.set_weighting(self.weighting.norm_tables(self.stats_ix), key=self._wkey)
+        if eng._final_key != self._fkey:
+            # a final() step (DateBM25F: my_whoosh.py:127-154) runs on the device, over every match (W14)
+            eng.set_final_date(None if self._fkey is None else self.weighting.doc_final_terms(self.ix))
+            eng._final_key = self._fkey
 
     # -- context manager / lifetime (my_flask.py:184) ---------------------------
     def __enter__(self):
@@ -336,11 +336,13 @@ class Searcher:
         values instead of scores under a final() weighting)."""
         if limit < 1 or limit > _ffi.MAX_K:
             raise ValueError("limit must be 1..%d for search_packed" % _ffi.MAX_K)
-        if self.weighting.use_final:
-            if limit > FINAL_MAX_K:
-                raise NotImplementedError("a final() weighting is served for limit <= %d" % FINAL_MAX_K)
-            return self.engine.search_batch_final(batch, limit)
-        return self._run_packed(batch, limit)
+        with self.engine.lock:
+            self._bind()
+            if self.weighting.use_final:
+                if limit > FINAL_MAX_K:
+                    raise NotImplementedError("a final() weighting is served for limit <= %d" % FINAL_MAX_K)
+                return self.engine.search_batch_final(batch, limit)
+            return self._run_packed(batch, limit)
 
     def search_packed_stream(self, batches, limit: int = 10):
         """``search_packed`` over an iterable of packed batches, pipelined two deep: while the GPU scores
@@ -356,7 +358,9 @@ class Searcher:
         T = max(1, -(-self.ix.n_docs_all // (self.engine.stats()["tile_docs"] or DEFAULT_TILE_DOCS)))
         max_leaves = max(_ffi.MAX_LEAVES_PER_QUERY, BOUNDS_BYTES_PER_CALL // (4 * (T + 1)))
         pending = None
+        self.engine.lock.acquire()                       # the handle is this stream's until the generator ends
         try:
+            self._bind()
             for batch in batches:
                 if batch.n_leaves > max_leaves:          # needs splitting: not pipelined
                     if pending is not None:
@@ -374,13 +378,21 @@ class Searcher:
                 p, pending = pending, None
                 yield p.collect()
         finally:
-            if pending is not None:                      # the consumer stopped early: free the workspace
-                pending.collect()
+            try:
+                if pending is not None:                  # the consumer stopped early: free the workspace
+                    pending.collect()
+            finally:
+                self.engine.lock.release()
 
     def search_batch(self, queries: Sequence[Query], limit: Optional[int] = 10) -> List[Results]:
         """Batched ``search``: one GPU pass for all queries (several when ``limit`` is
         ``None`` or exceeds the kernel's top-k capacity: the next pass collects only hits
         ordered strictly after the last one already returned)."""
+        with self.engine.lock:
+            self._bind()
+            return self._search_batch_locked(queries, limit)
+
+    def _search_batch_locked(self, queries: Sequence[Query], limit: Optional[int]) -> List[Results]:
         t_start = time.perf_counter()
         queries = list(queries)
         nq = len(queries)

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define BM25F_ABI_VERSION 2
+#define BM25F_ABI_VERSION 3
 
 #define BM25F_OK          0
 #define BM25F_EINVAL     -1   /* bad argument */
@@ -85,15 +85,15 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 256, <= 8 leaves, positive
-                                    weights, no paging bound - flat ORs on warp streams, ANDs whose smallest
+  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 256, positive weights, no paging
+                                    bound - flat ORs of up to 32 leaves on the cooperative tile kernel (small ones
+                                    by candidate-driven lookups), ANDs whose smallest
                                     group is far sparser than the rest by candidate-driven lookups, other
                                     ANDs on warp teams; else the bulk-copy pipeline),
                                     1 = bulk-copy pipeline, 2 = direct loads, 3 = warp streams,
                                     4 = warp teams (same eligibility as 3),
                                     5 = candidate-driven lookups for every eligible query (<= 32 leaves),
-                                    6 = as 0 but every eligible flat OR scored one-dense by lookups,
-                                    7 = as 0 but every eligible flat OR scored one-dense by hashing */
+                                    6 = as 0 but every eligible flat OR on the cooperative tile kernel, however small */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
   uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
@@ -113,12 +113,12 @@ typedef struct {
   uint32_t isect_split;          /* candidate-driven AND: target candidates per work item; default 2048 */
   uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
                                     below this (0xFFFFFFFF = never) */
-  uint32_t or1_ratio;            /* experimental: a flat OR is scored "one-dense" (densest leaf streamed without
-                                    accumulators by k_score_isect, the others looked up in it) when (postings of
-                                    the other leaves) x or1_ratio < postings of the query; 0 = never (default).
-                                    16 speeds an OR-only batch up by 18 % but slows the AND/OR mix down, because
-                                    the second stream is then the longer one */
-  uint32_t hash_split;           /* one-dense OR: target work (posting-equivalents) per work item */
+  uint32_t coop_warps;           /* cooperative tile kernel (flat ORs): consumer warps per CTA (+ 1 producer warp), 1..31 */
+  uint32_t coop_tile_docs;       /* ... documents per shared-memory tile (8-byte tagged slots; even, <= 65536) */
+  uint32_t coop_chunk;           /* ... postings per staged chunk (multiple of 32) */
+  uint32_t coop_stages;          /* ... chunks in flight (ring depth, 2..8) */
+  uint32_t coop_split;           /* ... target work (posting-equivalents) per work item */
+  uint32_t serial_streams;       /* 1: the candidate-driven / team kernels run after, not beside, the flat-OR kernel */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves
@@ -155,9 +155,9 @@ typedef struct {
   uint64_t postings_cta;         /* k_score_pipe / k_score_topk */
   uint64_t postings_lookup;      /* k_score_isect: postings of the smallest group are read, the other lists are
                                     searched (skip_to), so most of these postings are NOT read */
-  uint64_t postings_hash;        /* k_score_hash (experimental) */
+  uint64_t postings_tile;        /* k_score_tile: every posting is read and accumulated */
   float    ms_stream;            /* summed device time of k_score_stream alone (it overlaps k_score_isect) */
-  uint32_t reserved;
+  float    ms_tile;              /* summed device time of k_tile_item_bounds + k_score_tile (they may overlap k_score_isect) */
 } bm25f_stats;
 
 int  bm25f_abi_version(void);
