@@ -51,9 +51,7 @@ class Options(C.Structure):
                 ("subtile_docs", C.c_uint32), ("warp_split", C.c_uint32), ("stream_warps", C.c_uint32),
                 ("prefetch_postings", C.c_uint32), ("cta_warps", C.c_uint32), ("cta_prefetch", C.c_uint32),
                 ("cta_split", C.c_uint32), ("cta_slice_docs", C.c_uint32), ("isect_ratio", C.c_uint32),
-                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("coop_warps", C.c_uint32),
-                ("coop_tile_docs", C.c_uint32), ("coop_chunk", C.c_uint32), ("coop_stages", C.c_uint32),
-                ("coop_split", C.c_uint32), ("serial_streams", C.c_uint32)]
+                ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("serial_streams", C.c_uint32)]
 
 
 #: engine options a caller may pass (``bm25f_options`` field names; 0 = library default)
@@ -72,7 +70,7 @@ class Stats(C.Structure):
                 ("tile_docs", C.c_uint32), ("threads", C.c_uint32), ("ctas_per_sm", C.c_uint32),
                 ("packed_payload", C.c_uint32), ("device_bytes", C.c_uint64), ("postings_stream", C.c_uint64),
                 ("postings_team", C.c_uint64), ("postings_cta", C.c_uint64), ("postings_lookup", C.c_uint64),
-                ("postings_tile", C.c_uint64), ("ms_stream", C.c_float), ("ms_tile", C.c_float)]
+                ("reserved0", C.c_uint64), ("ms_stream", C.c_float), ("reserved1", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -11,7 +11,6 @@
 //   k_score_stream    (stream.cuh)        flat ORs: independent warps, accumulators in shared memory
 //   k_score_isect     (isect.cuh)         ANDs: candidate-driven lookups (IntersectionMatcher + skip_to)
 //   k_score_team      (team.cuh)          symmetric ANDs: CTA-built bounds table, private slices
-//   k_tile_item_bounds / k_score_tile (tile.cuh)   flat ORs: one CTA per query, TMA-staged posting chunks, tagged slots
 //   k_tile_bounds, k_score_pipe, k_score_topk   general fallback (k > 256, many leaves, paging, odd weights)
 //   k_merge_topk_warp / k_merge_topk      merge of per-item (or per-GPU) top-k lists
 //   k_decode_keys                         keys -> (score, docid, count)
@@ -160,9 +159,12 @@ __global__ void k_pack_postings(const uint32_t* __restrict__ docids, const float
 // pairs[i] = {docid, impact} with impact = tf / (tf + norm[lb]) for the postings [begin, end) of one
 // field (float64 divide, rounded once); refreshed whenever the weighting changes.
 // score = leaf weight * impact.
+//
+// weight_only: the field is not scorable (Whoosh gives such a field's terms a WeightScorer: the score of a posting is
+// its weight, no idf, no length norm - e.g. the reference's `book` ID field, my_index.py:152, :171): impact = tf.
 __global__ void k_impacts(const uint32_t* __restrict__ docids, const uint32_t* __restrict__ payload, const uint8_t* __restrict__ lb,
                           const float* __restrict__ norm_field, unsigned long long begin, unsigned long long end,
-                          int packed, uint2* __restrict__ pairs) {
+                          int packed, int weight_only, uint2* __restrict__ pairs) {
   unsigned long long i = begin + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (; i < end; i += stride) {
@@ -171,7 +173,7 @@ __global__ void k_impacts(const uint32_t* __restrict__ docids, const uint32_t* _
     uint32_t b;
     if (packed) { tf = (double)(pl >> 8); b = pl & 255u; }
     else { tf = (double)__uint_as_float(pl); b = lb[i]; }
-    const float u = tf > 0.0 ? (float)(tf / (tf + (double)norm_field[b])) : 0.0f;
+    const float u = tf > 0.0 ? (weight_only ? (float)tf : (float)(tf / (tf + (double)norm_field[b]))) : 0.0f;
     pairs[i] = make_uint2(docids[i], __float_as_uint(u));
   }
 }
@@ -987,7 +989,6 @@ __device__ __forceinline__ unsigned long long warp_topk_kth(const unsigned long 
 
 #include "final.cuh"
 #include "stream.cuh"
-#include "tile.cuh"
 #include "team.cuh"
 #include "isect.cuh"
 
@@ -1305,12 +1306,8 @@ struct bm25f_handle {
   int is_ctas_per_sm = 0;
   bool serial_streams = false;          // option: never run the second-stream kernels beside the first-stream ones
   uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000;   // candidate-driven AND: cost of a lookup in postings, candidates per item
-  // cooperative tile kernel (flat ORs): consumer warps per CTA, documents per tile, postings per stage, ring depth,
-  // target work per item
-  uint32_t ct_warps = 16, ct_tile_docs = 9216, ct_chunk = 1024, ct_stages = 3, ct_split = 1u << 22;
-  int ct_ctas_per_sm = 0;
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
-  cudaEvent_t ev[EV_RING][8] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone; [6], [7] the tile kernel (boundary table included)
+  cudaEvent_t ev[EV_RING][6] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone
   int ev_head = 0;                     // next slot to use
   int ev_pending = 0;                  // slots recorded but not yet folded into the stats
   bm25f_stats stats{};
@@ -1341,16 +1338,11 @@ struct bm25f_plan {
   uint32_t n_w4 = 0, n_w8 = 0;            // stream-kernel items / team-kernel items; the rest are CTA items
   ItemRec* d_items_w4 = nullptr;
   ItemRec* d_items_w8 = nullptr;
-  uint32_t n_ct = 0;                      // cooperative tile kernel items
-  ItemRec* d_items_ct = nullptr;
-  uint32_t* d_ct_boff = nullptr;          // [n_ct] first boundary-table entry of each item
-  uint32_t* d_ct_bounds = nullptr;
-  uint64_t n_ct_bounds = 0;
   uint32_t n_is = 0;                      // candidate-driven items
   ItemRec* d_items_is = nullptr;
   int k = 0, kp = 1, cap = 1024;
   uint64_t postings = 0;
-  uint64_t postings_cls[5] = {0, 0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven, cooperative tiles
+  uint64_t postings_cls[4] = {0, 0, 0, 0};   // per kernel class: stream, team, CTA, candidate-driven
   LeafRec* d_leaves = nullptr;
   QueryRec* d_queries = nullptr;
   ItemRec* d_items = nullptr;
@@ -1430,11 +1422,9 @@ int fold_events(bm25f_handle* h, int n) {
     CU(cudaEventElapsedTime(&b, e[1], e[2]));
     CU(cudaEventElapsedTime(&c, e[2], e[3]));
     CU(cudaEventElapsedTime(&d, e[0], e[3]));
-    float f = 0, g = 0;
+    float f = 0;
     CU(cudaEventElapsedTime(&f, e[4], e[5]));
-    CU(cudaEventElapsedTime(&g, e[6], e[7]));
     h->stats.ms_stream += f;
-    h->stats.ms_tile += g;
     h->stats.ms_bounds += a;
     h->stats.ms_score += b;
     h->stats.ms_merge += c;
@@ -1541,24 +1531,8 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->isect_split) h->is_split = opts->isect_split;
     if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
   }
-  if (opts) {
-    if (opts->coop_warps) h->ct_warps = opts->coop_warps;
-    if (opts->coop_tile_docs) h->ct_tile_docs = opts->coop_tile_docs;
-    if (opts->coop_chunk) h->ct_chunk = opts->coop_chunk;
-    if (opts->coop_stages) h->ct_stages = opts->coop_stages;
-    if (opts->coop_split) h->ct_split = opts->coop_split;
-    h->serial_streams = opts->serial_streams != 0;
-  }
-  if (h->variant > 6) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams), 5 (candidate-driven) or 6 (cooperative tiles for every eligible flat OR)"); }
-  if (h->ct_warps < 1 || h->ct_warps > (uint32_t)TL_MAX_CWARPS) { delete h; return fail(BM25F_EINVAL, "coop_warps must be 1..%d", TL_MAX_CWARPS); }
-  if (h->ct_tile_docs < 256 || h->ct_tile_docs > 65536 || (h->ct_tile_docs & 1)) { delete h; return fail(BM25F_EINVAL, "coop_tile_docs must be even, in 256..65536"); }
-  if (h->ct_chunk < 32 || (h->ct_chunk & 31) || h->ct_chunk > 8192) { delete h; return fail(BM25F_EINVAL, "coop_chunk must be a multiple of 32 in 32..8192"); }
-  if (h->ct_stages < 2 || h->ct_stages > (uint32_t)TL_MAX_STAGES) { delete h; return fail(BM25F_EINVAL, "coop_stages must be 2..%d", TL_MAX_STAGES); }
-  if ((h->variant == 0 || h->variant == 6) && tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps) + 2048 > (size_t)prop.sharedMemPerBlockOptin) {
-    const size_t need = tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps) + 2048;
-    delete h;
-    return fail(BM25F_EINVAL, "coop_tile_docs x coop_chunk x coop_stages needs %zu bytes of shared memory (> %zu)", need, (size_t)prop.sharedMemPerBlockOptin);
-  }
+  if (opts) h->serial_streams = opts->serial_streams != 0;
+  if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
   if (h->st_warps < 1 || h->st_warps > (uint32_t)ST_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "stream_warps must be 1..%d", ST_MAX_WARPS); }
@@ -1772,10 +1746,9 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   // the device maximum so that engines with different tile sizes can coexist.
   const int optin = (int)prop.sharedMemPerBlockOptin;
   {
-    const void* wfns[10] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
-                            (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>,
-                            (const void*)k_score_stream<8, false>, (const void*)k_score_stream<8, true>,
-                            (const void*)k_score_tile<1>, (const void*)k_score_tile<4>, (const void*)k_score_tile<8>};
+    const void* wfns[7] = {(const void*)k_score_stream<1, false>, (const void*)k_score_stream<4, false>, (const void*)k_score_team,
+                           (const void*)k_score_stream<1, true>, (const void*)k_score_stream<4, true>,
+                           (const void*)k_score_stream<8, false>, (const void*)k_score_stream<8, true>};
     for (const void* fn : wfns) {
       cudaFuncAttributes fa;
       CUH(cudaFuncGetAttributes(&fa, fn));
@@ -1812,8 +1785,16 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
 int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
   if (!h || !norm) return fail(BM25F_EINVAL, "null argument");
   CU(cudaSetDevice(h->device));
-  for (uint32_t i = 0; i < h->n_fields * 256; ++i)
-    if (!(norm[i] > 0.0f) || !std::isfinite(norm[i])) return fail(BM25F_EINVAL, "norm table entry %u is not a positive finite number", i);
+  std::vector<int> weight_only(h->n_fields + 1, 0);
+  for (uint32_t f = 0; f < h->n_fields; ++f) {
+    // a row of -1: the field is not scorable, its postings score their weight (Whoosh's WeightScorer)
+    bool all_neg1 = true;
+    for (uint32_t i = 0; i < 256; ++i) all_neg1 = all_neg1 && norm[f * 256 + i] == -1.0f;
+    weight_only[f] = all_neg1 ? 1 : 0;
+    if (all_neg1) continue;
+    for (uint32_t i = f * 256; i < (f + 1) * 256; ++i)
+      if (!(norm[i] > 0.0f) || !std::isfinite(norm[i])) return fail(BM25F_EINVAL, "norm table entry %u is not a positive finite number (or the whole row -1: field not scorable)", i);
+  }
   CU(cudaMemcpyAsync(h->d_norm, norm, (size_t)h->n_fields * 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   // refresh the per-posting impacts (one streaming pass over the store per field run)
   uint64_t t = 0;
@@ -1824,7 +1805,7 @@ int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
     const uint64_t b = h->term_offsets[t], e = h->term_offsets[t2];
     if (e > b) {
       const unsigned blocks = (unsigned)std::min<uint64_t>((e - b + 255) / 256, (uint64_t)h->n_sms * 16);
-      k_impacts<<<blocks, 256, 0, h->stream>>>(h->d_docids, h->d_payload, h->d_lb, h->d_norm + (size_t)f * 256, b, e, h->packed ? 1 : 0, h->d_pairs);
+      k_impacts<<<blocks, 256, 0, h->stream>>>(h->d_docids, h->d_payload, h->d_lb, h->d_norm + (size_t)f * 256, b, e, h->packed ? 1 : 0, weight_only[f], h->d_pairs);
       CU(cudaGetLastError());
     }
     t = t2;
@@ -1848,8 +1829,6 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_scores);
   cudaFree(p->d_docids);
   cudaFree(p->d_counts);
-  cudaFree(p->d_ct_boff);
-  cudaFree(p->d_ct_bounds);
   cudaFree(p->d_part_lo);
   cudaFree(p->d_final);
   delete p;
@@ -1952,7 +1931,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
   // A small batch (a single interactive query is the reference's use) would be a handful of items on
   // a handful of warps: cut its items finer so that the whole GPU works on it.
-  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split, ct_split = h->ct_split;
+  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
   if (Q <= 1024) {
     uint64_t total = 0;
     for (uint32_t i = 0; i < NL; ++i) {
@@ -1960,7 +1939,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
     const uint64_t per_item = std::max<uint64_t>(4096, total / ((uint64_t)h->n_sms * 32));   // ~2 items per stream-kernel warp
-    ct_split = (uint32_t)std::min<uint64_t>(ct_split, std::max<uint64_t>(32768, total / ((uint64_t)h->n_sms * 2)));   // ~2 items per SM
     if (per_item < wsplit) {
       is_split = (uint32_t)std::max<uint64_t>(128, (uint64_t)is_split * per_item / wsplit);
       tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
@@ -1971,9 +1949,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   // into its own item lists and counters), then stitched together.  A query's leaf records live at
   // the positions of its input leaves, so no thread needs another's running totals.
   struct PlanLocal {
-    std::vector<ItemRec> items[5];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven; 4: cooperative tiles
-    std::vector<uint64_t> item_w[5];
-    uint64_t postings = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+    std::vector<ItemRec> items[4];     // 0: warp streams; 1: warp teams; 2: CTA kernels; 3: candidate-driven
+    std::vector<uint64_t> item_w[4];
+    uint64_t postings = 0, cls_postings[4] = {0, 0, 0, 0};
     uint32_t n_parts = 0;
     bool any_nonpos = false;
     int rc = 0;
@@ -2102,30 +2080,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     const bool use_isect = isect_ok && ((final_mode && !stream_ok) || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? n_cand < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
-    // every other flat OR: one CTA per (query, range of tiles), k_score_tile
-    const bool use_tile = !use_isect && !final_mode && (h->variant == 0 || h->variant == 6) && (qr.flags & QF_SIMPLE_OR) && k <= FAST_MAX_K &&
-                          nlq <= (uint32_t)TL_MAX_LEAVES && qr.after_key == 0ull;
-    const bool use_team = !use_isect && !use_tile && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
-    const int cls = use_isect ? 3 : use_tile ? 4 : stream_ok ? (use_team ? 1 : 0) : 2;
+    const bool use_team = !use_isect && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
-    if (use_tile) {
-      // an item is a run of whole tiles; its boundary table (tiles + 1 rows of nlq entries) must fit TL_BCAP
-      const uint64_t Tt = h->ct_tile_docs;
-      const uint64_t ntiles = std::max<uint64_t>(1, (h->n_docs + Tt - 1) / Tt);
-      const uint64_t nt_cap = (uint64_t)TL_BCAP / nlq - 1;
-      const uint64_t work = P + ntiles * (32ull * nlq + 64ull);      // posting-equivalents: every (tile, leaf) phase has a fixed cost
-      nsplit = (uint32_t)std::min<uint64_t>(ntiles, std::max<uint64_t>((ntiles + nt_cap - 1) / nt_cap, (work + ct_split / 2) / ct_split));
-      qr.n_parts = nsplit;
-      for (uint32_t s = 0; s < nsplit; ++s) {
-        ItemRec it;
-        it.q = qi;
-        it.tile_begin = (uint32_t)((ntiles * s / nsplit) * Tt);                    // document range [lo, hi), tile-aligned
-        it.tile_end = (uint32_t)std::min<uint64_t>(h->n_docs, (ntiles * (s + 1) / nsplit) * Tt);
-        it.part = L.n_parts + s;
-        L.items[cls].push_back(it);
-        L.item_w[cls].push_back(work / nsplit);
-      }
-    } else if (use_isect) {
+    if (use_isect) {
       nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + is_split) / (2ull * is_split)));
       qr.n_parts = nsplit;
       for (uint32_t s = 0; s < nsplit; ++s) {
@@ -2207,9 +2165,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   for (auto& L : locals)
     if (L.rc) return fail(L.rc, "%s", L.err);
   // stitch: partial-list indices and bitmap offsets become global
-  std::vector<ItemRec> items[5];
-  std::vector<uint64_t> item_w[5];
-  uint64_t postings = 0, cls_postings[5] = {0, 0, 0, 0, 0};
+  std::vector<ItemRec> items[4];
+  std::vector<uint64_t> item_w[4];
+  uint64_t postings = 0, cls_postings[4] = {0, 0, 0, 0};
   uint32_t n_parts = 0;
   bool any_nonpos = false;
   for (unsigned t = 0; t < n_thr; ++t) {
@@ -2217,10 +2175,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     if (t > 0 && n_parts) {
       const uint32_t q0 = (uint32_t)((uint64_t)Q * t / n_thr), q1 = (uint32_t)((uint64_t)Q * (t + 1) / n_thr);
       for (uint32_t qi = q0; qi < q1; ++qi) queries[qi].part_begin += n_parts;
-      for (int c = 0; c < 5; ++c)
+      for (int c = 0; c < 4; ++c)
         for (auto& it : L.items[c]) it.part += n_parts;
     }
-    for (int c = 0; c < 5; ++c) {
+    for (int c = 0; c < 4; ++c) {
       items[c].insert(items[c].end(), L.items[c].begin(), L.items[c].end());
       item_w[c].insert(item_w[c].end(), L.item_w[c].begin(), L.item_w[c].end());
       cls_postings[c] += L.cls_postings[c];
@@ -2246,11 +2204,10 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->n_w4 = (uint32_t)items[0].size();
   p->n_w8 = (uint32_t)items[1].size();
   p->n_is = (uint32_t)items[3].size();
-  p->n_ct = (uint32_t)items[4].size();
   p->n_parts = n_parts;
   p->T = T;
   p->postings = postings;
-  for (int c = 0; c < 5; ++c) p->postings_cls[c] = cls_postings[c];
+  for (int c = 0; c < 4; ++c) p->postings_cls[c] = cls_postings[c];
   p->smem_score = p->simple_kernel ? score_smem_bytes(S, p->cap) : pipe_smem_bytes(h, p->cap);
   p->owns_memory = !use_arena;
   p->arena = use_arena ? slot : -1;
@@ -2271,13 +2228,12 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }                                                                   \
   } while (0)
   const size_t n_bounds = p->n_items ? (size_t)out_leaf * (T + 1) : 0;   // only the CTA kernels use the boundary table
-  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_ct;
-  const size_t boff_bytes = align_up((size_t)p->n_ct * 4);
+  const size_t n_it = (size_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
   std::vector<ItemRec> own_items;
   ItemRec* h_items;
   if (use_arena) {
     // the sorted item records follow the leaf / query records in the pinned arena
-    const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec)) + boff_bytes;
+    const size_t need = hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec));
     if (need > A.h_cap) {
       unsigned char* bigger = nullptr;
       const size_t cap = align_up(need * 2, 1u << 20);
@@ -2295,33 +2251,11 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     own_items.resize(n_it);
     h_items = own_items.data();
   }
-  std::vector<uint32_t> own_boff;
-  uint32_t* h_boff;
-  if (use_arena) {
-    h_boff = reinterpret_cast<uint32_t*>(A.h + hl_bytes + hq_bytes + align_up(n_it * sizeof(ItemRec)));
-  } else {
-    own_boff.resize(p->n_ct);
-    h_boff = own_boff.data();
-  }
   // layout of the item array: [CTA items][warp streams][warp teams][candidate-driven AND]
   order_items(items[2], item_w[2], h_items);
   order_items(items[0], item_w[0], h_items + p->n_items);
   order_items(items[1], item_w[1], h_items + p->n_items + p->n_w4);
   order_items(items[3], item_w[3], h_items + p->n_items + p->n_w4 + p->n_w8);
-  order_items(items[4], item_w[4], h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is);
-  {
-    // boundary tables of the tile items, in launch order
-    const ItemRec* ct = h_items + p->n_items + p->n_w4 + p->n_w8 + p->n_is;
-    uint64_t nb = 0;
-    for (uint32_t i = 0; i < p->n_ct; ++i) {
-      const uint64_t nt = ((uint64_t)ct[i].tile_end - ct[i].tile_begin + h->ct_tile_docs - 1) / h->ct_tile_docs;
-      h_boff[i] = (uint32_t)nb;
-      nb += (nt + 1) * queries[ct[i].q].n_leaves;
-    }
-    if (nb > 0xFFFFFFF0ull) { delete p; return fail(BM25F_EINVAL, "batch too large: %llu tile-boundary entries (split the batch)", (unsigned long long)nb); }
-    p->n_ct_bounds = nb;
-  }
-
   if (use_arena) {
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
@@ -2329,7 +2263,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
                  o_items = take(n_it * sizeof(ItemRec)), o_bounds = take(n_bounds * 4),
                  o_part = take((size_t)n_parts * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 8) * 8),
                  o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4),
-                 o_ctboff = take((size_t)p->n_ct * 4), o_ctbounds = take((size_t)p->n_ct_bounds * 4),
                  o_plo = take(final_mode ? (size_t)n_parts * k * 4 : 0), o_fin = take(final_mode ? (size_t)Q * k * 8 : 0);
     if (off > A.d_cap) {
       CUP(cudaStreamSynchronize(h->stream));
@@ -2353,8 +2286,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     p->d_scores = reinterpret_cast<float*>(d + o_sc);
     p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
     p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
-    p->d_ct_boff = reinterpret_cast<uint32_t*>(d + o_ctboff);
-    p->d_ct_bounds = reinterpret_cast<uint32_t*>(d + o_ctbounds);
     if (final_mode) {
       p->d_part_lo = reinterpret_cast<unsigned int*>(d + o_plo);
       p->d_final = reinterpret_cast<double*>(d + o_fin);
@@ -2370,8 +2301,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
-    RCP(dev_alloc(&p->d_ct_boff, p->n_ct));
-    RCP(dev_alloc(&p->d_ct_bounds, p->n_ct_bounds));
     if (final_mode) {
       RCP(dev_alloc(&p->d_part_lo, (size_t)n_parts * k + 1));
       RCP(dev_alloc(&p->d_final, (size_t)Q * k + 1));
@@ -2380,7 +2309,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   p->d_items_w4 = p->d_items + p->n_items;
   p->d_items_w8 = p->d_items + p->n_items + p->n_w4;
   p->d_items_is = p->d_items + p->n_items + p->n_w4 + p->n_w8;
-  p->d_items_ct = p->d_items_is + p->n_is;
   auto t_c = now();
   // Arena plans upload on the copy stream (bm25f_execute waits for ev_ready): the records of the next batch
   // travel while the current one is still being scored.  Nothing else touches this arena: its previous
@@ -2389,7 +2317,6 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   if (out_leaf) CUP(cudaMemcpyAsync(p->d_leaves, leaves, (size_t)out_leaf * sizeof(LeafRec), cudaMemcpyHostToDevice, up));
   if (Q) CUP(cudaMemcpyAsync(p->d_queries, queries, (size_t)Q * sizeof(QueryRec), cudaMemcpyHostToDevice, up));
   if (n_it) CUP(cudaMemcpyAsync(p->d_items, h_items, n_it * sizeof(ItemRec), cudaMemcpyHostToDevice, up));
-  if (p->n_ct) CUP(cudaMemcpyAsync(p->d_ct_boff, h_boff, (size_t)p->n_ct * 4, cudaMemcpyHostToDevice, up));
   if (use_arena) CUP(cudaEventRecord(A.ev_ready, up));
   // pageable sources must outlive the copy; a pinned arena is only rewritten two batches later
   if (!use_arena) CUP(cudaStreamSynchronize(h->stream));
@@ -2436,7 +2363,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     ++launches;
   }
   CU(cudaEventRecord(ev[1], st));
-  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is || p->n_ct) {
+  if (p->n_items || p->n_w4 || p->n_w8 || p->n_is) {
     ScoreParams sp;
     sp.docids = h->d_docids;
     sp.payload = h->d_payload;
@@ -2458,47 +2385,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.prof = h->d_prof;
     // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
     // registers) fit on an SM together and stall on different things: launch them side by side.
-    const bool side = (p->n_w4 || p->n_ct) && (p->n_is || p->n_w8) && !h->serial_streams;
+    const bool side = p->n_w4 && (p->n_is || p->n_w8) && !h->serial_streams;
     cudaStream_t ax = side ? h->aux_stream : st;
     if (side) {
       CU(cudaEventRecord(h->ev_fork, st));
       CU(cudaStreamWaitEvent(ax, h->ev_fork, 0));
-    }
-    if (p->n_ct) {
-      TileParams tp;
-      tp.pairs = h->d_pairs;
-      tp.leaves = p->d_leaves;
-      tp.queries = p->d_queries;
-      tp.items = p->d_items_ct;
-      tp.item_boff = p->d_ct_boff;
-      tp.bounds = p->d_ct_bounds;
-      tp.part_keys = p->d_part_keys;
-      tp.totals = p->d_totals;
-      tp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 5);
-      tp.n_items = p->n_ct;
-      tp.tile_docs = h->ct_tile_docs;
-      tp.chunk = h->ct_chunk;
-      tp.stages = h->ct_stages;
-      tp.doc_base = (uint32_t)h->doc_base;
-      tp.k = p->k;
-      const unsigned threads = (h->ct_warps + 1u) * 32u;
-      const size_t smem = tile_smem_bytes(h->ct_tile_docs, h->ct_chunk, h->ct_stages, h->ct_warps);
-      if (h->ct_ctas_per_sm == 0) {
-        int nb_ = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_tile<1>, (int)threads, smem));
-        if (nb_ < 1) return fail(BM25F_EINVAL, "k_score_tile does not fit an SM with %u threads and %zu bytes of shared memory", threads, smem);
-        h->ct_ctas_per_sm = nb_;
-      }
-      CU(cudaEventRecord(ev[6], st));
-      k_tile_item_bounds<<<(p->n_ct + 3) / 4, 128, 0, st>>>(tp);
-      CU(cudaGetLastError());
-      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->ct_ctas_per_sm), p->n_ct);
-      if (p->k <= 32) k_score_tile<1><<<grid, threads, smem, st>>>(tp);
-      else if (p->k <= 128) k_score_tile<4><<<grid, threads, smem, st>>>(tp);
-      else k_score_tile<8><<<grid, threads, smem, st>>>(tp);
-      CU(cudaGetLastError());
-      CU(cudaEventRecord(ev[7], st));
-      launches += 2;
     }
     if (p->n_w4) {
       StreamParams stp;
@@ -2612,7 +2503,6 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     }
   }
   if (!p->n_w4) { CU(cudaEventRecord(ev[4], st)); CU(cudaEventRecord(ev[5], st)); }
-  if (!p->n_ct) { CU(cudaEventRecord(ev[6], st)); CU(cudaEventRecord(ev[7], st)); }
   CU(cudaEventRecord(ev[2], st));
   if (p->Q && p->final_mode) {
     if (p->k <= 128) k_merge_final<4><<<(p->Q + 7) / 8, 256, 0, st>>>(p->d_part_keys, p->d_part_lo, p->d_queries, p->Q, p->k, p->d_final, p->d_docids, p->d_counts);
@@ -2656,14 +2546,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->stats.postings_team = p->postings_cls[1];
   h->stats.postings_cta = p->postings_cls[2];
   h->stats.postings_lookup = p->postings_cls[3];
-  h->stats.postings_tile = p->postings_cls[4];
-  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is + p->n_ct;
+  h->stats.n_items = (uint64_t)p->n_items + p->n_w4 + p->n_w8 + p->n_is;
   h->stats.n_launches = launches;
   if (h->ctas_per_sm == 0) {
     int nb_ = 0;
-    if (p->n_ct) {
-      nb_ = h->ct_ctas_per_sm;
-    } else if (p->n_w8 && !p->n_w4) {
+    if (p->n_w8 && !p->n_w4) {
       nb_ = h->tl_ctas_per_sm;
     } else if (p->n_w4) {
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_stream<1, false>, (int)h->st_warps * 32, stream_smem_bytes(h->st_warps, h->st_slot_bytes));
@@ -2896,7 +2783,7 @@ int bm25f_reset_stats(bm25f_handle* h) {
     cudaMemset(h->d_prof, 0, sizeof v);
   }
 #endif
-  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = h->stats.ms_stream = h->stats.ms_tile = 0.0f;
+  h->stats.ms_bounds = h->stats.ms_score = h->stats.ms_merge = h->stats.ms_total = h->stats.ms_stream = 0.0f;
   h->stats.n_executes = 0;
   return 0;
 }

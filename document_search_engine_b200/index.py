@@ -22,6 +22,7 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
+import json
 import threading
 
 import numpy as np
@@ -91,7 +92,8 @@ class FlatIndex:
                  stored: Optional[Sequence[Mapping]] = None,
                  doc_base: int = 0,
                  global_doc_count_all: Optional[int] = None,
-                 term_weight_total: Optional[np.ndarray] = None):
+                 term_weight_total: Optional[np.ndarray] = None,
+                 scorable: Optional[Sequence[bool]] = None):
         self.field_names = list(field_names)
         self.n_docs_all = int(n_docs_all)
         self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
@@ -116,6 +118,11 @@ class FlatIndex:
         # W8: idf / avgfl come from the whole corpus, never from a shard
         self.global_doc_count_all = int(self.n_docs_all if global_doc_count_all is None else global_doc_count_all)
         self.term_weight_total = term_weight_total
+        #: W15: per field, Whoosh's ``schema[field].scorable``.  TEXT fields are; an ID field like the reference's
+        #: ``book`` (``my_index.py:152``, ``:171``) is not: its terms score their posting weight (WeightScorer)
+        self.scorable = [True] * len(self.field_names) if scorable is None else [bool(x) for x in scorable]
+        if len(self.scorable) != len(self.field_names):
+            raise ValueError("scorable must have one entry per field")
         self.schema = Schema(self.field_names, stored=self._stored_names())
         self._engine_cache = {}
         self._engine_cache_lock = threading.Lock()
@@ -171,6 +178,10 @@ class FlatIndex:
             return -1
         return f * self.vocab_size + r
 
+    def is_scorable(self, fieldname) -> bool:
+        f = self.field_index(fieldname)
+        return f < 0 or self.scorable[f]
+
     def field_length(self, fieldname) -> int:
         f = self.field_index(fieldname)
         return 0 if f < 0 else int(self.field_length_total[f])
@@ -203,10 +214,12 @@ class FlatIndex:
     @classmethod
     def from_documents(cls, docs: Sequence[Mapping[str, object]], fields: Sequence[str],
                        analyzer=None, stored: Optional[Sequence[str]] = None,
-                       deleted: Iterable[int] = ()) -> "FlatIndex":
+                       deleted: Iterable[int] = (), id_fields: Sequence[str] = ()) -> "FlatIndex":
         """Build from tokenised documents: ``doc[field]`` is a token list or a string
         split on whitespace by default.  Token boosts are all 1 so ``tf`` is the term
-        count (W7)."""
+        count (W7).  ``id_fields``: fields indexed like Whoosh's ``ID`` type (the reference's ``book``,
+        ``my_index.py:152``): the whole value is one term, posting weight 1 (Existence format), no length
+        is stored and the field is not scorable (W15)."""
         analyzer = analyzer or (lambda text: text.split())
         n = len(docs)
         nf = len(fields)
@@ -216,6 +229,9 @@ class FlatIndex:
             for f, name in enumerate(fields):
                 v = doc.get(name)
                 if v is None:
+                    continue
+                if name in id_fields:
+                    postings.setdefault((f, v), {})[d] = 1.0
                     continue
                 toks = analyzer(v) if isinstance(v, str) else list(v)
                 lengths[f, d] = len(toks)
@@ -246,7 +262,8 @@ class FlatIndex:
                    docids=np.array(dl, dtype=np.uint32), tfs=np.array(tl, dtype=np.float32),
                    term_field=np.array([k[0] for k in keys], dtype=np.uint8),
                    len_bytes=lb, field_length_total=lengths.sum(axis=1).astype(np.uint64),
-                   terms=terms, deleted=del_arr, stored=stored_docs)
+                   terms=terms, deleted=del_arr, stored=stored_docs,
+                   scorable=[name not in id_fields for name in fields])
 
     # ---- document sharding (W8, SURVEY.md §8 e) ------------------------------
     def shard(self, g: int, n_shards: int) -> "FlatIndex":
@@ -271,7 +288,7 @@ class FlatIndex:
                          stored=None if self.stored is None else self.stored[lo:hi],
                          doc_base=self.doc_base + lo,
                          global_doc_count_all=self.global_doc_count_all,
-                         term_weight_total=self.term_weight_total)
+                         term_weight_total=self.term_weight_total, scorable=self.scorable)
 
     # ---- persistence (the "checkpoint": a flattened index file) --------------
     def save(self, path: str) -> None:
@@ -288,7 +305,9 @@ class FlatIndex:
                  deleted=self.deleted if self.deleted is not None else np.zeros(0, np.uint8),
                  vocab_size=-1 if self.vocab_size is None else self.vocab_size,
                  doc_base=self.doc_base, global_doc_count_all=self.global_doc_count_all,
-                 dict_field=tf_, dict_text=tt_, dict_id=ti_)
+                 dict_field=tf_, dict_text=tt_, dict_id=ti_, scorable=np.array(self.scorable, dtype=np.uint8),
+                 term_weight_total=(self.term_weight_total if self.term_weight_total is not None else np.zeros(0, np.float64)),
+                 stored_json=np.array("" if self.stored is None else json.dumps(list(self.stored), default=str)))
 
     @classmethod
     def load(cls, path: str) -> "FlatIndex":
@@ -305,4 +324,7 @@ class FlatIndex:
                    field_length_total=z["field_length_total"], terms=terms,
                    vocab_size=None if vs < 0 else vs, df=z["df"],
                    deleted=z["deleted"] if z["deleted"].size else None,
-                   doc_base=int(z["doc_base"]), global_doc_count_all=int(z["global_doc_count_all"]))
+                   doc_base=int(z["doc_base"]), global_doc_count_all=int(z["global_doc_count_all"]),
+                   scorable=[bool(x) for x in z["scorable"]] if "scorable" in z.files else None,
+                   term_weight_total=(z["term_weight_total"] if "term_weight_total" in z.files and z["term_weight_total"].size else None),
+                   stored=(json.loads(str(z["stored_json"])) if "stored_json" in z.files and str(z["stored_json"]) else None))

@@ -164,20 +164,43 @@ class _Compound(Query):
             yield from q.leaves()
 
     def normalize(self):
-        """Flatten same-type nesting, drop null children, unwrap singletons."""
+        """What Whoosh's ``CompoundQuery.normalize`` does to the trees this path serves ([W] query/compound.py;
+        ``QueryParser.parse`` normalizes by default, so every query the reference hands to ``search`` has been
+        through it, ``my_flask.py:189-193``): nested nodes of the same class are merged (the child's boost goes
+        into its subqueries), null children are dropped, EQUAL SUBQUERIES ARE KEPT ONCE (a stemmed field turns
+        ``walk walking`` into two equal terms: Whoosh scores the term once), a single survivor is returned
+        with the boosts multiplied."""
         subs: List[Query] = []
         for q in self.subqueries:
             q = q.normalize()
-            if isinstance(q, _Null):
-                continue
-            if type(q) is type(self) and q.boost == 1.0:
-                subs.extend(q.subqueries)
+            if type(q) is type(self):
+                subs.extend(_with_boost(s, s.boost * q.boost) for s in q.subqueries)
             else:
                 subs.append(q)
-        if not subs:
+        seen = set()
+        kept: List[Query] = []
+        for q in subs:
+            if isinstance(q, _Null) or q in seen:
+                continue
+            seen.add(q)
+            kept.append(q)
+        if not kept:
             return NullQuery
-        if len(subs) == 1 and self.boost == 1.0:
-            return subs[0]
+        if len(kept) == 1:
+            return _with_boost(kept[0], kept[0].boost * self.boost)
+        return type(self)(kept, boost=self.boost)
+
+    def flattened(self):
+        """Score-neutral restructuring for ``lower`` (no de-duplication: ``Searcher.search`` scores the tree it is
+        given, as Whoosh does): nested nodes of the same class are merged, their boost pushed into the children."""
+        subs: List[Query] = []
+        for q in self.subqueries:
+            if isinstance(q, _Compound):
+                q = q.flattened()
+            if type(q) is type(self):
+                subs.extend(_with_boost(s, s.boost * q.boost) for s in q.subqueries)
+            else:
+                subs.append(q)
         return type(self)(subs, boost=self.boost)
 
 
@@ -222,6 +245,18 @@ class Not(Query):
         return Not(q)
 
 
+def _with_boost(q: Query, boost: float) -> Query:
+    if boost == q.boost:
+        return q
+    if isinstance(q, Term):
+        return Term(q.fieldname, q.text, boost=boost)
+    if isinstance(q, Every):
+        return Every(q.fieldname, boost=boost)
+    if isinstance(q, _Compound):
+        return type(q)(q.subqueries, boost=boost)
+    return q                     # Not / Null carry no score
+
+
 #: ``Leaf.group`` of a leaf inside a NOT clause (BM25F_GROUP_NOT in include/bm25f.h)
 GROUP_NOT = 255
 
@@ -248,7 +283,10 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
     ``"every"`` or ``"null"``.  Boosts on compound nodes are pushed into the
     leaves, which is exact because W10 scores are sums of leaf scores.
     """
-    q = q.normalize()
+    if isinstance(q, _Compound):
+        q = q.flattened()
+        if len(q.subqueries) == 1 and not isinstance(q.subqueries[0], Not):
+            return lower(_with_boost(q.subqueries[0], q.subqueries[0].boost * q.boost))
     if isinstance(q, _Null):
         return [], 0, "null"
     if isinstance(q, Every):
@@ -267,6 +305,12 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
         negatives: List[Leaf] = []
         g = 0
         for s in q.subqueries:
+            if isinstance(s, _Null):
+                if conj:
+                    return [], 0, "null"          # Whoosh: an And with a NullMatcher child matches nothing
+                continue
+            if isinstance(s, _Compound) and len(s.subqueries) == 1 and isinstance(s.subqueries[0], Term):
+                s = _with_boost(s.subqueries[0], s.subqueries[0].boost * s.boost)
             if isinstance(s, Term):
                 leaves.append(Leaf(s.fieldname, s.text, s.boost * q.boost, g))
             elif isinstance(s, Or) and conj:
@@ -275,8 +319,11 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
                         raise UnsupportedQuery("And(Or(...)) groups may only contain Term leaves: %r" % (t,))
                     leaves.append(Leaf(t.fieldname, t.text, t.boost * s.boost * q.boost, g))
             elif isinstance(s, Not):
-                inner = s.query.subqueries if isinstance(s.query, Or) else [s.query]
+                nq = s.query.flattened() if isinstance(s.query, _Compound) else s.query
+                inner = nq.subqueries if isinstance(nq, Or) else [nq]
                 for t in inner:
+                    if isinstance(t, _Null):
+                        continue                  # NOT nothing: no constraint
                     if not isinstance(t, Term):
                         raise UnsupportedQuery("Not() may contain a Term or an Or of Terms: %r" % (t,))
                     negatives.append(Leaf(t.fieldname, t.text, 1.0, GROUP_NOT))

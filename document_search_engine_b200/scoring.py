@@ -56,13 +56,21 @@ class BM25F(WeightingModel):
 
     # -- host-side products consumed by the engine ---------------------------
     def leaf_weight(self, searcher, fieldname, text, boost=1.0) -> float:
+        """W15: Whoosh's ``BM25F.scorer`` returns a ``WeightScorer`` for a field that is not scorable (the
+        reference's ``book=ID`` field, ``my_index.py:152``; the UI's book filter generates ``book:xyz`` terms,
+        ``static/main.js:5-16``): the score is the posting weight, times the boost."""
+        if not searcher.stats_ix.is_scorable(fieldname):
+            return float(boost)
         return self.idf(searcher, fieldname, text) * (self.K1 + 1.0) * boost
 
     def norm_tables(self, ix) -> np.ndarray:
         """float32 ``[n_fields, 256]`` norm tables for index ``ix`` (global avgfl, W4/W8)."""
         out = np.empty((len(ix.field_names), 256), dtype=np.float32)
         for f, name in enumerate(ix.field_names):
-            out[f] = norm_table(self.field_B(name), self.K1, ix.avg_field_length(name)).astype(np.float32)
+            if not ix.is_scorable(name):
+                out[f] = -1.0               # W15: WeightScorer, the posting weight is the score
+            else:
+                out[f] = norm_table(self.field_B(name), self.K1, ix.avg_field_length(name)).astype(np.float32)
         return out
 
     def norm_key(self):

@@ -17,6 +17,8 @@ top-k always run on the GPU through ``libbm25f``; there is no CPU path here.
 """
 from __future__ import annotations
 
+import gc
+import struct
 import time
 from math import ceil, log
 from typing import Iterable, List, Optional, Sequence
@@ -24,8 +26,12 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from .query import Query, UnsupportedQuery, lower
+from .query import And, Or, Query, Term, UnsupportedQuery, lower
 from .scoring import BM25F, instantiate
+
+#: one lowered leaf as ``Searcher.pack`` keeps it: posting-list id (or -1 / -2 - field), boost, group
+_LEAF_REC = np.dtype([("tid", "<i8"), ("boost", "<f8"), ("group", "u1"), ("pad", "V7")])
+_LEAF_STRUCT = struct.Struct("<qdB7x")
 
 #: bound on the per-call tile-boundary table (bytes); larger batches are split
 BOUNDS_BYTES_PER_CALL = 1 << 30
@@ -220,6 +226,7 @@ class Searcher:
         with eng.lock:
             self._bind()
         self._idf_cache = {}
+        self._term_w = None
         self.closed = False
 
     def _bind(self):
@@ -274,45 +281,89 @@ class Searcher:
         return self
 
     # -- lowering -------------------------------------------------------------------
-    def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
-        """Lower query trees to the ``bm25f_query_batch`` layout.  Leaf weights
-        ``idf * (K1 + 1) * boost`` are evaluated in float64 and rounded once."""
-        offs = [0]
-        ngroups: List[int] = []
-        terms: List[int] = []
-        weights: List[float] = []
-        groups: List[int] = []
-        k1p = self.weighting.K1 + 1.0
+    def _term_weights(self) -> np.ndarray:
+        """float64 ``[n_terms]``: ``idf * (K1 + 1)`` of every posting list (W3 with the corpus-wide df / dc), or 1
+        for a term of a field that is not scorable (W15: WeightScorer, the leaf weight is the boost alone)."""
+        tw = self._term_w
+        if tw is None:
+            sx = self.stats_ix
+            dc = float(sx.doc_count_all())
+            tw = (np.log(dc / (sx.df.astype(np.float64) + 1.0)) + 1.0) * (self.weighting.K1 + 1.0)
+            for f, name in enumerate(sx.field_names):
+                if not sx.is_scorable(name):
+                    tw[sx.term_field == f] = 1.0
+            self._term_w = tw
+        return tw
+
+    def _lower_one(self, q: Query):
+        """``(index, n_leaves, n_groups, packed leaf records, query)`` of one query: what ``pack`` needs, remembered
+        on the query object.  A leaf record is ``_LEAF_REC``: posting-list id (-1: unknown term or field, W10;
+        ``-2 - f``: ``Every`` on field ``f``), boost, group."""
         ix = self.ix
-        for q in queries:
-            leaves, g, kind = lower(q)
+        cls = type(q)
+        if cls is Term:
+            leaves, g = [(ix.term_id(q.fieldname, q.text), q.boost, 0)], 1
+        elif (cls is And or cls is Or) and 0 < len(q.subqueries) <= 32 and all([type(t) is Term for t in q.subqueries]):
+            qb, conj = q.boost, cls is And
+            leaves = [(ix.term_id(t.fieldname, t.text), t.boost * qb, i if conj else 0) for i, t in enumerate(q.subqueries)]
+            g = len(leaves) if conj else 1
+        else:
+            low, g, kind = lower(q)
             if kind == "every":
                 # Whoosh's Every(field): every live document that has the field, constant score = boost
                 # (reference cli.py:9).  The library keeps one posting list per field for it.
-                lf = leaves[0]
-                f = ix.field_names.index(lf.fieldname) if lf.fieldname in ix.field_names else -1
-                terms.append(_ffi.TERM_UNKNOWN if f < 0 else _ffi.TERM_EVERY_BASE + f)
-                weights.append(float(lf.boost))
-                groups.append(0)
-                ngroups.append(1)
-                offs.append(len(terms))
-                continue
-            if kind == "null":
-                ngroups.append(0)
-                offs.append(len(terms))
-                continue
-            if len(leaves) > _ffi.MAX_LEAVES_PER_QUERY:
-                raise UnsupportedQuery("more than %d leaves in one query" % _ffi.MAX_LEAVES_PER_QUERY)
-            if g > 32:
-                raise UnsupportedQuery("more than 32 AND-groups in one query")
-            for lf in leaves:
-                tid = ix.term_id(lf.fieldname, lf.text)
-                terms.append(_ffi.TERM_UNKNOWN if tid < 0 else tid)
-                weights.append(self.idf(lf.fieldname, lf.text) * k1p * lf.boost)
-                groups.append(lf.group)
-            ngroups.append(g)
-            offs.append(len(terms))
-        return _ffi.PackedBatch(offs, ngroups, terms, np.asarray(weights, dtype=np.float64), groups, after_keys)
+                f = ix.field_index(low[0].fieldname)
+                leaves = [(-1 if f < 0 else -2 - f, float(low[0].boost), 0)]
+            elif kind == "null":
+                leaves, g = [], 0
+            else:
+                if len(low) > _ffi.MAX_LEAVES_PER_QUERY:
+                    raise UnsupportedQuery("more than %d leaves in one query" % _ffi.MAX_LEAVES_PER_QUERY)
+                if g > 32:
+                    raise UnsupportedQuery("more than 32 AND-groups in one query")
+                leaves = [(ix.term_id(lf.fieldname, lf.text), lf.boost, lf.group) for lf in low]
+        return (ix, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]))
+
+    def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
+        """Lower query trees to the ``bm25f_query_batch`` layout.  Leaf weights ``idf * (K1 + 1) * boost`` are
+        evaluated in float64 and rounded once (numpy gathers over a per-term table).  The lowered form of a query
+        is remembered on the query object (query trees are values: the reference builds one per request,
+        ``my_flask.py:189-193``, and never edits it), so packing the same objects again costs three list appends
+        per query."""
+        ix = self.ix
+        counts: List[int] = []
+        ngroups: List[int] = []
+        blobs: List[bytes] = []
+        lower1 = self._lower_one
+        gc_was_on = gc.isenabled()
+        gc.disable()                             # thousands of small objects: a collection in here costs more than the loop
+        try:
+            for q in queries:
+                c = q.__dict__.get("_lowered")
+                if c is None or c[0] is not ix:
+                    c = lower1(q)
+                    q.__dict__["_lowered"] = c
+                counts.append(c[1])
+                ngroups.append(c[2])
+                blobs.append(c[3])
+        finally:
+            if gc_was_on:
+                gc.enable()
+        offs = np.zeros(len(counts) + 1, dtype=np.uint32)
+        np.cumsum(counts, out=offs[1:])
+        rec = np.frombuffer(b"".join(blobs), dtype=_LEAF_REC)
+        tids = rec["tid"]
+        known = tids >= 0
+        w = np.zeros(rec.size, dtype=np.float64)
+        if rec.size:
+            w[known] = self._term_weights()[tids[known]]
+            w *= rec["boost"]
+        terms = np.where(known, tids, _ffi.TERM_UNKNOWN).astype(np.uint32)
+        ev = tids <= -2                               # Every(field): constant-score pseudo lists, weight = boost
+        if ev.any():
+            terms[ev] = (_ffi.TERM_EVERY_BASE + (-2 - tids[ev])).astype(np.uint32)
+            w[ev] = rec["boost"][ev]
+        return _ffi.PackedBatch(offs, np.asarray(ngroups, dtype=np.uint8), terms, w, rec["group"], after_keys)
 
     # -- searching ----------------------------------------------------------------
     def _run_packed(self, batch: _ffi.PackedBatch, k: int):

@@ -85,15 +85,14 @@ typedef struct {
   uint32_t tile_docs;            /* documents per shared-memory score tile (<= 65536) */
   uint32_t threads;              /* threads per CTA of the scoring kernel */
   uint32_t split_postings;       /* target postings per work item */
-  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 256, positive weights, no paging
-                                    bound - flat ORs of up to 32 leaves on the cooperative tile kernel (small ones
-                                    by candidate-driven lookups), ANDs whose smallest
+  uint32_t variant;              /* scoring kernel: 0 = auto (where eligible - k <= 256, <= 8 leaves, positive
+                                    weights, no paging bound - flat ORs on warp streams (small ones by
+                                    candidate-driven lookups), ANDs whose smallest
                                     group is far sparser than the rest by candidate-driven lookups, other
                                     ANDs on warp teams; else the bulk-copy pipeline),
                                     1 = bulk-copy pipeline, 2 = direct loads, 3 = warp streams,
                                     4 = warp teams (same eligibility as 3),
-                                    5 = candidate-driven lookups for every eligible query (<= 32 leaves),
-                                    6 = as 0 but every eligible flat OR on the cooperative tile kernel, however small */
+                                    5 = candidate-driven lookups for every eligible query (<= 32 leaves) */
   uint32_t chunk_postings;       /* pipeline: postings per shared-memory stage (multiple of 16) */
   uint32_t stages;               /* pipeline: ring depth (2..32) */
   uint32_t subtile_docs;         /* stream kernel: documents per warp-private sub-range of a flat OR
@@ -113,11 +112,6 @@ typedef struct {
   uint32_t isect_split;          /* candidate-driven AND: target candidates per work item; default 2048 */
   uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
                                     below this (0xFFFFFFFF = never) */
-  uint32_t coop_warps;           /* cooperative tile kernel (flat ORs): consumer warps per CTA (+ 1 producer warp), 1..31 */
-  uint32_t coop_tile_docs;       /* ... documents per shared-memory tile (8-byte tagged slots; even, <= 65536) */
-  uint32_t coop_chunk;           /* ... postings per staged chunk (multiple of 32) */
-  uint32_t coop_stages;          /* ... chunks in flight (ring depth, 2..8) */
-  uint32_t coop_split;           /* ... target work (posting-equivalents) per work item */
   uint32_t serial_streams;       /* 1: the candidate-driven / team kernels run after, not beside, the flat-OR kernel */
 } bm25f_options;
 
@@ -155,9 +149,9 @@ typedef struct {
   uint64_t postings_cta;         /* k_score_pipe / k_score_topk */
   uint64_t postings_lookup;      /* k_score_isect: postings of the smallest group are read, the other lists are
                                     searched (skip_to), so most of these postings are NOT read */
-  uint64_t postings_tile;        /* k_score_tile: every posting is read and accumulated */
+  uint64_t reserved0;
   float    ms_stream;            /* summed device time of k_score_stream alone (it overlaps k_score_isect) */
-  float    ms_tile;              /* summed device time of k_tile_item_bounds + k_score_tile (they may overlap k_score_isect) */
+  uint32_t reserved1;
 } bm25f_stats;
 
 int  bm25f_abi_version(void);
@@ -166,7 +160,10 @@ const char* bm25f_last_error(void);
 int  bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* opts, bm25f_handle** out);
 void bm25f_destroy(bm25f_handle* h);
 
-/* norm: [n_fields * 256] float32, norm[f][b] = K1 * ((1 - B_f) + B_f * fl(b) / avgfl_f). */
+/* norm: [n_fields * 256] float32, norm[f][b] = K1 * ((1 - B_f) + B_f * fl(b) / avgfl_f).
+ * A row of 256 x -1.0 marks a field that is not scorable (Whoosh: schema[field].scorable is false, e.g. the
+ * reference's `book` ID field, my_index.py:152): BM25F.scorer() gives its terms a WeightScorer, the score of a
+ * posting is its weight x the leaf weight (which the caller then sets to the query boost alone: no idf). */
 int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
 
 /* A weighting with a final() step (reference my_whoosh.py:127-154, DescDateBM25F / AscDateBM25F, selected at

@@ -85,10 +85,14 @@ class NumpyOracle:
         d = sub.docids[a:b].astype(np.int64)
         tf = sub.tfs[a:b].astype(np.float64)
         f = sub.field_names.index(fieldname)
-        fl = B2L_SCORING[sub.len_bytes[f][d]]
-        B = self.field_B.get(fieldname, self.B)
-        K1 = self.K1
-        s = self.idf(fieldname, text) * ((tf * (K1 + 1)) / (tf + K1 * ((1 - B) + B * fl / self.avgfl(fieldname))))  # W1
+        flags = getattr(sub, "scorable", None)
+        if flags is not None and not flags[f]:
+            s = tf.copy()                                                         # W15: WeightScorer, the posting weight
+        else:
+            fl = B2L_SCORING[sub.len_bytes[f][d]]
+            B = self.field_B.get(fieldname, self.B)
+            K1 = self.K1
+            s = self.idf(fieldname, text) * ((tf * (K1 + 1)) / (tf + K1 * ((1 - B) + B * fl / self.avgfl(fieldname))))  # W1
         if boost != 1.0:
             s = s * boost
         if sub.deleted is not None:

@@ -10,7 +10,7 @@ item as W1-W14 of SURVEY.md §8 c, and is anchored on the reference's call sites
 * weighting selection / defaults ........ ``my_flask.py:183-184``  (W2)
 * ``search_page`` / ``search`` limits ..... ``my_flask.py:208``, ``:211``, ``:304``, ``cli.py:9``
 * ``final`` hook contract ................ ``my_whoosh.py:127-154``  (W14)
-* which fields are scorable TEXT ........ ``my_index.py:172-177``
+* which fields are scorable TEXT ........ ``my_index.py:172-177``; ``book=ID`` is not: ``:152``, ``:171``  (W15)
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs
 may import this module.  It deliberately mirrors the shape of the library it
@@ -127,8 +127,13 @@ class OracleSearcher:
                 return NullMatcher()                            # W10: unknown term/field
             a, b = int(sub.term_offsets[tid]), int(sub.term_offsets[tid + 1])
             f = sub.field_names.index(q.fieldname)
-            scorer = BM25FScorer(self, q.fieldname, q.text,
-                                 self.field_B.get(q.fieldname, self.B), self.K1)
+            if not _scorable(sub, f):
+                # W15: BM25F.scorer() returns WeightScorer for a field whose schema type is not scorable
+                # (reference book=ID, my_index.py:152, :171; queried by the UI's book filter, static/main.js:5-16)
+                scorer = WeightScorer()
+            else:
+                scorer = BM25FScorer(self, q.fieldname, q.text,
+                                     self.field_B.get(q.fieldname, self.B), self.K1)
             m = PostingMatcher(sub.docids[a:b].tolist(), sub.tfs[a:b].tolist(),
                                sub.len_bytes[f], scorer, sub.deleted)
             return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
@@ -164,6 +169,18 @@ def _binary_tree(cls, ms):
         return ms[0]
     half = len(ms) // 2
     return cls(_binary_tree(cls, ms[:half]), _binary_tree(cls, ms[half:]))
+
+
+def _scorable(ix, f):
+    flags = getattr(ix, "scorable", None)
+    return True if flags is None else bool(flags[f])
+
+
+class WeightScorer:
+    """W15 (Whoosh scoring.WeightScorer): the score of a posting is its weight; no idf, no length norm."""
+
+    def score(self, weight, length_byte):
+        return weight
 
 
 class BM25FScorer:

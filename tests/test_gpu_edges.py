@@ -10,7 +10,7 @@ from oracle.numpy_oracle import NumpyOracle
 from tests.parity import assert_batch_parity, assert_query_parity
 
 pytestmark = pytest.mark.gpu
-VARIANTS = [0, 3, 4, 5, 6, 1]
+VARIANTS = [0, 3, 4, 5, 1]
 
 
 def check(ix, queries, limit=10, **kw):

@@ -136,33 +136,6 @@ def test_isect_kernel(cfg1, split, ratio, mode):
     assert_batch_parity(o, qs.queries[:60], res, 32)
 
 
-@pytest.mark.parametrize("warps,tile_docs,chunk,stages,split", [(16, 0, 0, 0, 0), (15, 9216, 1024, 3, 0), (4, 256, 32, 2, 4096),
-                                                                 (31, 1000, 64, 8, 1 << 14), (8, 4098, 4096, 2, 0),
-                                                                 (1, 512, 96, 3, 0), (16, 20480, 2048, 4, 1 << 16)])
-def test_tile_kernel(cfg1, warps, tile_docs, chunk, stages, split):
-    """Cooperative tile kernel forced for every flat OR (variant 6): CTA sizes, tiny / odd-sized tiles (many tiles
-    per query, tile ranges per item), chunks smaller and larger than a visit, ring depths, items that start
-    inside lists; single-term queries, the densest terms, duplicated terms; k = 10, 32 (hot-list overflow on
-    every tile for small tiles), 100 and 150 (four and eight keys per lane)."""
-    ix, o = cfg1
-    qs = make_queries(300, 50_000, 78, 1, 4, "or", skip_top=0)
-    extra = [Term("body", 1), Term("body", 3), Term("body", 40000), Or([Term("body", 1), Term("body", 900), Term("body", 901)]),
-             Or([Term("body", 2), Term("body", 30), Term("body", 31), Term("body", 32)]), Or([Term("body", 5), Term("body", 5)]),
-             Or([Term("body", 1), Term("body", 2), Term("body", 1)]), Or([Term("body", 7), Term("body", 49999), Term("body", 12345)]),
-             Or([Term("body", t) for t in range(1, 33)]), Or([Term("body", t, boost=0.5 + 0.25 * (t % 5)) for t in range(100, 120)])]
-    queries = list(qs.queries) + extra
-    kw = dict(variant=6, coop_warps=warps, coop_tile_docs=tile_docs, coop_chunk=chunk, coop_stages=stages, coop_split=split)
-    with ix.searcher(**kw) as s:
-        res = s.search_batch(queries, limit=10)
-        st = s.engine.stats()
-        assert st["postings_tile"] > 0 and st["postings_stream"] == 0
-    assert_batch_parity(o, queries, res, 10)
-    for k in (32, 100, 150):
-        with ix.searcher(**kw) as s:
-            res = s.search_batch(queries[-70:], limit=k)
-        assert_batch_parity(o, queries[-70:], res, k)
-
-
 @pytest.mark.parametrize("k", [1, 3, 100, 150, 1024])
 def test_limits(cfg1, k):
     ix, o = cfg1

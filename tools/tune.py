@@ -86,12 +86,12 @@ def main():
             n = max(1, st["n_executes"])
             ms = st["ms_total"] / n
             gbs = 9.0 * st["postings_touched"] / (st["ms_score"] / n * 1e-3) / 1e9
-            tile_gbs = 9.0 * st["postings_tile"] / max(1e-9, st["ms_tile"] / n * 1e-3) / 1e9
+            stream_gbs = 9.0 * st["postings_stream"] / max(1e-9, st["ms_stream"] / n * 1e-3) / 1e9
             print(json.dumps({"opt": opt, "mode": m, "parity": bad or "ok", "qps": len(queries) / (ms * 1e-3), "ms_total": ms,
                               "ms_bounds": st["ms_bounds"] / n, "ms_score": st["ms_score"] / n,
-                              "ms_merge": st["ms_merge"] / n, "ms_stream": st["ms_stream"] / n, "ms_tile": st["ms_tile"] / n,
+                              "ms_merge": st["ms_merge"] / n, "ms_stream": st["ms_stream"] / n,
                               "post_stream": st["postings_stream"], "post_lookup": st["postings_lookup"],
-                              "post_tile": st["postings_tile"], "tile_GBs": tile_gbs, "tile_frac_6547": tile_gbs / 6547.2,
+                              "stream_GBs": stream_gbs, "stream_frac_6547": stream_gbs / 6547.2,
                               "step_GBs": gbs, "items": st["n_items"], "ctas_per_sm": st["ctas_per_sm"],
                               "postings": st["postings_touched"]}), flush=True)
             eng.reset_stats()      # a BM25F_PROFILE build prints its phase timers here
