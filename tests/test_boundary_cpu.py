@@ -8,8 +8,11 @@ import numpy as np
 import pytest
 
 from document_search_engine_b200 import _ffi
-from document_search_engine_b200 import And, Or, Term
+from document_search_engine_b200 import And, FlatIndex, Or, Term
+from document_search_engine_b200.query import Not, NullQuery, QueryParser, lower
 from document_search_engine_b200.variants import Variants, expand_with_map
+from oracle.numpy_oracle import NumpyOracle
+from oracle.whoosh_port import OracleSearcher
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "bm25f.h")
@@ -96,3 +99,75 @@ def test_variants_table(tmp_path):
     assert str(q) == str(Term("exact", "colour"))
     q = expand_with_map(And([Term("body", 60), Term("body", 61)]), lambda r: r ^ 1)
     assert str(q) == str(And([Or([Term("body", 60), Term("body", 61)]), Or([Term("body", 61), Term("body", 60)])]))
+
+
+REFERENCE_VARIANTS = "/root/reference/uk_us_variations.txt"
+
+
+@pytest.mark.skipif(not os.path.exists(REFERENCE_VARIANTS), reason="the reference checkout is not on this machine")
+def test_reference_variants_file():
+    """The reference's real table (uk_us_variations.txt:1-154, loader my_flask.py:531-537): 154 pairs, 308 distinct
+    lowercase words, no word on both sides or in two pairs (so the OR-expansion never chains)."""
+    v = Variants.load(REFERENCE_VARIANTS)
+    assert len(v.uk_variations) == 154 and len(v.us_variations) == 154
+    assert len(v.uk_us_variations) == 308
+    assert not (set(v.uk_variations) & set(v.us_variations))
+    assert all(w == w.lower() and " " not in w for w in v.uk_us_variations)
+    for uk, us in v.uk_variations.items():
+        assert v.us_variations[us] == uk and v.other(uk) == us and v.other(us) == uk
+    # the rewrite of BASELINE config 3 on real words: one 2-way OR group per query word that has a variant
+    uk = sorted(v.uk_variations)[:4]
+    q = v.expand(And([Term("exact", w) for w in uk] + [Term("exact", "zzzz")]))
+    assert len(q.subqueries) == 5 and all(isinstance(s, Or) and len(s.subqueries) == 2 for s in q.subqueries[:4])
+    assert isinstance(q.subqueries[4], Term)
+    leaves, groups, kind = lower(q)
+    assert kind == "groups" and groups == 5 and len(leaves) == 9
+
+
+def test_non_scorable_field_w15():
+    """W15: Whoosh's BM25F.scorer() hands a field that is not scorable (the reference's ``book=ID``, my_index.py:152,
+    :171; the UI's book filter writes ``book:xyz`` / ``NOT book:xyz`` into the query, static/main.js:5-16) a
+    WeightScorer: the score of a posting is its weight (1.0 for an ID field), times the boost - no idf, no length."""
+    docs = [{"body": "seth speaks of joy", "book": "ss"}, {"body": "joy and vitality joy", "book": "nopr"},
+            {"body": "the nature of joy", "book": "nopr"}, {"body": "dreams", "book": "deavf1"}]
+    ix = FlatIndex.from_documents(docs, ["body", "book"], id_fields=["book"])
+    assert ix.scorable == [True, False] and ix.len_bytes[1].tolist() == [0, 0, 0, 0]
+    assert ix.term_id("book", "nopr") >= 0 and ix.term_id("book", "no") < 0          # the whole value is the term
+    for o in (OracleSearcher(ix), NumpyOracle(ix)):
+        top, total = o.search(Term("book", "nopr"))
+        assert total == 2 and top == [(1.0, 1), (1.0, 2)]
+        top, total = o.search(Term("book", "nopr", boost=2.5))
+        assert top == [(2.5, 1), (2.5, 2)]
+        both, _ = o.search(And([Term("body", "joy"), Term("book", "nopr")]))
+        joy = dict((d, s) for s, d in o.search(Term("body", "joy"))[0])
+        assert [(d, pytest.approx(joy[d] + 1.0, rel=1e-15)) for s, d in both] == [(d, s) for s, d in both]
+        assert sorted(d for _, d in both) == [1, 2]
+        top, total = o.search(And([Term("body", "joy"), Not(Term("book", "nopr"))]))
+        assert total == 1 and top[0][1] == 0 and top[0][0] == pytest.approx(joy[0], rel=1e-15)
+    # the host side hands the engine boost-only leaf weights and a -1 norm row for such a field
+    from document_search_engine_b200.scoring import BM25F
+    norm = BM25F().norm_tables(ix)
+    assert (norm[1] == -1.0).all() and (norm[0] > 0).all()
+    # a flat index file keeps the flag (and the stored fields)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        ix2 = FlatIndex.from_documents(docs, ["body", "book"], id_fields=["book"], stored=["book"])
+        ix2.save(os.path.join(d, "ix.npz"))
+        back = FlatIndex.load(os.path.join(d, "ix.npz"))
+        assert back.scorable == [True, False] and back.stored_fields(3) == {"book": "deavf1"}
+        assert np.array_equal(back.docids, ix2.docids) and back.term_id("book", "ss") == ix2.term_id("book", "ss")
+
+
+def test_normalize_like_whoosh():
+    """CompoundQuery.normalize ([W] query/compound.py) as the parser applies it (my_flask.py:189-193): equal
+    subqueries once, nested same-class nodes merged with their boost, null children dropped; ``lower`` itself does
+    not de-duplicate (Searcher.search scores the tree it is given)."""
+    a, b = Term("f", "a"), Term("f", "b")
+    assert And([a, a, b]).normalize() == And([a, b])
+    assert Or([a, Or([b, a], boost=2.0)]).normalize() == Or([a, Term("f", "b", boost=2.0), Term("f", "a", boost=2.0)])
+    assert And([a, NullQuery]).normalize() == a and Or([NullQuery]).normalize() == NullQuery
+    assert And([Or([a], boost=3.0)], boost=2.0).normalize() == Term("f", "a", boost=6.0)
+    assert QueryParser("f").parse("walk Walk home") == And([Term("f", "walk"), Term("f", "home")])
+    leaves, g, kind = lower(And([a, a, b]))
+    assert [(lf.text, lf.group) for lf in leaves] == [("a", 0), ("a", 1), ("b", 2)] and g == 3
+    assert lower(And([a, NullQuery]))[2] == "null" and lower(Or([a, NullQuery]))[1] == 1

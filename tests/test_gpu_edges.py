@@ -3,7 +3,7 @@ terms, extreme weights.  Every case is compared with the oracle."""
 import numpy as np
 import pytest
 
-from document_search_engine_b200 import And, BM25F, Every, FlatIndex, NullQuery, Or, Term
+from document_search_engine_b200 import And, BM25F, Every, FlatIndex, Not, NullQuery, Or, Term
 from document_search_engine_b200 import _ffi
 from document_search_engine_b200.corpus import make_corpus, make_queries
 from oracle.numpy_oracle import NumpyOracle
@@ -102,3 +102,25 @@ def test_bad_arguments_raise():
     with pytest.raises(_ffi.EngineError):
         ix._engine_cache.clear()
         ix.searcher(subtile_docs=100)                                                          # not a multiple of 128
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_non_scorable_field_w15(variant):
+    """W15: terms of a field that is not scorable (the reference's ``book=ID``, my_index.py:152; the UI's book filter
+    writes ``book:xyz`` / ``NOT book:xyz``, static/main.js:5-16) score their posting weight times the boost
+    (Whoosh's WeightScorer): alone, summed with BM25F leaves in And / Or, and as NOT clauses."""
+    rng = np.random.default_rng(7)
+    books = ["ss", "nopr", "deavf1", "tes%d" % 1, "tes%d" % 2]
+    docs = []
+    for d in range(3000):
+        toks = ["w%d" % t for t in rng.zipf(1.3, size=int(rng.integers(5, 60))) if t < 400]
+        docs.append({"body": toks or ["w1"], "book": books[int(rng.integers(0, len(books)))]})
+    ix = FlatIndex.from_documents(docs, ["body", "book"], id_fields=["book"], deleted=[5, 77, 1234])
+    qs = [Term("book", "nopr"), Term("book", "nopr", boost=2.5), Term("book", "none"),
+          Or([Term("book", "ss"), Term("book", "tes1")]),
+          And([Term("body", "w1"), Term("book", "ss")]), And([Term("body", "w2"), Term("body", "w3"), Term("book", "nopr", boost=0.25)]),
+          Or([Term("body", "w5"), Term("book", "deavf1")]),
+          And([Term("body", "w1"), Not(Term("book", "ss"))]), And([Term("body", "w1"), Not(Or([Term("book", "ss"), Term("book", "nopr")]))]),
+          And([Or([Term("body", "w2"), Term("body", "w9")]), Or([Term("book", "tes1"), Term("book", "tes2")])])]
+    for k in (10, 150):
+        check(ix, qs, limit=k, variant=variant)
