@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(512) k_score_topk(ScoreParams p) {
               uint32_t lb;
               if (PACKED) { tf = (float)(pl[e] >> 8); lb = pl[e] & 255u; }
               else { tf = __uint_as_float(pl[e]); lb = (lbs >> (8 * e)) & 255u; }
-              const float s = __fdividef(w * tf, tf + __ldg(nrm + lb));
+              const float nv = __ldg(nrm + lb);
+              const float s = nv < 0.0f ? w * tf : __fdividef(w * tf, tf + nv);   // norm -1: field not scorable, the weight is the score (W15)
               if (!(tf > 0.0f)) {
                 // tf == 0 marks a posting of a deleted document (W9): not a match
               } else if (simple_or) {
@@ -768,7 +769,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
             else { tf = __uint_as_float(pl); lb = sl[i]; }
             if (tf > 0.0f) {                                    // tf == 0 marks a deleted document (W9)
               slot = sd[i] - m.t0;
-              const float s = __fdividef(w * tf, tf + nrm[lb]);
+              const float nv = nrm[lb];
+              const float s = nv < 0.0f ? w * tf : __fdividef(w * tf, tf + nv);   // norm -1: field not scorable (W15)
               const float old = acc[slot];
               const float nw = old + s;
               acc[slot] = nw;
@@ -805,7 +807,8 @@ __global__ void __launch_bounds__(544) k_score_pipe(PipeParams pp) {
               if (PACKED) { tf = (float)(pl >> 8); lb = pl & 255u; }
               else { tf = __uint_as_float(pl); lb = sl[i]; }
               if (tf > 0.0f) {
-                const float s = __fdividef(w * tf, tf + nrm[lb]);
+                const float nv = nrm[lb];
+              const float s = nv < 0.0f ? w * tf : __fdividef(w * tf, tf + nv);   // norm -1: field not scorable (W15)
                 const float old = acc[slot];
                 const float nw = old + s;
                 acc[slot] = nw;
