@@ -125,6 +125,7 @@ class FlatIndex:
             raise ValueError("scorable must have one entry per field")
         self.schema = Schema(self.field_names, stored=self._stored_names())
         self._engine_cache = {}
+        self._lexicons = {}
         self._engine_cache_lock = threading.Lock()
 
     # ---- Whoosh Index surface -------------------------------------------------
@@ -181,6 +182,19 @@ class FlatIndex:
     def is_scorable(self, fieldname) -> bool:
         f = self.field_index(fieldname)
         return f < 0 or self.scorable[f]
+
+    def lexicon(self, fieldname) -> List[str]:
+        """The words of a field, sorted (what Whoosh's ``reader.lexicon(fieldname)`` iterates): the expansion
+        domain of ``Prefix`` / ``Wildcard`` queries.  Needs a string vocabulary."""
+        f = self.field_index(fieldname)
+        if f < 0:
+            return []
+        lex = self._lexicons.get(f)
+        if lex is None:
+            if self.terms is None:
+                raise NotImplementedError("pattern queries need a string vocabulary (this index numbers its terms)")
+            lex = self._lexicons[f] = sorted(t for (ff, t) in self.terms if ff == f and isinstance(t, str))
+        return lex
 
     def field_length(self, fieldname) -> int:
         f = self.field_index(fieldname)

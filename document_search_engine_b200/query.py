@@ -208,6 +208,125 @@ class And(_Compound):
     JOINT = " AND "
 
 
+class MultiTerm(Query):
+    """``Prefix`` / ``Wildcard`` (the reference's UI documents ``book:tes?``, ``search-form.html:20-40``; Whoosh
+    ``query/terms.py``).  [W] ``MultiTerm.matcher`` expands the pattern over the field's lexicon, in lexicon order,
+    into ``Or([Term(field, word), ...], boost=self.boost)`` - a single matching word becomes its plain ``Term``
+    matcher (the boost is NOT applied in that case), none a NullMatcher - and although pattern queries ask for a
+    constant score, ``Searcher.postings`` falls back to the searcher's weighting, so the expansion is scored by BM25F
+    like any other ``Or``.  The engine does the same rewrite on the host (``expand_multiterms``) and scores the
+    ``Or`` on the flat-OR kernels."""
+
+    def __init__(self, fieldname: str, text: str, boost: float = 1.0):
+        self.fieldname = fieldname
+        self.text = text
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return (type(other) is type(self) and other.fieldname == self.fieldname and other.text == self.text
+                and other.boost == self.boost)
+
+    def __hash__(self):
+        return hash((type(self).__name__, self.fieldname, self.text, self.boost))
+
+    def __repr__(self):
+        return "%s(%r, %r%s)" % (type(self).__name__, self.fieldname, self.text, "" if self.boost == 1.0 else ", boost=%s" % self.boost)
+
+    def leaves(self):
+        return iter(())
+
+    def matches(self, word: str) -> bool:
+        raise NotImplementedError
+
+    def literal_prefix(self) -> str:
+        """Every matching word starts with this (narrows the scan of the sorted lexicon)."""
+        raise NotImplementedError
+
+    def expand(self, lexicon: Sequence[str]) -> Query:
+        """``lexicon``: the field's words, sorted."""
+        from bisect import bisect_left
+        pre = self.literal_prefix()
+        words = []
+        for i in range(bisect_left(lexicon, pre), len(lexicon)):
+            w = lexicon[i]
+            if not w.startswith(pre):
+                break
+            if self.matches(w):
+                words.append(w)
+        if not words:
+            return NullQuery
+        if len(words) == 1:
+            return Term(self.fieldname, words[0])                 # Whoosh drops the pattern's boost here
+        return Or([Term(self.fieldname, w) for w in words], boost=self.boost)
+
+
+class Prefix(MultiTerm):
+    def __str__(self):
+        return "%s:%s*" % (self.fieldname, self.text)
+
+    def matches(self, word):
+        return word.startswith(self.text)
+
+    def literal_prefix(self):
+        return self.text
+
+
+class Wildcard(MultiTerm):
+    """``?`` one character, ``*`` any run, ``[...]`` a character class (fnmatch rules, as Whoosh)."""
+    SPECIAL_CHARS = frozenset("*?[")
+
+    def __str__(self):
+        return "%s:%s" % (self.fieldname, self.text)
+
+    def _regex(self):
+        r = self.__dict__.get("_rx")
+        if r is None:
+            import fnmatch
+            r = self.__dict__["_rx"] = re.compile(fnmatch.translate(self.text))
+        return r
+
+    def matches(self, word):
+        return self._regex().match(word) is not None
+
+    def literal_prefix(self):
+        for i, ch in enumerate(self.text):
+            if ch in self.SPECIAL_CHARS:
+                return self.text[:i]
+        return self.text
+
+    def normalize(self):
+        # [W] Wildcard.normalize: no special character -> Term; "*" -> Every; one trailing "*" -> Prefix
+        text = self.text
+        if text == "*":
+            return Every(self.fieldname, boost=self.boost)
+        if not any(ch in self.SPECIAL_CHARS for ch in text):
+            return Term(self.fieldname, text, boost=self.boost)
+        if text.endswith("*") and not any(ch in self.SPECIAL_CHARS for ch in text[:-1]):
+            return Prefix(self.fieldname, text[:-1], boost=self.boost)
+        return self
+
+
+def has_multiterm(q: Query) -> bool:
+    if isinstance(q, MultiTerm):
+        return True
+    if isinstance(q, _Compound):
+        return any(has_multiterm(s) for s in q.subqueries)
+    if isinstance(q, Not):
+        return has_multiterm(q.query)
+    return False
+
+
+def expand_multiterms(q: Query, lexicon_of) -> Query:
+    """Replace every ``Prefix`` / ``Wildcard`` node by its expansion; ``lexicon_of(fieldname)`` -> sorted words."""
+    if isinstance(q, MultiTerm):
+        return q.expand(lexicon_of(q.fieldname))
+    if isinstance(q, _Compound):
+        return type(q)([expand_multiterms(s, lexicon_of) for s in q.subqueries], boost=q.boost)
+    if isinstance(q, Not):
+        return Not(expand_multiterms(q.query, lexicon_of))
+    return q
+
+
 class Or(_Compound):
     JOINT = " OR "
 
@@ -254,6 +373,8 @@ def _with_boost(q: Query, boost: float) -> Query:
         return Every(q.fieldname, boost=boost)
     if isinstance(q, _Compound):
         return type(q)(q.subqueries, boost=boost)
+    if isinstance(q, MultiTerm):
+        return type(q)(q.fieldname, q.text, boost=boost)
     return q                     # Not / Null carry no score
 
 
@@ -371,6 +492,11 @@ class QueryParser:
                 nodes.append(tok)
                 continue
             field = field or self.fieldname
+            if any(ch in Wildcard.SPECIAL_CHARS for ch in tok):
+                # Whoosh's WildcardPlugin: the pattern is not analysed (lower-cased only)
+                known = self.schema is None or not hasattr(self.schema, "names") or field in self.schema.names()
+                nodes.append(Wildcard(field if known else self.fieldname, tok.lower() if known else "%s:%s" % (field, tok.lower())).normalize())
+                continue
             if self.schema is not None and hasattr(self.schema, "names") and field not in self.schema.names():
                 tok, field = "%s:%s" % (field, tok), self.fieldname
             terms = [self.termclass(field, t) for t in self.analyzer(field, tok)]

@@ -21,12 +21,13 @@ import gc
 import struct
 import time
 from math import ceil, log
+from collections.abc import Sequence as _SequenceABC
 from typing import Iterable, List, Optional, Sequence
 
 import numpy as np
 
 from . import _ffi
-from .query import And, Or, Query, Term, UnsupportedQuery, lower
+from .query import And, Or, Query, Term, UnsupportedQuery, expand_multiterms, has_multiterm, lower
 from .scoring import BM25F, instantiate
 
 #: one lowered leaf as ``Searcher.pack`` keeps it: posting-list id (or -1 / -2 - field), boost, group
@@ -91,10 +92,13 @@ class Hit:
 class Results:
     """Scored top-N plus the exact match count (``len(results)``, W13)."""
 
-    def __init__(self, searcher: "Searcher", q: Query, top_n, total: int, runtime: float = 0.0):
+    def __init__(self, searcher: "Searcher", q: Query, top_n, total: int, runtime: float = 0.0, rows=None):
         self.searcher = searcher
         self.q = q
-        self.top_n = list(top_n)             # [(score, docnum)] in W11 order
+        #: ``[(score, docnum)]`` in W11 order; built on first use from the engine's result rows when the batch
+        #: entry made this object (``rows = (scores row, docids row, count)``)
+        self._top_n = None if top_n is None else list(top_n)
+        self._rows = rows
         self._total = int(total)
         self.runtime = runtime
         # settable presentation hooks the reference assigns (my_flask.py:349-352)
@@ -102,6 +106,18 @@ class Results:
         self.order = None
         self.scorer = None
         self.formatter = None
+
+    @property
+    def top_n(self):
+        t = self._top_n
+        if t is None:
+            sc, dc, n = self._rows
+            t = self._top_n = list(zip(sc[:n].tolist(), dc[:n].tolist()))
+        return t
+
+    @top_n.setter
+    def top_n(self, value):
+        self._top_n = list(value)
 
     def __len__(self):
         return self._total
@@ -149,6 +165,40 @@ class Results:
     def __iter__(self):
         for i in range(len(self.top_n)):
             yield Hit(self, self.top_n[i][1], i, self.top_n[i][0])
+
+
+class BatchResults(_SequenceABC):
+    """What ``search_batch`` returns: a read-only sequence of ``Results``, one per query, over the engine's result
+    arrays.  A ``Results`` object is built when its position is read (a 10k-query batch is returned in the time
+    the GPU needs, not in the time Python needs to make 10k objects)."""
+
+    def __init__(self, searcher, queries, scores, docids, counts, totals, runtime):
+        self.searcher, self.queries = searcher, queries
+        self.scores, self.docids, self.counts, self.totals = scores, docids, counts, totals
+        self.runtime = runtime
+        self._made = {}
+
+    def __len__(self):
+        return len(self.queries)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self.queries)))]
+        if i < 0:
+            i += len(self.queries)
+        if not 0 <= i < len(self.queries):
+            raise IndexError(i)
+        r = self._made.get(i)
+        if r is None:
+            r = self._made[i] = Results(self.searcher, self.queries[i], None, int(self.totals[i]), runtime=self.runtime,
+                                        rows=(self.scores[i], self.docids[i], int(self.counts[i])))
+        return r
+
+    def __eq__(self, other):
+        return list(self) == list(other)
+
+    def __repr__(self):
+        return "<BatchResults of %d queries>" % len(self.queries)
 
 
 class ResultsPage:
@@ -308,6 +358,10 @@ class Searcher:
             leaves = [(ix.term_id(t.fieldname, t.text), t.boost * qb, i if conj else 0) for i, t in enumerate(q.subqueries)]
             g = len(leaves) if conj else 1
         else:
+            if has_multiterm(q):
+                # Prefix / Wildcard: Whoosh's MultiTerm.matcher expands the pattern over the field's lexicon into an
+                # Or of Terms (reference UI: book:tes?, search-form.html:20-40); same rewrite here, on the host
+                q = expand_multiterms(q, ix.lexicon)
             low, g, kind = lower(q)
             if kind == "every":
                 # Whoosh's Every(field): every live document that has the field, constant score = boost
@@ -455,6 +509,10 @@ class Searcher:
             dt = time.perf_counter() - t_start
             return [Results(self, queries[i], list(zip(final[i, :int(counts[i])].tolist(), docids[i, :int(counts[i])].tolist())),
                             int(tot[i]), runtime=dt) for i in range(nq)]
+        if limit is not None and limit <= _ffi.MAX_K:
+            # one pass serves every query: the per-query Results are made when somebody looks at them
+            scores, docids, counts, tot = self._run_packed(self.pack(queries), limit)
+            return BatchResults(self, queries, scores, docids, counts, tot, time.perf_counter() - t_start)
         want = [limit if limit is not None else None] * nq
         tops: List[list] = [[] for _ in range(nq)]
         totals = np.zeros(nq, dtype=np.uint64)

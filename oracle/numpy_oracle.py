@@ -23,7 +23,15 @@ B2L_SCORING = B2L.copy()
 B2L_SCORING[0] = 1.0            # W5: byte 0 → default length 1
 
 
-def lower_query(q):
+def _expand(q, ix):
+    """Prefix / Wildcard -> the words of the field's lexicon that fit, in lexicon order (Whoosh MultiTerm.matcher)."""
+    import fnmatch
+    f = ix.field_names.index(q.fieldname) if q.fieldname in ix.field_names else -1
+    fits = (lambda w: w.startswith(q.text)) if type(q).__name__ == "Prefix" else (lambda w: fnmatch.fnmatchcase(w, q.text))
+    return sorted(t for (ff, t) in (ix.terms or {}) if ff == f and isinstance(t, str) and fits(t))
+
+
+def lower_query(q, ix=None):
     """``(groups, negatives, kind)``: ``groups`` is a list of OR-groups, each a list of
     ``(fieldname, text, boost)``; all groups must match (W10) and no leaf of ``negatives``
     (``(fieldname, text)`` from Not children, Whoosh's AndNotMatcher) may."""
@@ -34,10 +42,24 @@ def lower_query(q):
         return [[(q.fieldname, None, q.boost)]], [], "every"
     if name == "Term":
         return [[(q.fieldname, q.text, q.boost)]], [], "groups"
+    if name in ("Prefix", "Wildcard"):
+        words = _expand(q, ix)
+        if not words:
+            return [], [], "null"
+        boost = 1.0 if len(words) == 1 else q.boost               # a single word: its plain term matcher, no boost
+        return [[(q.fieldname, w, boost) for w in words]], [], "groups"
     if name in ("Or", "And"):
         groups, flat, neg = [], [], []
         for s in q.subqueries:
             sn = type(s).__name__
+            if sn in ("Prefix", "Wildcard"):
+                words = _expand(s, ix)
+                b = (1.0 if len(words) == 1 else s.boost) * q.boost
+                if name == "And":
+                    groups.append([(s.fieldname, w, b) for w in words])      # no word: an empty group, nothing matches
+                else:
+                    flat.extend((s.fieldname, w, b) for w in words)
+                continue
             if sn == "Term":
                 (groups if name == "And" else flat).append(
                     [(s.fieldname, s.text, s.boost * q.boost)] if name == "And" else (s.fieldname, s.text, s.boost * q.boost))
@@ -45,7 +67,11 @@ def lower_query(q):
                 groups.append([(t.fieldname, t.text, t.boost * s.boost * q.boost) for t in s.subqueries])
             elif sn == "Not":
                 inner = s.query.subqueries if type(s.query).__name__ == "Or" else [s.query]
-                neg.extend((t.fieldname, t.text) for t in inner)
+                for t in inner:
+                    if type(t).__name__ in ("Prefix", "Wildcard"):
+                        neg.extend((t.fieldname, w) for w in _expand(t, ix))
+                    else:
+                        neg.append((t.fieldname, t.text))
             else:
                 raise NotImplementedError(s)
         if flat:
@@ -102,7 +128,7 @@ class NumpyOracle:
 
     def match_all(self, q):
         """All matches as (global docids ascending, float64 scores)."""
-        groups, negatives, kind = lower_query(q)
+        groups, negatives, kind = lower_query(q, self.ix)
         if kind == "null":
             return np.zeros(0, np.int64), np.zeros(0, np.float64)
         ds, ss = [], []

@@ -159,9 +159,40 @@ class OracleSearcher:
                 if notm.is_active():
                     m = AndNotMatcher(m, notm)
             return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
+        if name in ("Prefix", "Wildcard"):
+            # Whoosh query/terms.py MultiTerm.matcher: the words of the field's lexicon that fit the pattern, in
+            # lexicon order; none -> NullMatcher, one -> that term's matcher (without the pattern's boost), else the
+            # Or of the terms with the pattern's boost.  Scored by the searcher's weighting (Searcher.postings falls
+            # back to it although pattern queries ask for a constant score).
+            f = sub.field_names.index(q.fieldname) if q.fieldname in sub.field_names else -1
+            words = sorted(t for (ff, t) in (sub.terms or {}) if ff == f and isinstance(t, str) and _pattern_fits(q, t))
+            ms = [self._matcher(_T(q.fieldname, w), sub) for w in words]
+            if not ms:
+                return NullMatcher()
+            if len(ms) == 1:
+                return ms[0]
+            m = _binary_tree(UnionMatcher, ms)
+            return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
         if name == "_Null":
             return NullMatcher()
         raise NotImplementedError(name)
+
+
+class _T:
+    """A plain term (duck-typed like the engine's ``Term``) for expansions."""
+
+    def __init__(self, fieldname, text, boost=1.0):
+        self.fieldname, self.text, self.boost = fieldname, text, boost
+
+
+_T.__name__ = "Term"
+
+
+def _pattern_fits(q, word):
+    if type(q).__name__ == "Prefix":
+        return word.startswith(q.text)
+    import fnmatch
+    return fnmatch.fnmatchcase(word, q.text)
 
 
 def _binary_tree(cls, ms):

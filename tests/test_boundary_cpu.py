@@ -8,8 +8,8 @@ import numpy as np
 import pytest
 
 from document_search_engine_b200 import _ffi
-from document_search_engine_b200 import And, FlatIndex, Or, Term
-from document_search_engine_b200.query import Not, NullQuery, QueryParser, lower
+from document_search_engine_b200 import And, FlatIndex, Or, Prefix, Term, Wildcard
+from document_search_engine_b200.query import Not, NullQuery, QueryParser, expand_multiterms, lower
 from document_search_engine_b200.variants import Variants, expand_with_map
 from oracle.numpy_oracle import NumpyOracle
 from oracle.whoosh_port import OracleSearcher
@@ -171,3 +171,40 @@ def test_normalize_like_whoosh():
     leaves, g, kind = lower(And([a, a, b]))
     assert [(lf.text, lf.group) for lf in leaves] == [("a", 0), ("a", 1), ("b", 2)] and g == 3
     assert lower(And([a, NullQuery]))[2] == "null" and lower(Or([a, NullQuery]))[1] == 1
+
+
+def _books_index():
+    rng = np.random.default_rng(11)
+    books = ["ss", "nopr", "deavf1", "deavf2", "tes1", "tes2", "tes9", "test", "tps"]
+    docs = []
+    for d in range(400):
+        toks = ["w%d" % t for t in rng.zipf(1.4, size=int(rng.integers(4, 40))) if t < 200] or ["w1"]
+        docs.append({"body": toks, "book": books[int(rng.integers(0, len(books)))]})
+    return FlatIndex.from_documents(docs, ["body", "book"], id_fields=["book"])
+
+
+PATTERN_QUERIES = [Wildcard("book", "tes?"), Prefix("book", "dea"), Wildcard("book", "t*s"), Wildcard("book", "x*"),
+                   Wildcard("book", "tes[12]", boost=3.0), Prefix("book", "nop", boost=3.0), Prefix("body", "w1"),
+                   And([Term("body", "w1"), Wildcard("book", "tes?")]), And([Term("body", "w2"), Not(Prefix("book", "dea"))]),
+                   Or([Term("body", "w3"), Prefix("book", "t", boost=0.5)]), And([Prefix("body", "w19"), Wildcard("book", "q?")])]
+
+
+def test_pattern_queries_f3():
+    """Prefix / Wildcard (reference UI ``book:tes?``, search-form.html:20-40): expansion over the field's lexicon in
+    lexicon order, one word -> plain Term without the pattern's boost, none -> nothing ([W] MultiTerm.matcher); the
+    two oracles expand independently of the engine's host rewrite and must agree with each other and with it."""
+    ix = _books_index()
+    assert ix.lexicon("book") == sorted(["ss", "nopr", "deavf1", "deavf2", "tes1", "tes2", "tes9", "test", "tps"])
+    assert str(expand_multiterms(Wildcard("book", "tes?"), ix.lexicon)) == "(book:tes1 OR book:tes2 OR book:tes9 OR book:test)"
+    assert expand_multiterms(Prefix("book", "nop", boost=3.0), ix.lexicon) == Term("book", "nopr")
+    assert expand_multiterms(Wildcard("book", "x*"), ix.lexicon) == NullQuery
+    assert QueryParser("body").parse("w1 book:tes? NOT book:dea*") == And([Term("body", "w1"), Wildcard("book", "tes?"), Not(Prefix("book", "dea"))])
+    a, b = OracleSearcher(ix), NumpyOracle(ix)
+    for q in PATTERN_QUERIES:
+        ta, na = a.search(q, limit=None)
+        tb, nb = b.search(q, limit=None)
+        assert na == nb and [d for _, d in ta] == [d for _, d in tb], q
+        assert [s for s, _ in ta] == pytest.approx([s for s, _ in tb], rel=1e-12), q
+        # ... and with the expansion done by the engine's host code, scored as a plain tree
+        te, ne = a.search(expand_multiterms(q, ix.lexicon), limit=None)
+        assert ne == na and [d for _, d in te] == [d for _, d in ta], q

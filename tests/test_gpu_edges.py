@@ -124,3 +124,11 @@ def test_non_scorable_field_w15(variant):
           And([Or([Term("body", "w2"), Term("body", "w9")]), Or([Term("book", "tes1"), Term("book", "tes2")])])]
     for k in (10, 150):
         check(ix, qs, limit=k, variant=variant)
+
+
+def test_pattern_queries_f3():
+    """Prefix / Wildcard on the device path: the host expands them into Or-of-Terms, the flat-OR / group kernels score them."""
+    from tests.test_boundary_cpu import PATTERN_QUERIES, _books_index
+    ix = _books_index()
+    for variant in (0, 5):
+        check(ix, PATTERN_QUERIES, variant=variant)
