@@ -126,6 +126,8 @@ class FlatIndex:
         self.schema = Schema(self.field_names, stored=self._stored_names())
         self._engine_cache = {}
         self._lexicons = {}
+        self._forward = {}
+        self._text_of = None
         self._engine_cache_lock = threading.Lock()
 
     # ---- Whoosh Index surface -------------------------------------------------
@@ -195,6 +197,42 @@ class FlatIndex:
                 raise NotImplementedError("pattern queries need a string vocabulary (this index numbers its terms)")
             lex = self._lexicons[f] = sorted(t for (ff, t) in self.terms if ff == f and isinstance(t, str))
         return lex
+
+    def doc_terms(self, docnum: int, fieldname) -> List[Tuple[object, float]]:
+        """``[(text, weight)]`` of one document in one field: its term vector as Whoosh's ``Expander.add_document``
+        reads it (``searcher.key_terms([docnum], field)``, reference ``my_index.py:100``).  Served from a
+        per-field forward map (the posting store transposed once, on first use)."""
+        f = self.field_index(fieldname)
+        if f < 0:
+            return []
+        fw = self._forward.get(f)
+        if fw is None:
+            tids = np.nonzero(self.term_field == f)[0]
+            if tids.size == 0:
+                fw = (np.zeros(self.n_docs_all + 1, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32))
+            else:
+                a, b = int(self.term_offsets[tids[0]]), int(self.term_offsets[tids[-1] + 1])
+                if not (np.diff(tids) == 1).all():
+                    raise NotImplementedError("the posting lists of a field must be contiguous")
+                lens = np.diff(self.term_offsets[tids[0]:tids[-1] + 2].astype(np.int64))
+                term_of = np.repeat(tids, lens)
+                d = self.docids[a:b].astype(np.int64)
+                order = np.argsort(d, kind="stable")
+                starts = np.zeros(self.n_docs_all + 1, np.int64)
+                np.cumsum(np.bincount(d, minlength=self.n_docs_all), out=starts[1:])
+                fw = (starts, term_of[order], self.tfs[a:b][order])
+            self._forward[f] = fw
+            if self.terms is not None and self._text_of is None:
+                self._text_of = {tid: t for (ff, t), tid in self.terms.items()}
+        starts, term_of, w = fw
+        local = docnum - self.doc_base
+        lo, hi = int(starts[local]), int(starts[local + 1])
+        text = (lambda tid: self._text_of[tid]) if self.terms is not None else (lambda tid: tid - f * self.vocab_size)
+        return [(text(int(t)), float(x)) for t, x in zip(term_of[lo:hi], w[lo:hi])]
+
+    def term_frequency(self, fieldname, text) -> float:
+        """Whoosh ``reader.frequency``: the total weight of the term in the collection."""
+        return self.reader().frequency(fieldname, text)
 
     def field_length(self, fieldname) -> int:
         f = self.field_index(fieldname)

@@ -542,6 +542,80 @@ class Searcher:
         dt = time.perf_counter() - t_start
         return [Results(self, queries[i], tops[i], int(totals[i]), runtime=dt) for i in range(nq)]
 
+    # -- key terms / more-like-this (reference my_flask.py:428-446, my_index.py:100) -------------------------------
+    def key_terms_from_text(self, fieldname, text, numterms=5, normalize=True):
+        """``[(word, weight)]``: the terms of ``text`` (a token list, or a string split on whitespace: analysis is the
+        caller's) that best tell it from the collection, by Whoosh's default Bo1 model
+        (``classify.Expander`` / ``Bo1Model`` [W])."""
+        toks = text.split() if isinstance(text, str) else list(text)
+        return self._expanded_terms(fieldname, [(t, 1.0) for t in toks], numterms, normalize)
+
+    def key_terms(self, docnums, fieldname, numterms=5, normalize=True):
+        """The same for the term vectors of the given documents (``s.key_terms([doc], field, numterms=10)``,
+        reference ``my_index.py:100``)."""
+        vec = []
+        for d in docnums:
+            vec.extend(self.stats_ix.doc_terms(d, fieldname))
+        return self._expanded_terms(fieldname, vec, numterms, normalize)
+
+    def _expanded_terms(self, fieldname, vector, numterms, normalize):
+        sx = self.stats_ix
+        top_total, top_weight = 0.0, {}
+        for word, weight in vector:
+            top_total += weight
+            top_weight[word] = top_weight.get(word, 0.0) + weight
+        if not top_weight:
+            return []
+        N = float(sx.doc_count_all())
+        tlist, maxweight = [], 0.0
+        for word, weight in top_weight.items():
+            if sx.term_id(fieldname, word) < 0:
+                continue
+            f = sx.term_frequency(fieldname, word) / N
+            score = weight * log((1.0 + f) / f, 2) + log(1.0 + f, 2)         # Bo1Model.score
+            maxweight = max(maxweight, score)
+            tlist.append((score, word))
+        if not tlist:
+            return []
+        if normalize:
+            f = maxweight / N
+            norm = (maxweight * log((1.0 + f) / f) + log(1.0 + f)) / log(2.0)  # Bo1Model.normalizer
+        else:
+            norm = maxweight
+        tlist = [(weight / norm, t) for weight, t in tlist]
+        tlist.sort(key=lambda x: (0 - x[0], x[1]))
+        return [(t, weight) for weight, t in tlist[:numterms]]
+
+    def more_like(self, docnum, fieldname, text=None, top=10, numterms=5, normalize=True):
+        """Whoosh ``Searcher.more_like`` (reference ``my_flask.py:431-434``: ``more_like(docnum | None, 'exact', text=...,
+        top=5)``): the key terms of ``text`` (or of document ``docnum``) become an ``Or`` of boosted terms, scored on
+        the GPU like any other query; document ``docnum`` itself is masked out of the hits and of the total."""
+        if text:
+            kts = self.key_terms_from_text(fieldname, text, numterms=numterms, normalize=normalize)
+        else:
+            kts = self.key_terms([docnum], fieldname, numterms=numterms, normalize=normalize)
+        q = Or([Term(fieldname, word, boost=weight) for word, weight in kts])
+        if not kts:
+            return Results(self, q, [], 0)
+        r = self.search(q, limit=top + (0 if docnum is None else 1))
+        if docnum is not None:
+            masked = any(t == docnum for t in (d for _, d in r.top_n))
+            hits = [(s, d) for s, d in r.top_n if d != docnum][:top]
+            sx = self.stats_ix
+            in_mask = masked or any(self._doc_has_term(sx, docnum, fieldname, w) for w, _ in kts)
+            return Results(self, q, hits, len(r) - (1 if in_mask else 0), runtime=r.runtime)
+        return r
+
+    @staticmethod
+    def _doc_has_term(ix, docnum, fieldname, word) -> bool:
+        tid = ix.term_id(fieldname, word)
+        if tid < 0:
+            return False
+        d, _ = ix.postings(tid)
+        i = int(np.searchsorted(d, docnum - ix.doc_base))
+        live = ix.deleted is None or not ix.deleted[docnum - ix.doc_base]
+        return i < d.size and int(d[i]) == docnum - ix.doc_base and live
+
     def search(self, q: Query, limit: Optional[int] = 10, **kwargs) -> Results:
         if limit is not None and limit < 1:
             raise ValueError("limit must be >= 1")

@@ -119,6 +119,47 @@ class OracleSearcher:
         items.sort(reverse=True)                                # score desc, docnum asc
         return [(s, -nd) for s, nd in items], total
 
+    # -- key terms / more-like-this (Whoosh classify.py Expander + Bo1Model, searching.py more_like) ------------
+    def key_terms(self, vector, fieldname, numterms=5, normalize=True):
+        """``vector``: iterable of (word, weight) - the text's tokens with weight 1, or a document's term vector."""
+        ix = self.ix
+        N = float(ix.doc_count_all())
+        top = {}
+        for word, weight in vector:
+            top[word] = top.get(word, 0) + weight
+        tlist, maxweight = [], 0
+        for word, weight in top.items():
+            tid = ix.term_id(fieldname, word)
+            if tid < 0:
+                continue
+            a, b = int(ix.term_offsets[tid]), int(ix.term_offsets[tid + 1])
+            cf = float(sum(ix.tfs[a:b].tolist()))                  # reader.frequency: total weight in the collection
+            f = cf / N
+            score = weight * log((1.0 + f) / f, 2) + log(1.0 + f, 2)
+            if score > maxweight:
+                maxweight = score
+            tlist.append((score, word))
+        if not tlist:
+            return []
+        if normalize:
+            f = maxweight / N
+            norm = (maxweight * log((1.0 + f) / f) + log(1.0 + f)) / log(2.0)
+        else:
+            norm = maxweight
+        tlist = [(weight / norm, t) for weight, t in tlist]
+        tlist.sort(key=lambda x: (0 - x[0], x[1]))
+        return [(t, weight) for weight, t in tlist[:numterms]]
+
+    def more_like(self, docnum, fieldname, vector, top=10, numterms=5):
+        """``Or`` of the key terms with their weights as boosts, document ``docnum`` masked (never collected)."""
+        kts = self.key_terms(vector, fieldname, numterms=numterms)
+        if not kts:
+            return [], 0
+        q = _O([_T(fieldname, w, boost=wt) for w, wt in kts])
+        hits, total = self.search(q, limit=None)
+        keep = [(s, d) for s, d in hits if d != docnum]
+        return keep[:top], len(keep)
+
     def _matcher(self, q, sub):
         name = type(q).__name__
         if name == "Term":
@@ -186,6 +227,14 @@ class _T:
 
 
 _T.__name__ = "Term"
+
+
+class _O:
+    def __init__(self, subqueries, boost=1.0):
+        self.subqueries, self.boost = subqueries, boost
+
+
+_O.__name__ = "Or"
 
 
 def _pattern_fits(q, word):

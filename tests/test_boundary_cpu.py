@@ -208,3 +208,36 @@ def test_pattern_queries_f3():
         # ... and with the expansion done by the engine's host code, scored as a plain tree
         te, ne = a.search(expand_multiterms(q, ix.lexicon), limit=None)
         assert ne == na and [d for _, d in te] == [d for _, d in ta], q
+
+
+class _HostOnlySearcher(object):
+    """The host half of Searcher (no engine): enough for the key-term arithmetic."""
+
+    def __new__(cls, ix):
+        from document_search_engine_b200.searching import Searcher
+        s = object.__new__(Searcher)
+        s.ix = s.stats_ix = ix
+        return s
+
+
+def test_key_terms_f4():
+    """searcher.key_terms / key_terms_from_text (reference my_index.py:100, my_flask.py:431-434): Whoosh's Bo1 expansion
+    model, the engine's host code against the oracle's restatement; ties broken by the word, weights normalised."""
+    ix = _books_index()
+    s, o = _HostOnlySearcher(ix), OracleSearcher(ix)
+    text = "w1 w7 w7 w150 w3 nosuchword w7 w9"
+    got = s.key_terms_from_text("body", text, numterms=4)
+    want = o.key_terms([(t, 1) for t in text.split()], "body", numterms=4)
+    assert [w for w, _ in got] == [w for w, _ in want] and len(got) == 4
+    assert [x for _, x in got] == pytest.approx([x for _, x in want], rel=1e-12)
+    assert got[0][1] > got[-1][1] > 0 and got[0][1] <= 1.0 + 1e-12
+    assert "nosuchword" not in [w for w, _ in s.key_terms_from_text("body", text, numterms=50)]
+    # from a document's term vector
+    d = 17
+    vec = ix.doc_terms(d, "body")
+    assert sorted(w for w, _ in vec) == sorted(set(t for t in ["w%d" % i for i in range(200)] if ix.term_id("body", t) >= 0
+                                                   and d in ix.postings(ix.term_id("body", t))[0].tolist()))
+    got = s.key_terms([d], "body", numterms=10)
+    want = o.key_terms(vec, "body", numterms=10)
+    assert got == [(w, pytest.approx(x, rel=1e-12)) for w, x in want]
+    assert s.key_terms_from_text("body", "", numterms=3) == [] and s.key_terms_from_text("nofield", "w1") == []

@@ -132,3 +132,21 @@ def test_pattern_queries_f3():
     ix = _books_index()
     for variant in (0, 5):
         check(ix, PATTERN_QUERIES, variant=variant)
+
+
+def test_more_like_f4():
+    """searcher.more_like(docnum, field, text=..., top=5) (reference my_flask.py:431-434): key terms -> boosted Or on
+    the GPU, the document itself masked out; against the oracle's more_like."""
+    from oracle.whoosh_port import OracleSearcher
+    from tests.test_boundary_cpu import _books_index
+    ix = _books_index()
+    o = OracleSearcher(ix)
+    with ix.searcher() as s:
+        for docnum, text in ((17, None), (3, "w1 w7 w7 w150 w3 w9"), (None, "w2 w2 w5 w11"), (250, "nosuchword")):
+            r = s.more_like(docnum, "body", text=text, top=5)
+            vec = [(t, 1) for t in text.split()] if text else ix.doc_terms(docnum, "body")
+            want_top, want_total = o.more_like(docnum, "body", vec, top=5)
+            assert len(r) == want_total and [d for _, d in r.top_n] == [d for _, d in want_top]
+            assert [x for x, _ in r.top_n] == pytest.approx([x for x, _ in want_top], rel=1e-5)
+            assert docnum not in [h.docnum for h in r]
+    ix._engine_cache.clear()

@@ -133,3 +133,20 @@ def test_golden_fixtures_match_whoosh(tmp_path, path):
         got_top, got_total = whoosh_search(wix, q, c["k"], **kw)
         assert got_total == want["total"] and [d for _, d in got_top] == [d for _, d in want["top"]]
         assert [s for s, _ in got_top] == pytest.approx([s for s, _ in want["top"]], rel=1e-12)
+
+
+def test_flattener_on_a_real_index(tmp_path):
+    """flatten_index over Whoosh's own reader gives the arrays FlatIndex.from_documents builds from the same tokens."""
+    from document_search_engine_b200.flatten import flatten_index
+    docs = [{"body": ("w%d w%d w1" % (d % 13, d % 7)).split() * (1 + d % 3), "book": ["ss", "nopr", "tes1"][d % 3]} for d in range(120)]
+    wix = whoosh_index(tmp_path, docs, id_fields=["book"], deleted=[5, 6])
+    flat = flatten_index(wix, fields=["body", "book"])
+    ref = FlatIndex.from_documents(docs, ["body", "book"], id_fields=["book"], deleted=[5, 6])
+    assert flat.scorable == ref.scorable and np.array_equal(flat.len_bytes, ref.len_bytes)
+    assert np.array_equal(flat.field_length_total, ref.field_length_total) and np.array_equal(flat.deleted, ref.deleted)
+    for (f, t), tid in ref.terms.items():
+        ftid = flat.term_id(ref.field_names[f], t)
+        assert ftid >= 0 and flat.df[ftid] == ref.df[tid]
+        assert np.array_equal(flat.postings(ftid)[0], ref.postings(tid)[0]) and np.array_equal(flat.postings(ftid)[1], ref.postings(tid)[1])
+    for q in (Term("body", "w1"), And([Term("body", "w2"), Not(Term("book", "ss"))]), Or([Term("body", "w3"), Term("book", "tes1")])):
+        assert_same(OracleSearcher(flat).search(q, limit=10), whoosh_search(wix, q, 10), "flattened %s" % q)
