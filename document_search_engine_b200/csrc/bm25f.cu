@@ -178,6 +178,25 @@ __global__ void k_impacts(const uint32_t* __restrict__ docids, const uint32_t* _
   }
 }
 
+// The caller's promise about the posting lists (include/bm25f.h: docids < n_docs_all, ascending inside a list) is
+// checked once at upload: an out-of-range docid would index the length bytes, the deleted flags and the kernels'
+// accumulators out of bounds.  flag[0] = 1 + the first offending list (the smallest such list wins).
+__global__ void k_check_docids(const uint32_t* __restrict__ docids, const unsigned long long* __restrict__ offs,
+                               unsigned long long n_terms, uint32_t n_docs, unsigned long long* __restrict__ flag) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long t = (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long stride = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (; t < n_terms; t += stride) {
+    bool bad = false;
+    const unsigned long long b = offs[t], e = offs[t + 1];
+    for (unsigned long long i = b + lane; i < e; i += 32) {
+      const uint32_t d = docids[i];
+      if (d >= n_docs || (i > b && docids[i - 1] >= d)) bad = true;
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicMin(flag, t + 1ull);
+  }
+}
+
 // W9: postings of deleted documents never match.  They are removed from the device store at
 // upload (df / dc used for idf stay the stored ones: those are host-side statistics).
 __global__ void k_live_counts(const uint32_t* __restrict__ docids, const unsigned long long* __restrict__ offs,
@@ -1654,6 +1673,33 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   CUT(cudaMemcpyAsync(d_len, desc->len_bytes, (size_t)h->n_fields * h->n_docs, cudaMemcpyDefault, h->stream));
   CUT(cudaMemsetAsync(d_len + (size_t)h->n_fields * h->n_docs, 0, h->n_docs, h->stream));
   CUT(cudaStreamSynchronize(h->stream));     // every_docs / every_tfs are pageable
+
+  // ---- the lists must hold valid, ascending local docids -------------------------------------------
+  if (P_real && h->n_real_terms) {
+    unsigned long long* d_chk = nullptr;
+    unsigned long long* d_offs_chk = nullptr;
+    cudaError_t ec = cudaMalloc(reinterpret_cast<void**>(&d_chk), 8);
+    if (ec == cudaSuccess) ec = cudaMalloc(reinterpret_cast<void**>(&d_offs_chk), (h->n_real_terms + 1) * 8);
+    unsigned long long first_bad = ~0ull;
+    if (ec == cudaSuccess) ec = cudaMemcpyAsync(d_chk, &first_bad, 8, cudaMemcpyHostToDevice, h->stream);
+    if (ec == cudaSuccess) ec = cudaMemcpyAsync(d_offs_chk, h->term_offsets.data(), (h->n_real_terms + 1) * 8, cudaMemcpyHostToDevice, h->stream);
+    if (ec == cudaSuccess) {
+      const unsigned blocks = (unsigned)std::min<uint64_t>((h->n_real_terms + 7) / 8, (uint64_t)h->n_sms * 16);
+      k_check_docids<<<blocks, 256, 0, h->stream>>>(h->d_docids, d_offs_chk, h->n_real_terms, (uint32_t)h->n_docs, d_chk);
+      ec = cudaGetLastError();
+    }
+    if (ec == cudaSuccess) ec = cudaMemcpyAsync(&first_bad, d_chk, 8, cudaMemcpyDeviceToHost, h->stream);
+    if (ec == cudaSuccess) ec = cudaStreamSynchronize(h->stream);
+    cudaFree(d_chk);
+    cudaFree(d_offs_chk);
+    if (ec != cudaSuccess) { free_tmp(); bm25f_destroy(h); return fail(BM25F_ECUDA, "docid check: %s", cudaGetErrorString(ec)); }
+    if (first_bad != ~0ull) {
+      free_tmp();
+      bm25f_destroy(h);
+      return fail(BM25F_EINVAL, "posting list %llu: docids must be < n_docs_all (%llu) and strictly ascending inside a list",
+                  (unsigned long long)(first_bad - 1), (unsigned long long)desc->n_docs_all);
+    }
+  }
 
   // ---- W9: drop the postings of deleted documents from the device store -----------------------
   if (desc->deleted && P && h->n_terms) {

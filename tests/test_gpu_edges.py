@@ -150,3 +150,24 @@ def test_more_like_f4():
             assert [x for x, _ in r.top_n] == pytest.approx([x for x, _ in want_top], rel=1e-5)
             assert docnum not in [h.docnum for h in r]
     ix._engine_cache.clear()
+
+
+def test_malformed_posting_lists_are_refused():
+    """bm25f_create checks what the header only used to document: docids < n_docs_all, strictly ascending inside a list."""
+    ix = make_corpus(300, 100, 5, device="cpu")
+    for kind in ("range", "order", "dup"):
+        bad = make_corpus(300, 100, 5, device="cpu")
+        a, b = int(bad.term_offsets[40]), int(bad.term_offsets[41])
+        assert b - a >= 3
+        if kind == "range":
+            bad.docids[b - 1] = 300
+        elif kind == "order":
+            bad.docids[a], bad.docids[a + 1] = bad.docids[a + 1], bad.docids[a]
+        else:
+            bad.docids[a + 1] = bad.docids[a]
+        with pytest.raises(_ffi.EngineError) as e:
+            bad.searcher()
+        assert e.value.code == -1 and "posting list 40" in str(e.value)
+    with ix.searcher() as s:
+        assert len(s.search(Term("body", 3))) > 0
+    ix._engine_cache.clear()
