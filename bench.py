@@ -157,14 +157,20 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(world):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernels of one step, from the
-    committed ncu capture of this same command (profiles/r01_traffic.json), or None."""
-    if world != 1:
-        return None
+#: DRAM traffic is not measured inside a bench run (it needs ncu's counters, and a number taken under a profiler is
+#: not a bench value): the line carries null and points at the dated capture of this same command
+TRAFFIC_PROFILE = "profiles/r02_traffic.json (ncu --set full capture of this command: dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+
+
+def whoosh_module():
+    """Real Whoosh (reference requirements.txt:6) if it can be imported here, also from a driver-provided install
+    under baseline/_ref; None in this image."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(ref) and ref not in sys.path:
+        sys.path.append(ref)
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return float(json.load(f)["per_step"]["k_score_stream"]["dram_bytes"])
+        import whoosh
+        return whoosh
     except Exception:
         return None
 
@@ -207,6 +213,8 @@ def run_reference(args):
     target = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     vals = []
     last = None
+    if whoosh_module() is not None and c["n_docs"] <= 50_000:
+        return run_reference_whoosh(args, c, ix, qs)
     for i in range(args.warmup + args.steps):
         # rotate the sample so steps do not re-time identical queries
         off = (i * 997) % max(1, len(qs.queries) - 1)
@@ -230,6 +238,53 @@ def run_reference(args):
     return 0
 
 
+def run_reference_whoosh(args, c, ix, qs):
+    """The reference arm on real Whoosh (only when it can be imported, and for corpora a pure-Python indexer can
+    build in the bench's time: BASELINE configs[0]): index the corpus as 't%07d' tokens with a whitespace
+    tokenizer, time searcher.search(q, limit=k) with weighting=BM25F (my_flask.py:183-184, :208) on one core."""
+    import tempfile
+    from whoosh import fields, index, query as wq, scoring
+    from whoosh.analysis import SpaceSeparatedTokenizer
+    docs = [[] for _ in range(ix.n_docs_all)]
+    for tid in range(ix.n_terms):
+        d, tf = ix.postings(tid)
+        tok = "t%07d" % (tid - int(ix.term_field[tid]) * ix.vocab_size)
+        for dn, n in zip(d.tolist(), tf.tolist()):
+            docs[dn].extend([tok] * int(n))
+    tmp = tempfile.mkdtemp(prefix="bm25f_whoosh_")
+    wix = index.create_in(tmp, fields.Schema(body=fields.TEXT(analyzer=SpaceSeparatedTokenizer(), phrase=False)))
+    w = wix.writer()
+    for toks in docs:
+        w.add_document(body=" ".join(toks))
+    w.commit()
+
+    def conv(q):
+        n = type(q).__name__
+        if n == "Term":
+            return wq.Term("body", "t%07d" % q.text, boost=q.boost)
+        return {"And": wq.And, "Or": wq.Or}[n]([conv(s) for s in q.subqueries], boost=q.boost)
+    wqs = [conv(q) for q in qs.queries]
+    vals = []
+    with wix.searcher(weighting=scoring.BM25F) as s:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            for q in wqs:
+                s.search(q, limit=c["k"])
+            if i >= args.warmup:
+                vals.append(len(wqs) / (time.perf_counter() - t0))
+    v = float(np.mean(vals))
+    cfg = config_json(args, c, 1)
+    cfg["l2"] = "n/a (CPU)"
+    cb = {"value": v, "unit": "queries/s", "cores": 1, "kind": "whoosh",
+          "sample": "the whole batch through whoosh %s Searcher.search, one process" % getattr(__import__("whoosh"), "versionstring", lambda: "?")()}
+    print(json.dumps({"impl": "reference", "metric": "BM25F top-%d queries/sec" % c["k"], "value": v, "unit": "queries/s",
+                      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * c["n_queries"] / v,
+                      "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": cfg, "cpu_baseline": cb,
+                      "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    return 0
+
+
 def _cuda():
     try:
         import torch
@@ -248,12 +303,10 @@ def main():
     ap.add_argument("--docs", type=int, default=0)
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--k", type=int, default=0)
-    ap.add_argument("--variant", type=int, default=0, help="scoring kernel (include/bm25f.h); 0 = auto")
-    ap.add_argument("--subtile-docs", type=int, default=0)
-    ap.add_argument("--cta-slice-docs", type=int, default=0)
-    ap.add_argument("--cta-warps", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="engine option (a bm25f_options field, include/bm25f.h), e.g. --opt variant=3")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
-    ap.add_argument("--check", type=int, default=32, help="queries checked against the oracle before timing")
+    ap.add_argument("--check", type=int, default=200, help="queries checked against the oracle before timing")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
@@ -289,9 +342,11 @@ def main():
     # run on a side stream: the legacy default stream would serialise the library's second stream
     side = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(side)
-    ss = ShardedSearcher(ix, rank=rank, world=world, device=local_rank, weighting=BM25F,
-                         variant=args.variant, subtile_docs=args.subtile_docs, cta_slice_docs=args.cta_slice_docs,
-                         cta_warps=args.cta_warps)
+    engine_opts = {}
+    for o in args.opt:
+        name, _, value = o.partition("=")
+        engine_opts[name.strip()] = int(value, 0)
+    ss = ShardedSearcher(ix, rank=rank, world=world, device=local_rank, weighting=BM25F, **engine_opts)
     eng = ss.engine
     batch = ss.pack(qs.queries)
     if rank == 0:
@@ -406,20 +461,44 @@ def main():
                          "i+1 overlaps the GPU side of batch i; serial_value: one blocking search per step"}
     plan.close()
 
+    # The Whoosh-shaped entry: a list of Query objects in, Results out (Searcher.search_batch: lowering of the
+    # trees, packing, the same C-ABI call, result objects on demand).  "warm": the same query objects as the step
+    # before (their lowered form is remembered on them); "cold": fresh query objects every step.
+    facade = None
+    if world == 1:
+        from document_search_engine_b200.corpus import config_queries as _cq
+        searcher = ss.local
+
+        def facade_steps(fresh):
+            def run():
+                for i in range(args.steps):
+                    queries = _fresh[i] if fresh else qs.queries
+                    res = searcher.search_batch(queries, limit=k)
+                    assert len(res) == c["n_queries"] and res[0].scored_length() <= k
+            return run
+        _fresh = [_cq(args.config, c["n_queries"]).queries for _ in range(args.steps)]
+        searcher.search_batch(qs.queries, limit=k)
+        facade = {"warm_value": c["n_queries"] * args.steps / median_of_three(facade_steps(False))}
+        t0 = time.perf_counter()
+        facade_steps(True)()
+        facade["cold_value"] = c["n_queries"] * args.steps / (time.perf_counter() - t0)
+        facade["note"] = ("Searcher.search_batch(list of Query trees, limit) -> sequence of Results; warm: lowered forms "
+                          "cached on the query objects, cold: new query objects every step (one repetition)")
+
     if rank == 0:
         cfg = config_json(args, c, world)
         cfg["l2"] = cfg["l2"] % (st["device_bytes"] / 2 ** 30)
-        cfg["engine"] = {"variant": args.variant, "ctas_per_sm": st["ctas_per_sm"],
+        cfg["engine"] = {"options": engine_opts, "ctas_per_sm": st["ctas_per_sm"],
                          "packed_payload": bool(st["packed_payload"]), "work_items": int(st["n_items"]),
                          "kernels_per_step": int(st["n_launches"])}
         out = {"metric": "BM25F top-%d queries/sec" % k, "value": value, "unit": "queries/s", "n_gpus": world,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
                "e2e": dict({"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
-                            "d2h_bytes_per_step": int(d2h)}, **e2e_extra),
+                            "d2h_bytes_per_step": int(d2h), "facade": facade}, **e2e_extra),
                "gpu_launches": launches,
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                            "frac": achieved / peak, "traffic": measured_traffic(world), "peak_source": peak_src,
+                            "frac": achieved / peak, "traffic": None, "traffic_profile": TRAFFIC_PROFILE, "peak_source": peak_src,
                             "kernel": "k_score_stream (flat OR queries: every posting read once and accumulated)",
                             "kernel_ms_per_step": ms_stream,
                             "algorithmic_bytes_per_launch": BYTES_PER_POSTING * st["postings_stream"],

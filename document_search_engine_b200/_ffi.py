@@ -61,7 +61,7 @@ OPTION_NAMES = tuple(n for n, _ in Options._fields_)
 class QueryBatchDesc(C.Structure):
     _fields_ = [("n_queries", C.c_uint32), ("n_leaves", C.c_uint32), ("query_leaf_offsets", C.c_void_p),
                 ("query_n_groups", C.c_void_p), ("leaf_term", C.c_void_p), ("leaf_weight", C.c_void_p),
-                ("leaf_group", C.c_void_p), ("after_keys", C.c_void_p)]
+                ("leaf_group", C.c_void_p), ("after_keys", C.c_void_p), ("after_lo", C.c_void_p)]
 
 
 class Stats(C.Structure):
@@ -135,13 +135,14 @@ def _ptr(a: Optional[np.ndarray]):
 class PackedBatch:
     """A lowered query batch in the layout of ``bm25f_query_batch`` (host arrays)."""
 
-    def __init__(self, query_leaf_offsets, query_n_groups, leaf_term, leaf_weight, leaf_group, after_keys=None):
+    def __init__(self, query_leaf_offsets, query_n_groups, leaf_term, leaf_weight, leaf_group, after_keys=None, after_lo=None):
         self.query_leaf_offsets = np.ascontiguousarray(query_leaf_offsets, dtype=np.uint32)
         self.query_n_groups = np.ascontiguousarray(query_n_groups, dtype=np.uint8)
         self.leaf_term = np.ascontiguousarray(leaf_term, dtype=np.uint32)
         self.leaf_weight = np.ascontiguousarray(leaf_weight, dtype=np.float32)
         self.leaf_group = np.ascontiguousarray(leaf_group, dtype=np.uint8)
         self.after_keys = None if after_keys is None else np.ascontiguousarray(after_keys, dtype=np.uint64)
+        self.after_lo = None if after_lo is None else np.ascontiguousarray(after_lo, dtype=np.uint32)
         self.n_queries = int(self.query_n_groups.size)
         self.n_leaves = int(self.leaf_term.size)
         if self.query_leaf_offsets.size != self.n_queries + 1:
@@ -150,14 +151,15 @@ class PackedBatch:
     def desc(self) -> QueryBatchDesc:
         return QueryBatchDesc(self.n_queries, self.n_leaves, _ptr(self.query_leaf_offsets),
                               _ptr(self.query_n_groups), _ptr(self.leaf_term), _ptr(self.leaf_weight),
-                              _ptr(self.leaf_group), _ptr(self.after_keys))
+                              _ptr(self.leaf_group), _ptr(self.after_keys), _ptr(self.after_lo))
 
     def slice(self, a: int, b: int) -> "PackedBatch":
         o = self.query_leaf_offsets
         la, lb = int(o[a]), int(o[b])
         return PackedBatch(o[a:b + 1] - o[a], self.query_n_groups[a:b], self.leaf_term[la:lb],
                            self.leaf_weight[la:lb], self.leaf_group[la:lb],
-                           None if self.after_keys is None else self.after_keys[a:b])
+                           None if self.after_keys is None else self.after_keys[a:b],
+                           None if self.after_lo is None else self.after_lo[a:b])
 
     @property
     def nbytes(self) -> int:

@@ -70,9 +70,10 @@ struct LeafRec {            // 32 B
 
 struct QueryRec {           // 32 B
   uint32_t leaf_begin;
-  uint32_t n_leaves;
-  uint32_t n_groups;
+  uint16_t n_leaves;
+  uint16_t n_groups;
   uint32_t flags;           // bit0: one group, all weights > 0 -> "acc == 0" marks a fresh slot
+  uint32_t after_lo;        // final mode: low part (~docnum) of the paging bound; after_key is its high part
   unsigned long long after_key;
   uint32_t part_begin;      // first partial top-k list of this query
   uint32_t n_parts;
@@ -2025,6 +2026,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     QueryRec& qr = queries[qi];
     qr = QueryRec{};
     qr.after_key = b->after_keys ? b->after_keys[qi] : 0ull;
+    qr.after_lo = (b->after_keys && b->after_lo) ? b->after_lo[qi] : 0u;
     qr.leaf_begin = a;
     qr.part_begin = L.n_parts;
     if (nl > (uint32_t)MAXL) PFAIL(BM25F_EINVAL, "query %u has %u leaves (max %d)", qi, nl, MAXL);
@@ -2104,32 +2106,34 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     }
     for (uint32_t i = 0; i < nlq; ++i) leaves[a + i].qnl = nlq;
     for (uint32_t i = a + nlq; i < e; ++i) { leaves[i] = LeafRec{}; leaves[i].qleaf0 = i; leaves[i].qnl = 1; }   // unused slots stay harmless
-    qr.n_leaves = nlq;
-    qr.n_groups = G;
+    qr.n_leaves = (uint16_t)nlq;
+    qr.n_groups = (uint16_t)G;
     qr.flags = (G == 1 && all_pos && n_neg == 0) ? QF_SIMPLE_OR : 0u;
     if (!all_pos) L.any_nonpos = true;
     L.postings += P;
 
     // Route the query: stream kernel when it is eligible (top list fits one warp, few enough leaves
     // for register-resident rings, positive weights, no paging bound), else the CTA-per-item kernels.
-    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= FAST_MAX_K && nlq <= 8 && all_pos && qr.after_key == 0ull;
+    // (a paging bound is served by the warp kernels only in their final() instantiations, by the CTA kernels otherwise)
+    const bool no_bound = qr.after_key == 0ull || final_mode;
+    const bool stream_ok = (h->variant == 0 || h->variant >= 3) && k <= FAST_MAX_K && nlq <= 8 && all_pos && no_bound;
     // auto: a flat OR sweeps every sub-range anyway and runs best on independent warps (stream
     // kernel); an AND skips the slices in which a group is absent and runs best on warp teams
     // ... unless its smallest group is so much sparser than the rest that looking its documents up in
     // the other lists (Whoosh's IntersectionMatcher + skip_to) beats streaming every list
     const uint64_t g0 = gsize[order[0]];
-    if (n_neg && !(k <= FAST_MAX_K && nlq <= 32 && G < NEG_GROUP && all_pos && qr.after_key == 0ull))
+    if (n_neg && !(k <= FAST_MAX_K && nlq <= 32 && G < NEG_GROUP && all_pos && no_bound))
       PFAIL(BM25F_EINVAL, "query %u: NOT clauses are served for k <= 256, at most 32 leaves and 30 groups, positive weights and no paging bound", qi);
-    const bool isect_ok = k <= FAST_MAX_K && nlq <= 32 && all_pos && qr.after_key == 0ull;
+    const bool isect_ok = k <= FAST_MAX_K && nlq <= 32 && all_pos && no_bound;
     if (final_mode && !isect_ok && !stream_ok)
-      PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 256, at most 32 leaves, positive weights and no paging bound", qi);
+      PFAIL(BM25F_EINVAL, "query %u: a final() weighting is served for k <= 256, at most 32 leaves and positive weights", qi);
     const uint64_t n_cand = (qr.flags & QF_SIMPLE_OR) ? P * (uint64_t)(nlq > 1 ? nlq - 1 : 1) : g0 * (uint64_t)(nlq - 1);   // lookups
     // A flat OR with few L.postings is also cheaper the candidate-driven way (every posting is a candidate
     // and is still read exactly once; sweeping every sub-range of the document space is what costs).
     const bool use_isect = isect_ok && ((final_mode && !stream_ok) || h->variant == 5 || (n_neg && !stream_ok) || (h->variant == 0 &&
         ((qr.flags & QF_SIMPLE_OR) ? n_cand < (uint64_t)h->is_or_limit
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
-    const bool use_team = !use_isect && stream_ok && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
+    const bool use_team = !use_isect && stream_ok && qr.after_key == 0ull && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
     uint32_t nsplit;
     if (use_isect) {

@@ -34,6 +34,12 @@ __host__ __device__ __forceinline__ double orderable_f64_value(unsigned long lon
 __device__ __forceinline__ bool key2_gt(unsigned long long ah, uint32_t al, unsigned long long bh, uint32_t bl) {
   return ah > bh || (ah == bh && al > bl);
 }
+// ... a candidate: above the k-th best so far and, when the query carries a paging bound (the last hit of the
+// previous pass: search_page deep into a date-ordered listing, my_flask.py:211), strictly below that bound
+__device__ __forceinline__ bool key2_wanted(unsigned long long kh, uint32_t kl, unsigned long long th, uint32_t tl,
+                                            unsigned long long bh, uint32_t bl) {
+  return key2_gt(kh, kl, th, tl) && (bh == 0ull || key2_gt(bh, bl, kh, kl));
+}
 template <int KR>
 __device__ __forceinline__ void warp_topk2_insert_rows(unsigned long long (&th)[KR], uint32_t (&tl)[KR], unsigned long long kh,
                                                        uint32_t kl, int lane) {

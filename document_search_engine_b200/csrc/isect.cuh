@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
             kh = orderable_f64(final_value(score, __ldg(ip.final_add + doc)));
             kl = 0xFFFFFFFFu - (ip.doc_base + doc);
           }
-          unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_key, thr_lo));
+          unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_wanted(kh, kl, thr_key, thr_lo, q.after_key, q.after_lo));
           while (pm) {
             const int src = __ffs(pm) - 1;
             pm &= pm - 1u;

@@ -453,7 +453,7 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
                   }
                 }
               }
-              unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_gt(kh, kl, thr_key, thr_lo));
+              unsigned pm = __ballot_sync(0xFFFFFFFFu, key2_wanted(kh, kl, thr_key, thr_lo, q.after_key, q.after_lo));
               while (pm) {
                 const int src = __ffs(pm) - 1;
                 pm &= pm - 1u;

@@ -50,6 +50,13 @@ def make_keys(scores: np.ndarray, docids: np.ndarray) -> np.ndarray:
     return (u << np.uint64(32)) | (np.uint64(0xFFFFFFFF) - docids.astype(np.uint64))
 
 
+def orderable_f64(v: np.ndarray) -> np.ndarray:
+    """float64 -> uint64 with the same order (the high part of the engine's 96-bit final() keys, csrc/final.cuh)."""
+    u = np.ascontiguousarray(v, dtype=np.float64).view(np.uint64)
+    neg = (u >> np.uint64(63)) != 0
+    return np.where(neg, ~u, u | np.uint64(0x8000000000000000))
+
+
 class Hit:
     def __init__(self, results: "Results", docnum: int, pos: int, score: float):
         self.results = results
@@ -378,7 +385,8 @@ class Searcher:
                 leaves = [(ix.term_id(lf.fieldname, lf.text), lf.boost, lf.group) for lf in low]
         return (ix, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]))
 
-    def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
+    def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None,
+             after_lo: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
         """Lower query trees to the ``bm25f_query_batch`` layout.  Leaf weights ``idf * (K1 + 1) * boost`` are
         evaluated in float64 and rounded once (numpy gathers over a per-term table).  The lowered form of a query
         is remembered on the query object (query trees are values: the reference builds one per request,
@@ -417,7 +425,7 @@ class Searcher:
         if ev.any():
             terms[ev] = (_ffi.TERM_EVERY_BASE + (-2 - tids[ev])).astype(np.uint32)
             w[ev] = rec["boost"][ev]
-        return _ffi.PackedBatch(offs, np.asarray(ngroups, dtype=np.uint8), terms, w, rec["group"], after_keys)
+        return _ffi.PackedBatch(offs, np.asarray(ngroups, dtype=np.uint8), terms, w, rec["group"], after_keys, after_lo)
 
     # -- searching ----------------------------------------------------------------
     def _run_packed(self, batch: _ffi.PackedBatch, k: int):
@@ -502,13 +510,38 @@ class Searcher:
         queries = list(queries)
         nq = len(queries)
         if self.weighting.use_final:
-            # final values (float64) come straight from the device, one pass
-            if limit is None or limit > FINAL_MAX_K:
-                raise NotImplementedError("a final() weighting is served for limit <= %d" % FINAL_MAX_K)
-            final, docids, counts, tot = self.engine.search_batch_final(self.pack(queries), limit)
+            # final values (float64) come straight from the device; one pass serves limit <= 256, deeper pages
+            # (search_page(qp, pagenum=26, pagelen=10) on a date-ordered listing, my_flask.py:211) take another pass
+            # for the hits ordered strictly after the last one already returned
+            tops: List[list] = [[] for _ in range(nq)]
+            totals = np.zeros(nq, dtype=np.uint64)
+            active = list(range(nq))
+            after_hi = after_lo = None
+            first = True
+            while active:
+                k = FINAL_MAX_K if limit is None else min(limit, FINAL_MAX_K)
+                batch = self.pack([queries[i] for i in active], after_hi, after_lo)
+                final, docids, counts, tot = self.engine.search_batch_final(batch, k)
+                nxt, nh, nlo = [], [], []
+                for j, i in enumerate(active):
+                    c = int(counts[j])
+                    if first:
+                        totals[i] = tot[j]
+                    tops[i].extend(zip(final[j, :c].tolist(), docids[j, :c].tolist()))
+                    need = int(totals[i]) if limit is None else min(limit, int(totals[i]))
+                    if c == k and len(tops[i]) < need:
+                        nxt.append(i)
+                        nh.append(final[j, c - 1])
+                        nlo.append(0xFFFFFFFF - int(docids[j, c - 1]))
+                if limit is not None:
+                    for i in active:
+                        del tops[i][limit:]
+                active = nxt
+                if nxt:
+                    after_hi, after_lo = orderable_f64(np.asarray(nh, dtype=np.float64)), np.asarray(nlo, dtype=np.uint32)
+                first = False
             dt = time.perf_counter() - t_start
-            return [Results(self, queries[i], list(zip(final[i, :int(counts[i])].tolist(), docids[i, :int(counts[i])].tolist())),
-                            int(tot[i]), runtime=dt) for i in range(nq)]
+            return [Results(self, queries[i], tops[i], int(totals[i]), runtime=dt) for i in range(nq)]
         if limit is not None and limit <= _ffi.MAX_K:
             # one pass serves every query: the per-query Results are made when somebody looks at them
             scores, docids, counts, tot = self._run_packed(self.pack(queries), limit)

@@ -126,7 +126,11 @@ typedef struct {
   const float*    leaf_weight;         /* [n_leaves] idf * (K1 + 1) * boost, rounded from float64 */
   const uint8_t*  leaf_group;          /* [n_leaves] group index inside the query, or BM25F_GROUP_NOT */
   const uint64_t* after_keys;          /* [n_queries] or NULL: only hits ordered strictly after this
-                                          key are collected (paging past BM25F_MAX_K); 0 = no bound */
+                                          key are collected (paging past BM25F_MAX_K); 0 = no bound.
+                                          While a final() step is set the bound is the 96-bit key of the last hit already
+                                          returned: after_keys = the float64 final value made orderable (sign bit set for
+                                          v >= 0, all bits inverted for v < 0), after_lo = 0xFFFFFFFF - its docnum */
+  const uint32_t* after_lo;            /* [n_queries] or NULL (see after_keys) */
 } bm25f_query_batch;
 
 typedef struct {
@@ -172,9 +176,9 @@ int  bm25f_set_weighting(bm25f_handle* h, const float* norm);
  * without a date.  While set, a match with BM25F score s ranks by the float64 value
  *     v = 1 - 1/s                      (no date)
  *     v = ((1 - 1/s) + date_add) / 1e9 (dated)
- * descending, docnum ascending; plans are fetched with bm25f_fetch_final (which returns v), k <= 256, at most
- * 32 leaves per query, and bm25f_search_batch / bm25f_submit / bm25f_fetch are refused.  NULL switches the
- * step off again. */
+ * descending, docnum ascending; plans are fetched with bm25f_fetch_final (which returns v), k <= 256 per pass
+ * (deeper pages: another pass with after_keys / after_lo), at most 32 leaves per query, and
+ * bm25f_search_batch / bm25f_submit / bm25f_fetch are refused.  NULL switches the step off again. */
 int  bm25f_set_final_date(bm25f_handle* h, const double* date_add);
 
 /* Host planning + upload of one batch.  The plan can be executed any number of times. */

@@ -117,10 +117,8 @@ def test_final_switches_with_the_weighting(dated):
         assert_batch_parity(o_plain, qs, s.search_batch(qs, limit=10), 10)
     with dated.searcher(weighting=DescDateBM25F) as s:
         assert_batch_parity(o_desc, qs, s.search_batch(qs, limit=10), 10, abs_tol=FINAL_TOL)
-        with pytest.raises(NotImplementedError):
-            s.search_batch(qs, limit=500)
         page = s.search_page(qs[0], 2, pagelen=5)
-        assert page.total == len(s.search(qs[0], limit=10)) or True
+        assert page.total == len(s.search(qs[0], limit=10))
     with dated.searcher(weighting=BM25F) as s:
         assert_batch_parity(o_plain, qs, s.search_batch(qs, limit=10), 10)
 
@@ -164,3 +162,25 @@ def test_final_merge_across_shards(dated, k):
         n = int(c[i])
         assert_query_parity(o, q, list(zip(v[i, :n].tolist(), d[i, :n].tolist())), int(totals[i]), k,
                             ctx="query %d" % i, abs_tol=FINAL_TOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls", [DescDateBM25F, AscDateBM25F])
+def test_final_deep_paging(dated, cls):
+    """search_page(qp, pagenum=N, pagelen=10) deep into a date-ordered listing (reference my_flask.py:211: limit =
+    pagenum * pagelen grows past the 256 keys a warp keeps): further passes collect the hits ordered strictly after
+    the last one returned; limit=None returns every match.  Two searchers with different weightings on one index
+    (the reference opens one per request, my_flask.py:183-184) keep their own scoring."""
+    w = cls()
+    o = NumpyOracle(dated, final_add=w.doc_final_terms(dated))
+    qs = [q for q in date_queries(60, 5) if len(o.match_all(q)[0]) > 300][:6] + date_queries(4, 6)
+    assert len(qs) > 4
+    with dated.searcher(weighting=cls) as s, dated.searcher(weighting=BM25F) as plain:
+        for limit in (257, 700, None):
+            res = s.search_batch(qs, limit=limit)
+            assert_batch_parity(o, qs, res, limit, abs_tol=FINAL_TOL)
+        assert_batch_parity(NumpyOracle(dated), qs, plain.search_batch(qs, limit=10), 10)
+        page = s.search_page(qs[0], 30, pagelen=10)
+        want, total = o.search(qs[0], limit=300)
+        assert page.total == total and page.offset == 290 and [h.docnum for h in page] == [d for _, d in want[290:300]]
+        assert_batch_parity(o, qs[:2], s.search_batch(qs[:2], limit=20), 20, abs_tol=FINAL_TOL)

@@ -33,7 +33,7 @@ def test_config2_sample_against_oracle(cfg2):
     qs = config_queries(2, 10_000).queries
     scores, docids, counts, totals = _run(cfg2, qs)
     o = NumpyOracle(cfg2)
-    for i in range(0, len(qs), 250):           # 40 queries of the real batch
+    for i in range(0, len(qs), 50):            # 200 queries of the real batch
         n = int(counts[i])
         assert_query_parity(o, qs[i], list(zip(scores[i, :n].tolist(), docids[i, :n].tolist())), int(totals[i]), K,
                             ctx="config 2 query %d" % i)
@@ -43,10 +43,41 @@ def test_config3_variants_sample_against_oracle(cfg2):
     qs = config_queries(3, 2_000).queries       # AND of four 2-way OR-groups, 8 leaves
     scores, docids, counts, totals = _run(cfg2, qs)
     o = NumpyOracle(cfg2)
-    for i in range(0, len(qs), 100):
+    for i in range(0, len(qs), 10):            # 200 queries
         n = int(counts[i])
         assert_query_parity(o, qs[i], list(zip(scores[i, :n].tolist(), docids[i, :n].tolist())), int(totals[i]), K,
                             ctx="config 3 query %d" % i)
+
+
+def _sample_against_oracle(ix, qs, k, every, ctx, **kw):
+    s = Searcher(ix, weighting=BM25F, **kw)
+    scores, docids, counts, totals = s.engine.search_batch(s.pack(qs), k)
+    o = NumpyOracle(ix)
+    checked = 0
+    for i in range(0, len(qs), every):
+        n = int(counts[i])
+        assert_query_parity(o, qs[i], list(zip(scores[i, :n].tolist(), docids[i, :n].tolist())), int(totals[i]), k,
+                            ctx="%s query %d" % (ctx, i))
+        checked += 1
+    s.engine.close()
+    ix._engine_cache.clear()
+    return checked
+
+
+def test_config4_shape_top100_sample_against_oracle():
+    """BASELINE configs[3] shape at 2M documents (vocabulary 500k, 2-4-term AND/OR, top-100: four keys per lane in the
+    warp kernels), 200 sampled queries of a 4000-query batch against the oracle."""
+    ix = config_corpus(4, n_docs=2_000_000)
+    qs = config_queries(4, 4_000).queries
+    assert _sample_against_oracle(ix, qs, 100, 20, "config 4 shape") == 200
+
+
+def test_config5_shape_two_fields_sample_against_oracle():
+    """BASELINE configs[4] shape at 1M documents (vocabulary 1M, two fields, title boost 2: every query term is an OR
+    across the fields), 250 sampled queries of a 5000-query batch against the oracle."""
+    ix = config_corpus(5, n_docs=1_000_000)
+    qs = config_queries(5, 5_000).queries
+    assert _sample_against_oracle(ix, qs, 10, 20, "config 5 shape") == 250
 
 
 def test_kernel_families_agree_and_idempotent(cfg2):
