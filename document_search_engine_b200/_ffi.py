@@ -15,7 +15,7 @@ import numpy as np
 
 ABI_VERSION = 3
 MAX_K = 1024
-MAX_LEAVES_PER_QUERY = 64
+MAX_LEAVES_PER_QUERY = 256
 TERM_UNKNOWN = 0xFFFFFFFF
 TERM_EVERY_BASE = 0xFFFFFF00       # + field index: Every(field)
 

@@ -22,6 +22,7 @@ from __future__ import annotations
 
 from typing import Dict, Iterable, List, Mapping, Optional, Sequence, Tuple
 
+import itertools
 import json
 import threading
 
@@ -30,6 +31,7 @@ import numpy as np
 from .numeric import lengths_to_bytes
 
 FORMAT_VERSION = 1
+_TOKENS = itertools.count(1)
 
 
 class Schema:
@@ -124,6 +126,8 @@ class FlatIndex:
         if len(self.scorable) != len(self.field_names):
             raise ValueError("scorable must have one entry per field")
         self.schema = Schema(self.field_names, stored=self._stored_names())
+        #: identifies this index object in caches that must not hold on to it (Searcher.pack)
+        self.token = next(_TOKENS)
         self._engine_cache = {}
         self._lexicons = {}
         self._forward = {}

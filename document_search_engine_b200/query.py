@@ -38,6 +38,12 @@ class Query:
     def normalize(self) -> "Query":
         return self
 
+    def __getstate__(self):
+        # the lowered form Searcher.pack remembers on a query belongs to one index: it does not travel
+        d = dict(self.__dict__)
+        d.pop("_lowered", None)
+        return d
+
     def __ne__(self, other):
         return not self.__eq__(other)
 

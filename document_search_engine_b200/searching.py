@@ -383,7 +383,7 @@ class Searcher:
                 if g > 32:
                     raise UnsupportedQuery("more than 32 AND-groups in one query")
                 leaves = [(ix.term_id(lf.fieldname, lf.text), lf.boost, lf.group) for lf in low]
-        return (ix, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]))
+        return (ix.token, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]))
 
     def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None,
              after_lo: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
@@ -392,7 +392,7 @@ class Searcher:
         is remembered on the query object (query trees are values: the reference builds one per request,
         ``my_flask.py:189-193``, and never edits it), so packing the same objects again costs three list appends
         per query."""
-        ix = self.ix
+        token = self.ix.token
         counts: List[int] = []
         ngroups: List[int] = []
         blobs: List[bytes] = []
@@ -402,7 +402,7 @@ class Searcher:
         try:
             for q in queries:
                 c = q.__dict__.get("_lowered")
-                if c is None or c[0] is not ix:
+                if c is None or c[0] != token:
                     c = lower1(q)
                     q.__dict__["_lowered"] = c
                 counts.append(c[1])

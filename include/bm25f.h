@@ -52,7 +52,7 @@ extern "C" {
 #define BM25F_ENOMEM     -4   /* out of (device or host) memory */
 #define BM25F_EABI       -5   /* ABI version mismatch */
 
-#define BM25F_MAX_LEAVES_PER_QUERY 64
+#define BM25F_MAX_LEAVES_PER_QUERY 256
 #define BM25F_MAX_K               1024
 #define BM25F_TERM_UNKNOWN 0xFFFFFFFFu  /* leaf_term value for a term/field not in the index (empty matcher) */
 #define BM25F_GROUP_NOT 0xFFu            /* leaf_group value of a leaf inside a NOT clause: its documents are excluded from
