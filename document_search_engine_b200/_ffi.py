@@ -28,7 +28,7 @@ EXPORTS = (
     "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
     "bm25f_reset_stats", "bm25f_submit", "bm25f_collect", "bm25f_set_final_date", "bm25f_fetch_final",
-    "bm25f_plan_device_final", "bm25f_merge_final_lists",
+    "bm25f_plan_device_final", "bm25f_merge_final_lists", "bm25f_plan_gather_span", "bm25f_merge_gathered",
 )
 
 
@@ -116,6 +116,8 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_fetch_final.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.bm25f_plan_device_final.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     lib.bm25f_merge_final_lists.argtypes = [vp, vp, vp, i32, u32, i32, vp, vp, vp, vp]
+    lib.bm25f_plan_gather_span.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.bm25f_merge_gathered.argtypes = [vp, vp, i32, C.c_uint64, C.c_uint64, u32, i32, vp, vp, vp, vp, vp, vp]
     if lib.bm25f_abi_version() != ABI_VERSION:
         raise RuntimeError("libbm25f ABI %d != binding ABI %d" % (lib.bm25f_abi_version(), ABI_VERSION))
     if path == os.environ.get("BM25F_LIB", LIB_PATH):
@@ -204,6 +206,13 @@ class Plan:
         dk, dt = C.c_void_p(), C.c_void_p()
         _check(self.engine.lib, self.engine.lib.bm25f_plan_device_results(self._p, C.byref(dk), C.byref(dt)))
         return dk.value, dt.value
+
+    def gather_span(self) -> Tuple[int, int, int]:
+        """``(device pointer, words, offset of the totals)`` of the span that holds this workspace plan's keys and
+        match counts: what one all-gather of the sharded exchange step moves."""
+        base, span, off = C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(self.engine.lib, self.engine.lib.bm25f_plan_gather_span(self._p, C.byref(base), C.byref(span), C.byref(off)))
+        return base.value, int(span.value), int(off.value)
 
     def device_final(self) -> Tuple[int, int, int]:
         """Raw device pointers ``(final values [Q*k] f64, docids [Q*k] u32, totals [Q] u64)`` of a plan prepared
@@ -333,6 +342,12 @@ class Engine:
     def merge_keys(self, d_keys: int, n_lists: int, n_queries: int, k: int, d_out: int):
         """Runs on the handle's stream (see ``set_stream``)."""
         _check(self.lib, self.lib.bm25f_merge_keys(self._h, d_keys, n_lists, n_queries, k, d_out, None))
+
+    def merge_gathered(self, d_gathered: int, n_lists: int, span: int, totals_offset: int, n_queries: int, k: int,
+                       d_keys: int, d_scores: int, d_docids: int, d_counts: int, d_totals: int):
+        """Merge + count + decode of an all-gathered exchange buffer; runs on the handle's stream."""
+        _check(self.lib, self.lib.bm25f_merge_gathered(self._h, d_gathered, n_lists, span, totals_offset, n_queries, k,
+                                                       d_keys, d_scores, d_docids, d_counts, d_totals, None))
 
     def merge_final_lists(self, d_vals: int, d_docids: int, n_lists: int, n_queries: int, k: int, d_out_final: int,
                           d_out_docids: int, d_out_counts: int):

@@ -1229,6 +1229,36 @@ __global__ void k_decode_keys(const unsigned long long* __restrict__ keys, uint3
   }
 }
 
+// The exchange step of a document-sharded batch in one kernel after the merge: decode the merged keys and add up
+// the shards' match counts.  `gathered` holds, per shard, `span` 64-bit words: its [Q * k] keys first, its [Q]
+// totals at word `tot_off`.
+__global__ void k_decode_keys_sum(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ gathered,
+                                  int n_lists, unsigned long long span, unsigned long long tot_off, uint32_t Q, int k,
+                                  float* __restrict__ scores, uint32_t* __restrict__ docids, uint32_t* __restrict__ counts,
+                                  unsigned long long* __restrict__ totals) {
+  const uint32_t q = blockIdx.x;
+  if (q >= Q) return;
+  int n = 0;
+  for (int i = threadIdx.x; i < k; i += blockDim.x) {
+    const unsigned long long key = keys[(size_t)q * k + i];
+    const bool ok = key != 0ull;
+    scores[(size_t)q * k + i] = ok ? key_score(key) : -INFINITY;
+    docids[(size_t)q * k + i] = ok ? key_doc(key) : 0xFFFFFFFFu;
+    n += ok;
+  }
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    s_n = 0;
+    unsigned long long t = 0ull;
+    for (int l = 0; l < n_lists; ++l) t += gathered[(size_t)l * span + tot_off + q];
+    totals[q] = t;
+  }
+  __syncthreads();
+  if (n) atomicAdd(&s_n, n);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[q] = (uint32_t)s_n;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -1981,8 +2011,11 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
 
   // A small batch (a single interactive query is the reference's use) would be a handful of items on
   // a handful of warps: cut its items finer so that the whole GPU works on it.
+  // Work items are cut so that the batch spreads over every warp of the GPU: a single interactive query (the
+  // reference's use) as well as a 10k-query batch on a 1/8 document shard, where no query alone reaches the
+  // default item size and the heaviest one would otherwise pin one warp for the whole step.
   uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
-  if (Q <= 1024) {
+  {
     uint64_t total = 0;
     for (uint32_t i = 0; i < NL; ++i) {
       const uint32_t term = resolve_term(h, b->leaf_term[i]);
@@ -2777,6 +2810,37 @@ int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint3
                                                                reinterpret_cast<unsigned long long*>(d_out_keys));
     CU(cudaGetLastError());
   }
+  return 0;
+}
+
+int bm25f_plan_gather_span(bm25f_plan* p, uint64_t** d_base, uint64_t* span_words, uint64_t* totals_offset_words) {
+  if (!p || !d_base || !span_words || !totals_offset_words) return fail(BM25F_EINVAL, "null argument");
+  if (p->final_mode) return fail(BM25F_EINVAL, "plans with a final() step have no 64-bit key lists");
+  if (p->owns_memory) return fail(BM25F_EINVAL, "only workspace plans (bm25f_prepare_arena) keep keys and totals in one span");
+  *d_base = reinterpret_cast<uint64_t*>(p->d_keys);
+  *totals_offset_words = (uint64_t)(p->d_totals - p->d_keys);
+  *span_words = *totals_offset_words + p->Q;
+  return 0;
+}
+
+int bm25f_merge_gathered(bm25f_handle* h, const uint64_t* d_gathered, int n_lists, uint64_t span_words, uint64_t totals_offset_words,
+                         uint32_t n_queries, int k, uint64_t* d_keys, float* d_scores, uint32_t* d_docids, uint32_t* d_counts,
+                         uint64_t* d_totals, void* stream) {
+  if (!h || !d_gathered || !d_keys || !d_scores || !d_docids || !d_counts || !d_totals) return fail(BM25F_EINVAL, "null argument");
+  if (k < 1 || k > BM25F_MAX_K || n_lists < 1 || span_words < (uint64_t)n_queries * k) return fail(BM25F_EINVAL, "bad k, n_lists or span");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  if (!n_queries) return 0;
+  int kp = 1;
+  while (kp < k) kp <<= 1;
+  const unsigned long long* g = reinterpret_cast<const unsigned long long*>(d_gathered);
+  unsigned long long* out = reinterpret_cast<unsigned long long*>(d_keys);
+  if (k <= 32) k_merge_topk_warp<<<(n_queries + 7) / 8, 256, 0, st>>>(g, nullptr, 1, n_lists, (unsigned long long)span_words, n_queries, k, out);
+  else k_merge_topk<<<n_queries, 128, (size_t)2 * kp * 8, st>>>(g, nullptr, 1, n_lists, (unsigned long long)span_words, n_queries, k, kp, out);
+  CU(cudaGetLastError());
+  k_decode_keys_sum<<<n_queries, 64, 0, st>>>(out, g, n_lists, (unsigned long long)span_words, (unsigned long long)totals_offset_words,
+                                              n_queries, k, d_scores, d_docids, d_counts, reinterpret_cast<unsigned long long*>(d_totals));
+  CU(cudaGetLastError());
   return 0;
 }
 

@@ -8,9 +8,9 @@ offset (W8).  Replicated on every rank: the term dictionary, the corpus-wide ``d
 
 Per batch the path has ONE exchange step: every rank scores its shard and produces, per
 query, a local top-k as 64-bit W11 keys over *global* docnums and a local match count;
-then ``all_gather`` of the ``Q*k`` keys and ``all_reduce(sum)`` of the ``Q`` totals, and the
-merge kernel (``bm25f_merge_keys``) selects the top-k of the ``G*k`` candidates per query on
-every rank.  PyTorch supplies the NCCL plumbing and the receive buffers; scoring, top-k and
+then ONE ``all_gather`` of the span of the plan's workspace that holds both the ``Q*k`` keys and the ``Q``
+totals, and ``bm25f_merge_gathered`` (merge kernel + a decode kernel that also adds up the totals) selects the
+top-k of the ``G*k`` candidates per query on every rank.  PyTorch supplies the NCCL plumbing and the receive buffers; scoring, top-k and
 the merge are the library's own kernels.
 """
 from __future__ import annotations
@@ -56,6 +56,16 @@ def merge_keys_host(gathered: np.ndarray, k: int) -> np.ndarray:
     allk = np.transpose(gathered, (1, 0, 2)).reshape(Q, G * k)
     allk = np.sort(allk.astype(np.uint64), axis=1)[:, ::-1]      # descending = W11 order
     return np.ascontiguousarray(allk[:, :k])
+
+
+def merge_gathered_host(gathered: np.ndarray, n_queries: int, k: int, totals_offset: int):
+    """Host restatement of ``bm25f_merge_gathered`` for CPU (gloo) tests: ``gathered`` is ``[G, span]`` uint64, every
+    row a shard's ``[Q * k]`` keys followed (at word ``totals_offset``) by its ``[Q]`` match counts.  Returns
+    ``(merged keys [Q, k], totals [Q])``."""
+    G = gathered.shape[0]
+    keys = gathered[:, :n_queries * k].reshape(G, n_queries, k)
+    totals = gathered[:, totals_offset:totals_offset + n_queries].astype(np.uint64).sum(axis=0)
+    return merge_keys_host(keys, k), totals
 
 
 def merge_final_host(vals: np.ndarray, docids: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -117,7 +127,7 @@ class ShardedSearcher:
         b = self._bufs.get(key)
         if b is None:
             dev = "cuda:%d" % self.device
-            b = dict(gathered=torch.empty(self.world * Q * k, dtype=torch.int64, device=dev),
+            b = dict(gathered=None,                   # sized on first use from the plan's gather span
                      merged=torch.empty(Q * k, dtype=torch.int64, device=dev),
                      totals=torch.empty(Q, dtype=torch.int64, device=dev),
                      scores=torch.empty(Q * k, dtype=torch.float32, device=dev),
@@ -133,19 +143,21 @@ class ShardedSearcher:
         Q, k = plan.n_queries, plan.k
         b = self._buffers(Q, k, slot)
         plan.execute()
-        d_keys, d_totals = plan.device_results()
-        local_keys = device_view(d_keys, Q * k, self.device)
-        local_totals = device_view(d_totals, Q, self.device)
         if self.world > 1:
-            dist.all_gather_into_tensor(b["gathered"], local_keys, group=self.group)
-            b["totals"].copy_(local_totals)
-            dist.all_reduce(b["totals"], op=dist.ReduceOp.SUM, group=self.group)
-            self.engine.merge_keys(b["gathered"].data_ptr(), self.world, Q, k, b["merged"].data_ptr())
+            # ONE collective and two kernels: the plan's keys and match counts sit in one span of its workspace
+            base, span, tot_off = plan.gather_span()
+            g = b["gathered"]
+            if g is None or g.numel() != self.world * span:
+                g = b["gathered"] = torch.empty(self.world * span, dtype=torch.int64, device="cuda:%d" % self.device)
+            dist.all_gather_into_tensor(g, device_view(base, span, self.device), group=self.group)
+            self.engine.merge_gathered(g.data_ptr(), self.world, span, tot_off, Q, k, b["merged"].data_ptr(), b["scores"].data_ptr(),
+                                       b["docids"].data_ptr(), b["counts"].data_ptr(), b["totals"].data_ptr())
         else:
-            b["merged"].copy_(local_keys)
-            b["totals"].copy_(local_totals)
-        self.engine.decode_keys(b["merged"].data_ptr(), Q, k, b["scores"].data_ptr(), b["docids"].data_ptr(),
-                                b["counts"].data_ptr())
+            d_keys, d_totals = plan.device_results()
+            b["merged"].copy_(device_view(d_keys, Q * k, self.device))
+            b["totals"].copy_(device_view(d_totals, Q, self.device))
+            self.engine.decode_keys(b["merged"].data_ptr(), Q, k, b["scores"].data_ptr(), b["docids"].data_ptr(),
+                                    b["counts"].data_ptr())
         return b
 
     def _search_packed_final(self, batch: _ffi.PackedBatch, k: int):

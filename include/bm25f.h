@@ -229,6 +229,15 @@ int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_
  * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
+/* The exchange step of a document-sharded batch with ONE collective: a workspace plan (bm25f_prepare_arena) keeps its
+ * [n_queries * k] keys and its [n_queries] match counts in one span of 64-bit words (bm25f_plan_gather_span: first word,
+ * length, offset of the counts), so a single all-gather of that span moves both; bm25f_merge_gathered then merges the
+ * n_lists key lists per query (W11 order, as Whoosh's one collector over all segments), adds up the counts and decodes:
+ * d_keys [n_queries * k] merged keys, d_scores / d_docids [n_queries * k], d_counts / d_totals [n_queries]. */
+int  bm25f_plan_gather_span(bm25f_plan* plan, uint64_t** d_base, uint64_t* span_words, uint64_t* totals_offset_words);
+int  bm25f_merge_gathered(bm25f_handle* h, const uint64_t* d_gathered, int n_lists, uint64_t span_words,
+                          uint64_t totals_offset_words, uint32_t n_queries, int k, uint64_t* d_keys, float* d_scores,
+                          uint32_t* d_docids, uint32_t* d_counts, uint64_t* d_totals, void* stream);
 /* Final mode (my_whoosh.py:127-154) across document shards (Whoosh segments with doc offsets, W8).
  * bm25f_plan_device_final: the device-resident results of a plan
  * prepared under a final() step (final values [n_queries * k] float64, global docnums [n_queries * k] with

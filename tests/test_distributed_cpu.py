@@ -14,7 +14,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from document_search_engine_b200.corpus import make_corpus, make_queries
-from document_search_engine_b200.distributed import decode_keys_host, merge_final_host, merge_keys_host
+from document_search_engine_b200.distributed import decode_keys_host, merge_final_host, merge_gathered_host, merge_keys_host
 from document_search_engine_b200.searching import make_keys
 from oracle.numpy_oracle import NumpyOracle
 
@@ -58,6 +58,16 @@ def _worker(rank, world, port, out):
         tot = torch.from_numpy(totals.copy())
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         merged = merge_keys_host(gathered.numpy().view(np.uint64).reshape(world, len(qs), K), K)
+        # the same exchange with ONE collective, as ShardedSearcher.run_plan does it: keys and match counts travel in
+        # one span (here with the padding the library's workspace puts between them)
+        tot_off = len(qs) * K + 32
+        span = np.zeros(tot_off + len(qs), dtype=np.uint64)
+        span[:len(qs) * K] = keys.reshape(-1)
+        span[tot_off:] = totals.astype(np.uint64)
+        g2 = torch.empty(world * span.size, dtype=torch.int64)
+        dist.all_gather_into_tensor(g2, torch.from_numpy(span.view(np.int64)))
+        merged2, tot2 = merge_gathered_host(g2.numpy().view(np.uint64).reshape(world, span.size), len(qs), K, tot_off)
+        assert np.array_equal(merged2, merged) and np.array_equal(tot2.astype(np.int64), tot.numpy())
         if rank == 0:
             scores, docids, counts = decode_keys_host(merged)
             np.savez(out, scores=scores, docids=docids, counts=counts, totals=tot.numpy())

@@ -61,7 +61,7 @@ def test_config1_variants_groups(cfg1):
 
 
 @pytest.mark.parametrize("variant,chunk,stages", [(1, 64, 2), (1, 256, 8), (1, 2048, 3), (2, 0, 0)])
-@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (19456, 1 << 20)])
+@pytest.mark.parametrize("tile_docs,split", [(256, 512), (1024, 4096), (4096, 0), (16384, 0), (17408, 1 << 20)])
 def test_tiling_and_splitting(cfg1, tile_docs, split, variant, chunk, stages):
     """Tiny tiles, tiny work items, tiny/huge pipeline stages: many tiles per query, chunks that
     split posting sub-ranges, many partial lists to merge."""
