@@ -1904,8 +1904,7 @@ void bm25f_plan_destroy(bm25f_plan* p) {
   cudaFree(p->d_items);
   cudaFree(p->d_bounds);
   cudaFree(p->d_part_keys);
-  cudaFree(p->d_keys);
-  cudaFree(p->d_totals);
+  cudaFree(p->d_keys);          // the totals live behind the keys
   cudaFree(p->d_scores);
   cudaFree(p->d_docids);
   cudaFree(p->d_counts);
@@ -2021,9 +2020,11 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       const uint32_t term = resolve_term(h, b->leaf_term[i]);
       if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
-    const uint64_t per_item = std::max<uint64_t>(4096, total / ((uint64_t)h->n_sms * 32));   // ~2 items per stream-kernel warp
+    // ~2 items per stream-kernel warp; a large batch is not cut finer than 32k postings an item (every item costs the
+    // planner and the merge: at 8 shards x 10k queries finer items made the step host-bound)
+    const uint64_t per_item = std::max<uint64_t>(Q <= 1024 ? 4096 : 32768, total / ((uint64_t)h->n_sms * 32));
     if (per_item < wsplit) {
-      is_split = (uint32_t)std::max<uint64_t>(128, (uint64_t)is_split * per_item / wsplit);
+      is_split = (uint32_t)std::max<uint64_t>(Q <= 1024 ? 128 : 1024, (uint64_t)is_split * per_item / wsplit);
       tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
       wsplit = (uint32_t)per_item;
     }
@@ -2382,8 +2383,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     RCP(dev_alloc(&p->d_items, n_it));
     RCP(dev_alloc(&p->d_bounds, n_bounds));
     RCP(dev_alloc(&p->d_part_keys, (size_t)n_parts * k));
-    RCP(dev_alloc(&p->d_keys, (size_t)Q * k));
-    RCP(dev_alloc(&p->d_totals, (size_t)Q + 8));
+    // keys and totals in one allocation: one span for the sharded exchange (bm25f_plan_gather_span)
+    RCP(dev_alloc(&p->d_keys, align_up((size_t)Q * k * 8) / 8 + (size_t)Q + 8));
+    p->d_totals = p->d_keys + align_up((size_t)Q * k * 8) / 8;
     RCP(dev_alloc(&p->d_scores, (size_t)Q * k));
     RCP(dev_alloc(&p->d_docids, (size_t)Q * k));
     RCP(dev_alloc(&p->d_counts, Q));
@@ -2816,7 +2818,6 @@ int bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint3
 int bm25f_plan_gather_span(bm25f_plan* p, uint64_t** d_base, uint64_t* span_words, uint64_t* totals_offset_words) {
   if (!p || !d_base || !span_words || !totals_offset_words) return fail(BM25F_EINVAL, "null argument");
   if (p->final_mode) return fail(BM25F_EINVAL, "plans with a final() step have no 64-bit key lists");
-  if (p->owns_memory) return fail(BM25F_EINVAL, "only workspace plans (bm25f_prepare_arena) keep keys and totals in one span");
   *d_base = reinterpret_cast<uint64_t*>(p->d_keys);
   *totals_offset_words = (uint64_t)(p->d_totals - p->d_keys);
   *span_words = *totals_offset_words + p->Q;

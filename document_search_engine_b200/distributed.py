@@ -127,14 +127,29 @@ class ShardedSearcher:
         b = self._bufs.get(key)
         if b is None:
             dev = "cuda:%d" % self.device
+            # the decoded results sit in ONE buffer (totals | scores | docids | counts) so that a step brings them to
+            # the host with one copy
+            out = torch.empty(self._out_words(Q, k), dtype=torch.int64, device=dev)
+            o32 = out.view(torch.int32)
             b = dict(gathered=None,                   # sized on first use from the plan's gather span
                      merged=torch.empty(Q * k, dtype=torch.int64, device=dev),
-                     totals=torch.empty(Q, dtype=torch.int64, device=dev),
-                     scores=torch.empty(Q * k, dtype=torch.float32, device=dev),
-                     docids=torch.empty(Q * k, dtype=torch.int32, device=dev),
-                     counts=torch.empty(Q, dtype=torch.int32, device=dev))
+                     out=out, totals=out[:Q],
+                     scores=o32[2 * Q:2 * Q + Q * k].view(torch.float32),
+                     docids=o32[2 * Q + Q * k:2 * Q + 2 * Q * k],
+                     counts=o32[2 * Q + 2 * Q * k:3 * Q + 2 * Q * k])
             self._bufs[key] = b
         return b
+
+    @staticmethod
+    def _out_words(Q: int, k: int) -> int:
+        return Q + (2 * Q * k + Q + 1) // 2
+
+    @staticmethod
+    def _split_out(h: np.ndarray, Q: int, k: int):
+        """``(scores, docids, counts, totals)`` views of one result buffer (int64 words, layout of ``_buffers``)."""
+        w32 = h.view(np.uint32)
+        return (w32[2 * Q:2 * Q + Q * k].view(np.float32).reshape(Q, k), w32[2 * Q + Q * k:2 * Q + 2 * Q * k].reshape(Q, k),
+                w32[2 * Q + 2 * Q * k:3 * Q + 2 * Q * k], h[:Q].view(np.uint64))
 
     def run_plan(self, plan: _ffi.Plan, slot: int = 0):
         """Execute a prepared plan on this shard, exchange, merge.  Everything is enqueued on
@@ -205,13 +220,9 @@ class ShardedSearcher:
             b = self.run_plan(plan)
             Q = batch.n_queries
             h = self._host_buffers(Q, k)
-            for name in ("scores", "docids", "counts", "totals"):
-                h[name].copy_(b[name], non_blocking=True)
+            h.copy_(b["out"], non_blocking=True)
             torch.cuda.current_stream(self.device).synchronize()
-            scores = h["scores"].numpy().reshape(Q, k).copy()
-            docids = h["docids"].numpy().view(np.uint32).reshape(Q, k).copy()
-            counts = h["counts"].numpy().view(np.uint32).copy()
-            totals = h["totals"].numpy().view(np.uint64).copy()
+            scores, docids, counts, totals = self._split_out(h.numpy().copy(), Q, k)
         finally:
             plan.close()
         return scores, docids, counts, totals
@@ -235,10 +246,7 @@ class ShardedSearcher:
             plan, h, ev, Q = item
             try:
                 ev.synchronize()
-                return (h["scores"].numpy().reshape(Q, k).copy(),
-                        h["docids"].numpy().view(np.uint32).reshape(Q, k).copy(),
-                        h["counts"].numpy().view(np.uint32).copy(),
-                        h["totals"].numpy().view(np.uint64).copy())
+                return self._split_out(h.numpy().copy(), Q, k)
             finally:
                 plan.close()
 
@@ -248,8 +256,7 @@ class ShardedSearcher:
                 Q = batch.n_queries
                 b = self.run_plan(plan, slot)
                 h = self._host_buffers(Q, k, slot)
-                for name in ("scores", "docids", "counts", "totals"):
-                    h[name].copy_(b[name], non_blocking=True)
+                h.copy_(b["out"], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(stream)
                 cur = (plan, h, ev, Q)
@@ -270,9 +277,5 @@ class ShardedSearcher:
         key = ("host", Q, k, slot)
         h = self._bufs.get(key)
         if h is None:
-            h = dict(scores=torch.empty(Q * k, dtype=torch.float32).pin_memory(),
-                     docids=torch.empty(Q * k, dtype=torch.int32).pin_memory(),
-                     counts=torch.empty(Q, dtype=torch.int32).pin_memory(),
-                     totals=torch.empty(Q, dtype=torch.int64).pin_memory())
-            self._bufs[key] = h
+            h = self._bufs[key] = torch.empty(self._out_words(Q, k), dtype=torch.int64).pin_memory()
         return h

@@ -229,7 +229,7 @@ int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_
  * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
-/* The exchange step of a document-sharded batch with ONE collective: a workspace plan (bm25f_prepare_arena) keeps its
+/* The exchange step of a document-sharded batch with ONE collective: a plan keeps its
  * [n_queries * k] keys and its [n_queries] match counts in one span of 64-bit words (bm25f_plan_gather_span: first word,
  * length, offset of the counts), so a single all-gather of that span moves both; bm25f_merge_gathered then merges the
  * n_lists key lists per query (W11 order, as Whoosh's one collector over all segments), adds up the counts and decodes:
