@@ -1014,6 +1014,7 @@ __device__ __forceinline__ unsigned long long warp_topk_kth(const unsigned long 
 #include "stream.cuh"
 #include "team.cuh"
 #include "isect.cuh"
+#include "plan.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Merge of sorted top-k lists.  List l of query q starts at keys + start(q) + l * stride.
@@ -1358,6 +1359,11 @@ struct bm25f_handle {
   int tl_ctas_per_sm = 0;
   int is_ctas_per_sm = 0;
   bool serial_streams = false;          // option: never run the second-stream kernels beside the first-stream ones
+  bool host_plan = false;               // option: never plan a batch on the device (plan.cuh)
+  unsigned long long* d_term_offsets = nullptr;   // the device planner's copies of term_offsets / term_field
+  uint8_t* d_term_field = nullptr;
+  unsigned int* h_ctr = nullptr;        // pinned: the device planner's counters of the last executed plan (statistics)
+  bool stats_from_ctr = false;          // ... which bm25f_get_stats folds in after a synchronize
   uint32_t is_ratio = 1, is_split = 2048, is_or_limit = 40000;   // candidate-driven AND: cost of a lookup in postings, candidates per item
   static constexpr int EV_RING = 32;   // executes whose timings may be pending at once
   cudaEvent_t ev[EV_RING][6] = {};     // [0..3] step phases; [4], [5] bracket the stream kernel alone
@@ -1414,6 +1420,8 @@ struct bm25f_plan {
   double* d_final = nullptr;           // final mode: [Q * k] final values
   bool submitted = false;       // bm25f_submit: bm25f_execute also brings the results to the arena's pinned h_out
   bool simple_kernel = false;   // k_score_topk instead of k_score_pipe (option, or a non-positive leaf weight)
+  bool device_planned = false;  // plan.cuh: the items and their counts exist only on the device (d_ctr)
+  unsigned int* d_ctr = nullptr;
 };
 
 namespace {
@@ -1507,6 +1515,9 @@ void bm25f_destroy(bm25f_handle* h) {
   cudaFree(h->d_final_add);
   cudaFree(h->d_final_blk);
   cudaFree(h->d_prof);
+  cudaFree(h->d_term_offsets);
+  cudaFree(h->d_term_field);
+  if (h->h_ctr) cudaFreeHost(h->h_ctr);
   for (auto& A : h->arenas) {
     cudaFree(A.d);
     if (A.h) cudaFreeHost(A.h);
@@ -1585,6 +1596,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
   }
   if (opts) h->serial_streams = opts->serial_streams != 0;
+  if (opts) h->host_plan = opts->host_plan != 0;
   if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
@@ -1810,6 +1822,13 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     }
     t = t2;
   }
+  // the device planner's view of the posting lists (after the compaction above)
+  RCT(dev_alloc(&h->d_term_offsets, h->n_terms + 1, h));
+  RCT(dev_alloc(&h->d_term_field, h->n_terms + 1, h));
+  CUT(cudaMemcpyAsync(h->d_term_offsets, h->term_offsets.data(), (h->n_terms + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+  if (h->n_terms) CUT(cudaMemcpyAsync(h->d_term_field, h->term_field.data(), h->n_terms, cudaMemcpyHostToDevice, h->stream));
+  CUT(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ctr), PL_CTR_BYTES, cudaHostAllocDefault));
+  memset(h->h_ctr, 0, PL_CTR_BYTES);
   CUT(cudaStreamSynchronize(h->stream));
   free_tmp();
 #undef RCT
@@ -1944,6 +1963,24 @@ void order_items(const std::vector<ItemRec>& items, const std::vector<uint64_t>&
   for (size_t i = 0; i < items.size(); ++i) out[count[NB - 1 - bucket(w[i])]++] = items[i];
 }
 
+// Work items are cut so that the batch spreads over every warp of the GPU: a single interactive query (the
+// reference's use) as well as a 10k-query batch on a 1/8 document shard, where no query alone reaches the
+// default item size and the heaviest one would otherwise pin one warp for the whole step.
+void item_sizes(const bm25f_handle* h, uint32_t Q, uint64_t total, uint32_t* wsplit_out, uint32_t* is_split_out, uint32_t* tl_split_out) {
+  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
+  // ~2 items per stream-kernel warp; a large batch is not cut finer than 32k postings an item (every item costs the
+  // planner and the merge: at 8 shards x 10k queries finer items made the step host-bound)
+  const uint64_t per_item = std::max<uint64_t>(Q <= 1024 ? 4096 : 32768, total / ((uint64_t)h->n_sms * 32));
+  if (per_item < wsplit) {
+    is_split = (uint32_t)std::max<uint64_t>(Q <= 1024 ? 128 : 1024, (uint64_t)is_split * per_item / wsplit);
+    tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
+    wsplit = (uint32_t)per_item;
+  }
+  *wsplit_out = wsplit;
+  *is_split_out = is_split;
+  *tl_split_out = tl_split;
+}
+
 // Planner threads of this process: BM25F_PLAN_THREADS, else the host's cores shared out between the ranks of
 // the box (torchrun exports LOCAL_WORLD_SIZE; one process per GPU, and all of them plan at the same time
 // because the collectives keep them in step), at most 8.
@@ -1961,6 +1998,166 @@ unsigned plan_thread_budget() {
   return budget;
 }
 
+// Batches the warp kernels serve alone are planned on the device (plan.cuh): the host checks eligibility, stages the
+// caller's arrays in the arena's pinned memory and enqueues one copy and three small kernels on the copy stream.
+// *done stays false when the batch is not eligible (the host planner then runs, and reports malformed input).
+constexpr uint32_t DEVICE_PLAN_MIN_Q = 256;   // below this the host plans faster than three launches and full grids cost
+
+int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out, bool* done) {
+  *done = false;
+  const uint32_t Q = b->n_queries, NL = b->n_leaves;
+  static const bool trace = getenv("BM25F_TRACE") != nullptr;
+#define DECLINE(why)                                                                          \
+  do {                                                                                        \
+    if (trace) fprintf(stderr, "[bm25f prepare] host planner: query %u %s\n", qi, why);      \
+    return 0;                                                                                 \
+  } while (0)
+  uint64_t total = 0;
+  for (uint32_t qi = 0; qi < Q; ++qi) {
+    const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
+    if (e < a || e > NL) DECLINE("has a bad leaf range");
+    if (e - a > (uint32_t)PL_MAX_LEAVES) DECLINE("has more than 8 leaves");
+    const uint32_t G = b->query_n_groups[qi];
+    if (G > (uint32_t)PL_MAX_LEAVES) DECLINE("has more than 8 groups");
+    uint32_t prev_g = 0;
+    for (uint32_t i = a; i < e; ++i) {
+      const uint32_t g = b->leaf_group[i];
+      if (g >= G || g < prev_g) DECLINE("has a NOT clause or malformed groups");
+      prev_g = g;
+      const float w = b->leaf_weight[i];
+      if (!std::isfinite(w)) DECLINE("has a non-finite weight");
+      const uint32_t term = resolve_term(h, b->leaf_term[i]);
+      if (term == BM25F_TERM_UNKNOWN) continue;          // dropped: its weight (0 for a term no shard knows) does not matter
+      if (term >= h->n_real_terms + h->n_fields) DECLINE("names a posting list out of range");
+      if (!(w > 1e-30f)) DECLINE("has a non-positive weight");
+      total += h->term_offsets[term + 1] - h->term_offsets[term];
+    }
+  }
+#undef DECLINE
+  uint32_t wsplit, is_split, tl_split;
+  item_sizes(h, Q, total, &wsplit, &is_split, &tl_split);
+
+  const int slot = h->arena_next;
+  bm25f_handle::Arena& A = h->arenas[slot];
+  if (A.submitted) return fail(BM25F_EINVAL, "two submitted batches are in flight: bm25f_collect the oldest one first");
+  h->arena_next ^= 1;
+
+  // pinned staging: the caller's arrays, back to back
+  size_t hoff = 0;
+  auto htake = [&](size_t bytes) { const size_t o = hoff; hoff += align_up(bytes); return o; };
+  const size_t i_qoff = htake((size_t)(Q + 1) * 4), i_ng = htake(Q), i_term = htake((size_t)NL * 4), i_w = htake((size_t)NL * 4),
+               i_g = htake(NL);
+  const size_t in_bytes = hoff;
+  if (A.h_cap < in_bytes) {
+    if (A.h) cudaFreeHost(A.h);
+    A.h = nullptr;
+    A.h_cap = 0;
+    const size_t cap = align_up(in_bytes * 2 + (1u << 20), 1u << 20);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&A.h), cap, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e));
+    A.h_cap = cap;
+  }
+  memcpy(A.h + i_qoff, b->query_leaf_offsets, (size_t)(Q + 1) * 4);
+  memcpy(A.h + i_ng, b->query_n_groups, Q);
+  memcpy(A.h + i_term, b->leaf_term, (size_t)NL * 4);
+  memcpy(A.h + i_w, b->leaf_weight, (size_t)NL * 4);
+  memcpy(A.h + i_g, b->leaf_group, NL);
+
+  // every query may be cut into max_split items at most, so the item array cannot overflow
+  const uint32_t max_split = 4u + 65536u / Q;
+  const size_t item_cap = (size_t)Q * max_split;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
+  const size_t o_in = take(in_bytes), o_leaves = take((size_t)NL * sizeof(LeafRec)), o_queries = take((size_t)Q * sizeof(QueryRec)),
+               o_items = take(item_cap * sizeof(ItemRec)), o_tmp = take((size_t)Q * sizeof(uint4)), o_ctr = take(PL_CTR_BYTES),
+               o_part = take(item_cap * k * 8), o_keys = take((size_t)Q * k * 8), o_tot = take((size_t)(Q + 8) * 8),
+               o_sc = take((size_t)Q * k * 4), o_doc = take((size_t)Q * k * 4), o_cnt = take((size_t)Q * 4);
+  if (off > A.d_cap) {
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->copy_stream));
+    cudaFree(A.d);
+    A.d = nullptr;
+    A.d_cap = 0;
+    const size_t cap = align_up(off + off / 2, 1u << 20);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&A.d), cap);
+    if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaMalloc(%zu): %s", cap, cudaGetErrorString(e));
+    A.d_cap = cap;
+  }
+  bm25f_plan* p = new (std::nothrow) bm25f_plan();
+  if (!p) return fail(BM25F_ENOMEM, "host allocation failed");
+  unsigned char* d = A.d;
+  p->h = h;
+  p->Q = Q;
+  p->k = k;
+  p->kp = 1;
+  while (p->kp < k) p->kp <<= 1;
+  p->cap = pipe_key_capacity(k, (int)h->NT);
+  p->n_leaves = NL;
+  p->T = 1;
+  p->owns_memory = false;
+  p->arena = slot;
+  p->device_planned = true;
+  p->n_w4 = 1;                       // "maybe": the kernels read the counts from d_ctr
+  p->n_is = 1;
+  p->n_w8 = k <= 32 ? 1 : 0;
+  p->n_parts = (uint32_t)item_cap;
+  p->d_leaves = reinterpret_cast<LeafRec*>(d + o_leaves);
+  p->d_queries = reinterpret_cast<QueryRec*>(d + o_queries);
+  p->d_items = reinterpret_cast<ItemRec*>(d + o_items);
+  p->d_items_w4 = p->d_items_w8 = p->d_items_is = p->d_items;
+  p->d_ctr = reinterpret_cast<unsigned int*>(d + o_ctr);
+  p->d_part_keys = reinterpret_cast<unsigned long long*>(d + o_part);
+  p->d_keys = reinterpret_cast<unsigned long long*>(d + o_keys);
+  p->d_totals = reinterpret_cast<unsigned long long*>(d + o_tot);
+  p->d_scores = reinterpret_cast<float*>(d + o_sc);
+  p->d_docids = reinterpret_cast<uint32_t*>(d + o_doc);
+  p->d_counts = reinterpret_cast<uint32_t*>(d + o_cnt);
+
+  PlanParams pp;
+  pp.term_offsets = h->d_term_offsets;
+  pp.term_field = h->d_term_field;
+  pp.q_off = reinterpret_cast<const uint32_t*>(d + o_in + i_qoff);
+  pp.q_ng = d + o_in + i_ng;
+  pp.leaf_term = reinterpret_cast<const uint32_t*>(d + o_in + i_term);
+  pp.leaf_w = reinterpret_cast<const float*>(d + o_in + i_w);
+  pp.leaf_g = d + o_in + i_g;
+  pp.leaves = p->d_leaves;
+  pp.queries = p->d_queries;
+  pp.items = p->d_items;
+  pp.tmp = reinterpret_cast<uint4*>(d + o_tmp);
+  pp.ctr = p->d_ctr;
+  pp.Q = Q;
+  pp.n_docs = (uint32_t)h->n_docs;
+  pp.n_fields = h->n_fields;
+  pp.n_real_terms = (uint32_t)h->n_real_terms;
+  pp.max_split = max_split;
+  pp.wsplit = wsplit;
+  pp.is_split = is_split;
+  pp.tl_split = tl_split;
+  pp.is_or_limit = h->is_or_limit;
+  pp.is_ratio = h->is_ratio;
+  pp.st_slot_bytes = h->st_slot_bytes;
+  pp.tl_slot_bytes = h->tl_slot_bytes;
+  pp.k = k;
+  cudaStream_t up = h->copy_stream;
+  cudaError_t ce = cudaMemcpyAsync(d + o_in, A.h, in_bytes, cudaMemcpyHostToDevice, up);
+  if (ce == cudaSuccess) ce = cudaMemsetAsync(p->d_ctr, 0, PL_CTR_BYTES, up);
+  if (ce == cudaSuccess) {
+    k_plan_queries<<<(Q + 127) / 128, 128, 0, up>>>(pp);
+    k_plan_scan<<<1, 1024, 0, up>>>(pp);
+    k_plan_items<<<(Q + 127) / 128, 128, 0, up>>>(pp);
+    ce = cudaGetLastError();
+  }
+  if (ce == cudaSuccess) ce = cudaEventRecord(A.ev_ready, up);
+  if (ce != cudaSuccess) {
+    delete p;
+    return fail(BM25F_ECUDA, "device planner: %s", cudaGetErrorString(ce));
+  }
+  *out = p;
+  *done = true;
+  return 0;
+}
+
 // Host planning + upload.  With use_arena the plan's buffers live in the handle's grow-only
 // workspaces (pinned host staging, one device arena): no allocation on the hot path.
 int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan** out, bool use_arena) {
@@ -1973,6 +2170,11 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
   if (NL && (!b->leaf_term || !b->leaf_weight || !b->leaf_group)) return fail(BM25F_EINVAL, "null leaf arrays");
   if (Q && (b->query_leaf_offsets[0] != 0 || b->query_leaf_offsets[Q] != NL)) return fail(BM25F_EINVAL, "query_leaf_offsets does not span n_leaves");
   CU(cudaSetDevice(h->device));
+  if (use_arena && !h->host_plan && h->variant == 0 && !h->d_final_add && !b->after_keys && k <= FAST_MAX_K && Q >= DEVICE_PLAN_MIN_Q) {
+    bool done = false;
+    const int rc = prepare_on_device(h, b, k, out, &done);
+    if (rc || done) return rc;
+  }
 
   const uint32_t S = h->S;
   const uint32_t T = (uint32_t)std::max<uint64_t>(1, (h->n_docs + S - 1) / S);
@@ -2008,26 +2210,14 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     queries = own_queries.data();
   }
 
-  // A small batch (a single interactive query is the reference's use) would be a handful of items on
-  // a handful of warps: cut its items finer so that the whole GPU works on it.
-  // Work items are cut so that the batch spreads over every warp of the GPU: a single interactive query (the
-  // reference's use) as well as a 10k-query batch on a 1/8 document shard, where no query alone reaches the
-  // default item size and the heaviest one would otherwise pin one warp for the whole step.
-  uint32_t wsplit = h->wsplit, is_split = h->is_split, tl_split = h->tl_split;
+  uint32_t wsplit, is_split, tl_split;
   {
     uint64_t total = 0;
     for (uint32_t i = 0; i < NL; ++i) {
       const uint32_t term = resolve_term(h, b->leaf_term[i]);
       if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
-    // ~2 items per stream-kernel warp; a large batch is not cut finer than 32k postings an item (every item costs the
-    // planner and the merge: at 8 shards x 10k queries finer items made the step host-bound)
-    const uint64_t per_item = std::max<uint64_t>(Q <= 1024 ? 4096 : 32768, total / ((uint64_t)h->n_sms * 32));
-    if (per_item < wsplit) {
-      is_split = (uint32_t)std::max<uint64_t>(Q <= 1024 ? 128 : 1024, (uint64_t)is_split * per_item / wsplit);
-      tl_split = (uint32_t)std::max<uint64_t>(16384, (uint64_t)tl_split * per_item / wsplit);
-      wsplit = (uint32_t)per_item;
-    }
+    item_sizes(h, Q, total, &wsplit, &is_split, &tl_split);
   }
   // Planning is per query and independent: ranges of queries are planned by a few host threads (each
   // into its own item lists and counters), then stitched together.  A query's leaf records live at
@@ -2085,7 +2275,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
         if (!neg) gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
       }
       if (neg) { ++n_neg_in; continue; }
-      if (!(b->leaf_weight[i] > 1e-30f)) all_pos = false;
+      if (term != BM25F_TERM_UNKNOWN && !(b->leaf_weight[i] > 1e-30f)) all_pos = false;   // (an unknown term's leaf is dropped)
       if (!std::isfinite(b->leaf_weight[i])) PFAIL(BM25F_EINVAL, "query %u: leaf weight is not finite", qi);
     }
     bool dead = false;
@@ -2491,12 +2681,14 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       stp.k = p->k;
       stp.items = p->d_items_w4;
       stp.n_items = p->n_w4;
+      stp.n_items_dev = p->device_planned ? p->d_ctr + PL_CTR_ITEMS + 0 : nullptr;
+      stp.items_off_dev = p->device_planned ? p->d_ctr + PL_CTR_OFF + 0 : nullptr;
       stp.slot_bytes = h->st_slot_bytes;
       stp.final_add = h->d_final_add;
       stp.final_blk = h->d_final_blk;
       stp.part_lo = p->d_part_lo;
       stp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q);
-      const unsigned grid = std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
+      const unsigned grid = p->device_planned ? (unsigned)h->n_sms : std::min<unsigned>((unsigned)h->n_sms, (p->n_w4 + h->st_warps - 1) / h->st_warps);
       CU(cudaEventRecord(ev[4], st));
       const size_t smem = stream_smem_bytes(h->st_warps, h->st_slot_bytes);
       if (p->final_mode) {
@@ -2520,6 +2712,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       ip.totals = p->d_totals;
       ip.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 2);
       ip.n_items = p->n_is;
+      ip.n_items_dev = p->device_planned ? p->d_ctr + PL_CTR_ITEMS + 2 : nullptr;
+      ip.items_off_dev = p->device_planned ? p->d_ctr + PL_CTR_OFF + 2 : nullptr;
       ip.doc_base = (uint32_t)h->doc_base;
       ip.k = p->k;
       ip.final_add = h->d_final_add;
@@ -2529,7 +2723,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_isect<1, false>, IS_WARPS * 32, 0));
         h->is_ctas_per_sm = std::max(1, nb_);
       }
-      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_is + IS_WARPS - 1) / IS_WARPS);
+      const unsigned grid = p->device_planned ? (unsigned)(h->n_sms * h->is_ctas_per_sm)
+                                              : std::min<unsigned>((unsigned)(h->n_sms * h->is_ctas_per_sm), (p->n_is + IS_WARPS - 1) / IS_WARPS);
       if (p->final_mode) {
         // final() of every match before the top-k: 96-bit keys, more registers, 2 CTAs per SM at least
         const unsigned gridf = std::min<unsigned>((unsigned)(h->n_sms * 2), (p->n_is + IS_WARPS - 1) / IS_WARPS);
@@ -2552,6 +2747,8 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       tp.totals = p->d_totals;
       tp.queue = reinterpret_cast<unsigned int*>(p->d_totals + p->Q + 1);
       tp.n_items = p->n_w8;
+      tp.n_items_dev = p->device_planned ? p->d_ctr + PL_CTR_ITEMS + 1 : nullptr;
+      tp.items_off_dev = p->device_planned ? p->d_ctr + PL_CTR_OFF + 1 : nullptr;
       tp.slot_bytes = h->tl_slot_bytes;
       tp.doc_base = (uint32_t)h->doc_base;
       tp.prefetch = h->tl_prefetch;
@@ -2561,7 +2758,7 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_, k_score_team, (int)h->tl_warps * 32, team_smem_bytes(h)));
         h->tl_ctas_per_sm = std::max(1, nb_);
       }
-      const unsigned grid = std::min<unsigned>((unsigned)(h->n_sms * h->tl_ctas_per_sm), p->n_w8);
+      const unsigned grid = p->device_planned ? (unsigned)(h->n_sms * h->tl_ctas_per_sm) : std::min<unsigned>((unsigned)(h->n_sms * h->tl_ctas_per_sm), p->n_w8);
       k_score_team<<<grid, h->tl_warps * 32u, team_smem_bytes(h), ax>>>(tp);
       CU(cudaGetLastError());
       ++launches;
@@ -2628,6 +2825,12 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_cnt, p->d_counts, (size_t)p->Q * 4, cudaMemcpyDeviceToHost, st));
     if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_tot, p->d_totals, (size_t)p->Q * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(A.ev_done, st));
+  }
+  h->stats_from_ctr = p->device_planned;
+  if (p->device_planned) {
+    // the planner's counters follow the results; bm25f_get_stats reads them after a synchronize
+    CU(cudaMemcpyAsync(h->h_ctr, p->d_ctr, PL_CTR_BYTES, cudaMemcpyDeviceToHost, st));
+    launches += 3;                   // k_plan_queries, k_plan_scan, k_plan_items (bm25f_prepare_arena enqueued them)
   }
   h->stats.postings_touched = p->postings;
   h->stats.postings_stream = p->postings_cls[0];
@@ -2882,6 +3085,19 @@ int bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_querie
 
 int bm25f_get_stats(bm25f_handle* h, bm25f_stats* out) {
   if (!h || !out) return fail(BM25F_EINVAL, "null argument");
+  if (h->stats_from_ctr) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    const unsigned int* c = h->h_ctr;
+    unsigned long long post[PL_POST_WORDS];
+    memcpy(post, c + PL_CTR_WORDS, sizeof post);
+    h->stats.postings_touched = post[0];
+    h->stats.postings_stream = post[1];
+    h->stats.postings_team = post[2];
+    h->stats.postings_cta = 0;
+    h->stats.postings_lookup = post[3];
+    h->stats.n_items = (uint64_t)c[PL_CTR_ITEMS] + c[PL_CTR_ITEMS + 1] + c[PL_CTR_ITEMS + 2];
+  }
   *out = h->stats;
   return 0;
 }

@@ -29,6 +29,8 @@ struct IsectParams {
   unsigned long long* totals;      // [Q]
   unsigned int* queue;             // work counter, zeroed before the launch
   uint32_t n_items;
+  const uint32_t* n_items_dev;     // batches planned on the device (k_plan_*): the item count and the position of this
+  const uint32_t* items_off_dev;   // kernel's items inside `items` live there (else null)
   uint32_t doc_base;
   int k;
   // FINAL instantiation only (a weighting with a final() step, reference my_whoosh.py:127-154):
@@ -47,9 +49,9 @@ __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1
     uint32_t item_idx = 0;
     if (lane == 0) item_idx = atomicAdd(ip.queue, 1u);
     item_idx = __shfl_sync(0xFFFFFFFFu, item_idx, 0);
-    if (item_idx >= ip.n_items) break;
+    if (item_idx >= (ip.n_items_dev ? __ldg(ip.n_items_dev) : ip.n_items)) break;
 
-    const ItemRec item = ip.items[item_idx];
+    const ItemRec item = ip.items[(ip.items_off_dev ? __ldg(ip.items_off_dev) : 0u) + item_idx];
     const QueryRec q = ip.queries[item.q];
     const int L = (int)q.n_leaves;
     const uint32_t full = (q.n_groups >= 32u) ? 0xFFFFFFFFu : ((1u << q.n_groups) - 1u);

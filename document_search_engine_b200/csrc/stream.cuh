@@ -45,6 +45,8 @@ struct StreamParams {
   unsigned long long* totals;      // [Q]
   unsigned int* queue;             // work counter, zeroed before the launch
   uint32_t n_items;
+  const uint32_t* n_items_dev;     // batches planned on the device (k_plan_*): the item count and the position of this
+  const uint32_t* items_off_dev;   // kernel's items inside `items` live there (else null)
   uint32_t slot_bytes;             // accumulator bytes per warp (multiple of 512)
   uint32_t doc_base;
   uint32_t pf_dist;                // L2 prefetch distance in postings (0: off)
@@ -246,9 +248,9 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
     uint32_t item_idx = 0;
     if (lane == 0) item_idx = atomicAdd(sp.queue, 1u);
     item_idx = __shfl_sync(0xFFFFFFFFu, item_idx, 0);
-    if (item_idx >= sp.n_items) break;
+    if (item_idx >= (sp.n_items_dev ? __ldg(sp.n_items_dev) : sp.n_items)) break;
 
-    const ItemRec item = sp.items[item_idx];
+    const ItemRec item = sp.items[(sp.items_off_dev ? __ldg(sp.items_off_dev) : 0u) + item_idx];
     const QueryRec q = sp.queries[item.q];
     const int L = (int)q.n_leaves;
     const uint32_t G = q.n_groups;

@@ -37,6 +37,8 @@ struct TeamParams {
   unsigned long long* totals;      // [Q]
   unsigned int* queue;             // work counter, zeroed before the launch
   uint32_t n_items;
+  const uint32_t* n_items_dev;     // batches planned on the device (k_plan_*): the item count and the position of this
+  const uint32_t* items_off_dev;   // kernel's items inside `items` live there (else null)
   uint32_t slot_bytes;             // accumulator bytes per warp (multiple of 512)
   uint32_t doc_base;
   uint32_t prefetch;               // slices ahead to bulk-prefetch into L2 (0: off)
@@ -77,9 +79,9 @@ __global__ void __launch_bounds__(TM_MAX_WARPS * 32, 1) k_score_team(TeamParams 
     if (tid == 0) sh.item = atomicAdd(tp.queue, 1u);
     __syncthreads();
     const uint32_t item_idx = sh.item;
-    if (item_idx >= tp.n_items) break;
+    if (item_idx >= (tp.n_items_dev ? __ldg(tp.n_items_dev) : tp.n_items)) break;
 
-    const ItemRec item = tp.items[item_idx];
+    const ItemRec item = tp.items[(tp.items_off_dev ? __ldg(tp.items_off_dev) : 0u) + item_idx];
     const QueryRec q = tp.queries[item.q];
     const uint32_t L = q.n_leaves;
     const uint32_t G = q.n_groups;

@@ -113,6 +113,9 @@ typedef struct {
   uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
                                     below this (0xFFFFFFFF = never) */
   uint32_t serial_streams;       /* 1: the candidate-driven / team kernels run after, not beside, the flat-OR kernel */
+  uint32_t host_plan;            /* 1: always plan batches on the host (default: batches of >= 256 queries that the warp
+                                    kernels serve alone - <= 8 leaves a query, positive weights, no NOT clause, no paging
+                                    bound, no final() step, k <= 256 - are planned by three small kernels on the device) */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves
