@@ -1384,10 +1384,12 @@ struct bm25f_handle {
     size_t h_out_cap = 0;
     cudaEvent_t ev_ready = nullptr;       // the plan's records are on the device (copy stream)
     cudaEvent_t ev_done = nullptr;        // a submitted batch's results are in h_out
+    cudaEvent_t ev_scored = nullptr;      // ... are final on the device (the copy to h_out runs on d2h_stream)
     bm25f_plan* submitted = nullptr;      // submitted and not yet collected
   } arenas[2];
   int arena_next = 0;
   cudaStream_t copy_stream = nullptr;    // plan uploads, so that they do not queue behind the running batch
+  cudaStream_t d2h_stream = nullptr;     // results of submitted batches, so that the next batch's kernels do not queue behind them
   PlanPool* pool = nullptr;              // created on the first large batch
 };
 
@@ -1485,6 +1487,16 @@ int fold_events(bm25f_handle* h, int n) {
     CU(cudaEventElapsedTime(&d, e[0], e[3]));
     float f = 0;
     CU(cudaEventElapsedTime(&f, e[4], e[5]));
+    static const bool trace = getenv("BM25F_TRACE") != nullptr;
+    if (trace && h->stats.n_executes > 0) {
+      // idle time of the stream between the previous execute's last kernel and this one's first
+      cudaEvent_t* prev = h->ev[(slot + bm25f_handle::EV_RING - 1) % bm25f_handle::EV_RING];
+      float gap = 0;
+      if (cudaEventElapsedTime(&gap, prev[3], e[0]) == cudaSuccess)
+        fprintf(stderr, "[bm25f execute] gap %.3f ms, bounds %.3f, score %.3f (stream %.3f), merge %.3f\n", gap, a, b, f, c);
+      else
+        cudaGetLastError();
+    }
     h->stats.ms_stream += f;
     h->stats.ms_bounds += a;
     h->stats.ms_score += b;
@@ -1524,8 +1536,10 @@ void bm25f_destroy(bm25f_handle* h) {
     if (A.h_out) cudaFreeHost(A.h_out);
     if (A.ev_ready) cudaEventDestroy(A.ev_ready);
     if (A.ev_done) cudaEventDestroy(A.ev_done);
+    if (A.ev_scored) cudaEventDestroy(A.ev_scored);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->d2h_stream) cudaStreamDestroy(h->d2h_stream);
   for (auto& set : h->ev)
     for (auto& e : set)
       if (e) cudaEventDestroy(e);
@@ -1595,6 +1609,12 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     if (opts->isect_split) h->is_split = opts->isect_split;
     if (opts->isect_or_limit) h->is_or_limit = opts->isect_or_limit == 0xFFFFFFFFu ? 0u : opts->isect_or_limit;
   }
+  if (!opts || !opts->isect_or_limit) {
+    // The sweep a flat OR costs on the stream kernel grows with the shard's document space, the lookups of the
+    // candidate-driven kernel do not: the break-even moves with n_docs.  (Measured on config 2: 40000 at 1M documents;
+    // on a 125k-document shard 5000 runs the step in 0.40 ms, 40000 in 0.63 ms.)
+    h->is_or_limit = (uint32_t)std::min<uint64_t>(40000, std::max<uint64_t>(2000, 40000ull * h->n_docs / 1000000ull));
+  }
   if (opts) h->serial_streams = opts->serial_streams != 0;
   if (opts) h->host_plan = opts->host_plan != 0;
   if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
@@ -1638,9 +1658,11 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   CUH(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
   CUH(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CUH(cudaStreamCreateWithFlags(&h->d2h_stream, cudaStreamNonBlocking));
   for (auto& A : h->arenas) {
     CUH(cudaEventCreateWithFlags(&A.ev_ready, cudaEventDisableTiming));
     CUH(cudaEventCreateWithFlags(&A.ev_done, cudaEventDisableTiming));
+    CUH(cudaEventCreateWithFlags(&A.ev_scored, cudaEventDisableTiming));
   }
   CUH(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUH(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -2012,6 +2034,10 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
     if (trace) fprintf(stderr, "[bm25f prepare] host planner: query %u %s\n", qi, why);      \
     return 0;                                                                                 \
   } while (0)
+  // The batch's postings only size the work items: in a large batch every 8th leaf is looked up (the random reads of
+  // term_offsets were most of this loop)
+  const uint32_t sample = NL >= 8192 ? 8u : 1u;
+  const auto t_a = std::chrono::steady_clock::now();
   uint64_t total = 0;
   for (uint32_t qi = 0; qi < Q; ++qi) {
     const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
@@ -2030,10 +2056,12 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
       if (term == BM25F_TERM_UNKNOWN) continue;          // dropped: its weight (0 for a term no shard knows) does not matter
       if (term >= h->n_real_terms + h->n_fields) DECLINE("names a posting list out of range");
       if (!(w > 1e-30f)) DECLINE("has a non-positive weight");
-      total += h->term_offsets[term + 1] - h->term_offsets[term];
+      if (i % sample == 0) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
   }
+  total *= sample;
 #undef DECLINE
+  const auto t_b = std::chrono::steady_clock::now();
   uint32_t wsplit, is_split, tl_split;
   item_sizes(h, Q, total, &wsplit, &is_split, &tl_split);
 
@@ -2064,7 +2092,9 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
   memcpy(A.h + i_g, b->leaf_group, NL);
 
   // every query may be cut into max_split items at most, so the item array cannot overflow
-  const uint32_t max_split = 4u + 65536u / Q;
+  // (the slack shrinks with k: the partial lists, k keys an item, stay below ~256 MB)
+  const uint32_t slack = (uint32_t)std::min<size_t>(1u << 20, std::max<size_t>(65536, ((size_t)256 << 20) / ((size_t)k * 8)));
+  const uint32_t max_split = 4u + slack / Q;
   const size_t item_cap = (size_t)Q * max_split;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes); return o; };
@@ -2152,6 +2182,10 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
   if (ce != cudaSuccess) {
     delete p;
     return fail(BM25F_ECUDA, "device planner: %s", cudaGetErrorString(ce));
+  }
+  if (trace) {
+    auto us = [](auto x, auto y) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(y - x).count() / 1e3; };
+    fprintf(stderr, "[bm25f prepare] device planner: check %.0f us, stage + enqueue %.0f us\n", us(t_a, t_b), us(t_b, std::chrono::steady_clock::now()));
   }
   *out = p;
   *done = true;
@@ -2806,11 +2840,11 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
   h->ev_head = (h->ev_head + 1) % bm25f_handle::EV_RING;
   ++h->ev_pending;
   if (p->submitted) {
-    // results -> the arena's pinned landing zone, behind the kernels on the same stream
+    // results -> the arena's pinned landing zone: totals, scores, docids and counts are neighbours in the arena, so one
+    // copy, on its own stream (the next batch's kernels start while it travels)
     bm25f_handle::Arena& A = h->arenas[p->arena];
-    const size_t n = (size_t)p->Q * p->k;
-    const size_t o_doc = align_up(n * 4), o_cnt = o_doc + align_up(n * 4), o_tot = o_cnt + align_up((size_t)p->Q * 4),
-                 need = o_tot + align_up((size_t)p->Q * 8);
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(p->d_totals);
+    const size_t need = (size_t)(reinterpret_cast<const unsigned char*>(p->d_counts + p->Q) - base);
     if (need > A.h_out_cap) {
       if (A.h_out) cudaFreeHost(A.h_out);
       A.h_out = nullptr;
@@ -2820,11 +2854,10 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
       if (e != cudaSuccess) return fail(BM25F_ENOMEM, "cudaHostAlloc(%zu): %s", cap, cudaGetErrorString(e));
       A.h_out_cap = cap;
     }
-    if (n) CU(cudaMemcpyAsync(A.h_out, p->d_scores, n * 4, cudaMemcpyDeviceToHost, st));
-    if (n) CU(cudaMemcpyAsync(A.h_out + o_doc, p->d_docids, n * 4, cudaMemcpyDeviceToHost, st));
-    if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_cnt, p->d_counts, (size_t)p->Q * 4, cudaMemcpyDeviceToHost, st));
-    if (p->Q) CU(cudaMemcpyAsync(A.h_out + o_tot, p->d_totals, (size_t)p->Q * 8, cudaMemcpyDeviceToHost, st));
-    CU(cudaEventRecord(A.ev_done, st));
+    CU(cudaEventRecord(A.ev_scored, st));
+    CU(cudaStreamWaitEvent(h->d2h_stream, A.ev_scored, 0));
+    if (p->Q) CU(cudaMemcpyAsync(A.h_out, base, need, cudaMemcpyDeviceToHost, h->d2h_stream));
+    CU(cudaEventRecord(A.ev_done, h->d2h_stream));
   }
   h->stats_from_ctr = p->device_planned;
   if (p->device_planned) {
@@ -2871,6 +2904,7 @@ int bm25f_synchronize(bm25f_handle* h) {
   if (!h) return fail(BM25F_EINVAL, "null handle");
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
+  CU(cudaStreamSynchronize(h->d2h_stream));
   return fold_events(h, h->ev_pending);
 }
 
@@ -2987,11 +3021,14 @@ int bm25f_collect(bm25f_handle* h, bm25f_plan* p, float* out_scores, uint32_t* o
     return fail(BM25F_ECUDA, "cudaEventSynchronize: %s", cudaGetErrorString(e));
   }
   const size_t n = (size_t)p->Q * p->k;
-  const size_t o_doc = align_up(n * 4), o_cnt = o_doc + align_up(n * 4), o_tot = o_cnt + align_up((size_t)p->Q * 4);
-  if (out_scores && n) memcpy(out_scores, A.h_out, n * 4);
+  const unsigned char* base = reinterpret_cast<const unsigned char*>(p->d_totals);      // h_out mirrors [d_totals, d_counts + Q)
+  const size_t o_sc = (size_t)(reinterpret_cast<const unsigned char*>(p->d_scores) - base),
+               o_doc = (size_t)(reinterpret_cast<const unsigned char*>(p->d_docids) - base),
+               o_cnt = (size_t)(reinterpret_cast<const unsigned char*>(p->d_counts) - base);
+  if (out_scores && n) memcpy(out_scores, A.h_out + o_sc, n * 4);
   if (out_docids && n) memcpy(out_docids, A.h_out + o_doc, n * 4);
   if (out_counts && p->Q) memcpy(out_counts, A.h_out + o_cnt, (size_t)p->Q * 4);
-  if (out_totals && p->Q) memcpy(out_totals, A.h_out + o_tot, (size_t)p->Q * 8);
+  if (out_totals && p->Q) memcpy(out_totals, A.h_out, (size_t)p->Q * 8);
   bm25f_plan_destroy(p);
   return fold_events(h, 1);          // this batch's timings (batches finish in submission order)
 }

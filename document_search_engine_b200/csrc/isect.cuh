@@ -44,6 +44,7 @@ template <int KR, bool FINAL>
 __global__ void __launch_bounds__(IS_WARPS * 32, (FINAL || KR > 4) ? 2 : KR == 1 ? 5 : 3) k_score_isect(IsectParams ip) {   // 48 registers for k <= 32: two CTAs fit beside the stream kernel
   const int lane = threadIdx.x & 31;
   const uint2* __restrict__ store = ip.pairs;
+  if (ip.n_items_dev && blockIdx.x * (uint32_t)IS_WARPS >= __ldg(ip.n_items_dev)) return;   // device-planned batch, full grid
 
   for (;;) {
     uint32_t item_idx = 0;

@@ -228,6 +228,8 @@ __global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamPar
   const int warp = threadIdx.x >> 5;
   const int nwarps = blockDim.x >> 5;
   const uint32_t slot_bytes = sp.slot_bytes;
+  // a device-planned batch is launched with a full grid: CTAs beyond the item count leave their SM to the other kernels
+  if (sp.n_items_dev && blockIdx.x * (uint32_t)nwarps >= __ldg(sp.n_items_dev)) return;
   // shared memory: [nwarps][slot_bytes] slots | [nwarps][ST_MAX_LEAVES][32] tails (8 B) | [nwarps][ST_HOT] hot (2 B) | [nwarps] hot counters |
   // [nwarps][ST_MAX_LEAVES] leaf records (32 B, 16-byte aligned)
   SubCtx cx;

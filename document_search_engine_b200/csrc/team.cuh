@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(TM_MAX_WARPS * 32, 1) k_score_team(TeamParams 
   const int warp = tid >> 5;
   const int NW = nthr >> 5;
   const uint32_t slot_bytes = tp.slot_bytes;
+  if (tp.n_items_dev && blockIdx.x >= __ldg(tp.n_items_dev)) return;      // device-planned batch, full grid: nothing left for this CTA
   TeamShared& sh = *reinterpret_cast<TeamShared*>(smem_raw + (size_t)NW * slot_bytes);
   SubCtx cx;
   cx.slots_addr = smem_u32(smem_raw) + (uint32_t)warp * slot_bytes;

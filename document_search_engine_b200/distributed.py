@@ -239,6 +239,7 @@ class ShardedSearcher:
             yield from self.local.search_packed_stream(batches, k)
             return
         stream = torch.cuda.current_stream(self.device)
+        d2h = self._d2h_stream()          # results travel beside the next batch's kernels, not in front of them
         inflight = None
         slot = 0
 
@@ -256,9 +257,11 @@ class ShardedSearcher:
                 Q = batch.n_queries
                 b = self.run_plan(plan, slot)
                 h = self._host_buffers(Q, k, slot)
-                h.copy_(b["out"], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(stream)
+                d2h.wait_stream(stream)
+                with torch.cuda.stream(d2h):
+                    h.copy_(b["out"], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(d2h)
                 cur = (plan, h, ev, Q)
                 slot ^= 1
                 if inflight is not None:
@@ -272,6 +275,12 @@ class ShardedSearcher:
         finally:
             if inflight is not None:
                 finish(inflight)
+
+    def _d2h_stream(self):
+        s = self._bufs.get("d2h_stream")
+        if s is None:
+            s = self._bufs["d2h_stream"] = torch.cuda.Stream(self.device)
+        return s
 
     def _host_buffers(self, Q: int, k: int, slot: int = 0):
         key = ("host", Q, k, slot)

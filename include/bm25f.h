@@ -111,7 +111,8 @@ typedef struct {
                                     (leaves - 1) x isect_ratio < postings of the query; default 1 */
   uint32_t isect_split;          /* candidate-driven AND: target candidates per work item; default 2048 */
   uint32_t isect_or_limit;       /* a flat OR goes the candidate-driven way when postings x (leaves - 1) is
-                                    below this (0xFFFFFFFF = never) */
+                                    below this (0xFFFFFFFF = never); default 40000 x n_docs_all / 1e6, within
+                                    2000..40000: the sweep it avoids is as long as the shard's document space */
   uint32_t serial_streams;       /* 1: the candidate-driven / team kernels run after, not beside, the flat-OR kernel */
   uint32_t host_plan;            /* 1: always plan batches on the host (default: batches of >= 256 queries that the warp
                                     kernels serve alone - <= 8 leaves a query, positive weights, no NOT clause, no paging

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--check", type=int, default=16)
     ap.add_argument("--opts", nargs="*", default=["default"])
     ap.add_argument("--modes", nargs="*", default=["cfg"], help="cfg | and | or : query mix to time")
+    ap.add_argument("--arena", action="store_true", help="plan in the engine's workspaces (the path bm25f_search_batch / bm25f_submit take: device planner)")
     args = ap.parse_args()
     from document_search_engine_b200.corpus import CONFIGS, config_corpus, config_queries, make_queries
     from document_search_engine_b200.scoring import BM25F
@@ -74,7 +75,7 @@ def main():
                 except AssertionError as e:
                     bad = str(e)
                     break
-            plan = eng.prepare(batch, k)
+            plan = eng.prepare(batch, k, arena=args.arena)
             for _ in range(2):
                 plan.execute()
             eng.synchronize()
