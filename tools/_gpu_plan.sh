@@ -1,4 +1,9 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2_gputests.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/r2_gputests.log
-timeout 300 python bench.py --docs 125000 --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_shard_emul.json 2> gpurun_out/r2_shard_emul.err; echo "bench rc=$?"
-timeout 300 python bench.py --docs 250000 --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_shard_emul4.json 2> gpurun_out/r2_shard_emul4.err; echo "bench rc=$?"
+show='
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); print({k: d[k] for k in ("opt","mode","parity","ms_total","ms_score","ms_stream","items","post_stream","post_lookup")})'
+export BM25F_LIB=/root/repo/document_search_engine_b200/csrc/libbm25f_old.so
+timeout 300 python tools/tune.py --config 2 --steps 10 --modes cfg and --opts default 2> gpurun_out/tune.err | python -c "$show"
+timeout 300 python tools/tune.py --config 2 --docs 125000 --steps 10 --modes cfg and --opts default 2> gpurun_out/tune.err | python -c "$show"
+timeout 300 python tools/tune.py --config 3 --steps 10 --opts default 2> gpurun_out/tune.err | python -c "$show"
