@@ -2029,35 +2029,54 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
   *done = false;
   const uint32_t Q = b->n_queries, NL = b->n_leaves;
   static const bool trace = getenv("BM25F_TRACE") != nullptr;
-#define DECLINE(why)                                                                          \
-  do {                                                                                        \
-    if (trace) fprintf(stderr, "[bm25f prepare] host planner: query %u %s\n", qi, why);      \
-    return 0;                                                                                 \
+#define DECLINE(why)                                                                \
+  do {                                                                              \
+    if (trace) fprintf(stderr, "[bm25f prepare] host planner: a query %s\n", why);  \
+    return 0;                                                                       \
   } while (0)
-  // The batch's postings only size the work items: in a large batch every 8th leaf is looked up (the random reads of
-  // term_offsets were most of this loop)
-  const uint32_t sample = NL >= 8192 ? 8u : 1u;
+  // Eligibility in two branch-free passes (this runs once a batch on the submitting thread: at 8 ranks x 10k queries
+  // it was a third of the host's step).  The batch's postings only size the work items: in a large batch every 8th
+  // leaf is looked up (the random reads of term_offsets were most of the time).
   const auto t_a = std::chrono::steady_clock::now();
-  uint64_t total = 0;
+  const uint32_t* qoff = b->query_leaf_offsets;
+  const uint8_t* qng = b->query_n_groups;
+  const uint8_t* lgrp = b->leaf_group;
+  const uint32_t* lterm = b->leaf_term;
+  const float* lw = b->leaf_weight;
+  // (1) per query: leaf range, at most 8 leaves and groups, groups non-decreasing and below n_groups (a NOT leaf is 0xFF)
+  uint32_t bad_q = 0;
   for (uint32_t qi = 0; qi < Q; ++qi) {
-    const uint32_t a = b->query_leaf_offsets[qi], e = b->query_leaf_offsets[qi + 1];
+    const uint32_t a = qoff[qi], e = qoff[qi + 1], G = qng[qi];
     if (e < a || e > NL) DECLINE("has a bad leaf range");
-    if (e - a > (uint32_t)PL_MAX_LEAVES) DECLINE("has more than 8 leaves");
-    const uint32_t G = b->query_n_groups[qi];
-    if (G > (uint32_t)PL_MAX_LEAVES) DECLINE("has more than 8 groups");
-    uint32_t prev_g = 0;
+    bad_q |= (e - a > (uint32_t)PL_MAX_LEAVES) | (G > (uint32_t)PL_MAX_LEAVES);
+    uint32_t prev_g = 0, bad = 0;
     for (uint32_t i = a; i < e; ++i) {
-      const uint32_t g = b->leaf_group[i];
-      if (g >= G || g < prev_g) DECLINE("has a NOT clause or malformed groups");
+      const uint32_t g = lgrp[i];
+      bad |= (g >= G) | (g < prev_g);
       prev_g = g;
-      const float w = b->leaf_weight[i];
-      if (!std::isfinite(w)) DECLINE("has a non-finite weight");
-      const uint32_t term = resolve_term(h, b->leaf_term[i]);
-      if (term == BM25F_TERM_UNKNOWN) continue;          // dropped: its weight (0 for a term no shard knows) does not matter
-      if (term >= h->n_real_terms + h->n_fields) DECLINE("names a posting list out of range");
-      if (!(w > 1e-30f)) DECLINE("has a non-positive weight");
-      if (i % sample == 0) total += h->term_offsets[term + 1] - h->term_offsets[term];
     }
+    bad_q |= bad;
+  }
+  if (bad_q) DECLINE("has more than 8 leaves or groups, a NOT clause or malformed groups");
+  // (2) per leaf: finite weight; a known term must be in range and carry a positive weight (an unknown term's leaf is
+  // dropped: its weight - 0 for a term no shard knows - does not matter)
+  const uint32_t n_lists = (uint32_t)(h->n_real_terms + h->n_fields);
+  const uint32_t n_fields = h->n_fields;
+  uint32_t bad_l = 0;
+  for (uint32_t i = 0; i < NL; ++i) {
+    const uint32_t t = lterm[i];
+    const float w = lw[i];
+    const uint32_t unknown = (t == BM25F_TERM_UNKNOWN) | ((t >= BM25F_TERM_EVERY_BASE) & (t - BM25F_TERM_EVERY_BASE >= n_fields));
+    const uint32_t every = (t >= BM25F_TERM_EVERY_BASE) & (unknown ^ 1u);
+    const uint32_t finite = (std::fabs(w) <= 3.402823466e+38f);               // false for NaN and infinities
+    bad_l |= (finite ^ 1u) | ((unknown ^ 1u) & (((every ^ 1u) & (t >= n_lists)) | (uint32_t)!(w > 1e-30f)));
+  }
+  if (bad_l) DECLINE("has a non-finite or non-positive weight, or names a posting list out of range");
+  const uint32_t sample = NL >= 8192 ? 8u : 1u;
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < NL; i += sample) {
+    const uint32_t term = resolve_term(h, lterm[i]);
+    if (term != BM25F_TERM_UNKNOWN) total += h->term_offsets[term + 1] - h->term_offsets[term];
   }
   total *= sample;
 #undef DECLINE
@@ -2092,8 +2111,8 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
   memcpy(A.h + i_g, b->leaf_group, NL);
 
   // every query may be cut into max_split items at most, so the item array cannot overflow
-  // (the slack shrinks with k: the partial lists, k keys an item, stay below ~256 MB)
-  const uint32_t slack = (uint32_t)std::min<size_t>(1u << 20, std::max<size_t>(65536, ((size_t)256 << 20) / ((size_t)k * 8)));
+  // (the slack shrinks with k: the partial lists, k keys an item, stay below ~1 GB)
+  const uint32_t slack = (uint32_t)std::min<size_t>(1u << 20, std::max<size_t>(65536, ((size_t)1 << 30) / ((size_t)k * 8)));
   const uint32_t max_split = 4u + slack / Q;
   const size_t item_cap = (size_t)Q * max_split;
   size_t off = 0;

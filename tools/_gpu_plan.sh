@@ -1,9 +1,4 @@
 cd /root/repo; mkdir -p gpurun_out
-show='
-import sys, json
-for l in sys.stdin:
-    d=json.loads(l); print({k: d[k] for k in ("opt","mode","parity","ms_total","ms_score","ms_stream","items","post_stream","post_lookup")})'
-export BM25F_LIB=/root/repo/document_search_engine_b200/csrc/libbm25f_old.so
-timeout 300 python tools/tune.py --config 2 --steps 10 --modes cfg and --opts default 2> gpurun_out/tune.err | python -c "$show"
-timeout 300 python tools/tune.py --config 2 --docs 125000 --steps 10 --modes cfg and --opts default 2> gpurun_out/tune.err | python -c "$show"
-timeout 300 python tools/tune.py --config 3 --steps 10 --opts default 2> gpurun_out/tune.err | python -c "$show"
+timeout 300 python -m pytest tests/test_gpu_plan.py tests/test_gpu_edges.py -x -q -m gpu 2>&1 | tail -3
+BM25F_TRACE=1 timeout 300 python bench.py --docs 125000 --steps 20 --warmup 3 --no-cpu > gpurun_out/r2_shard_emul.json 2> gpurun_out/r2_shard_emul.err; echo "bench rc=$?"
+grep "device planner" gpurun_out/r2_shard_emul.err | sed -n '30,34p'
