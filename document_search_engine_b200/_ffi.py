@@ -52,7 +52,7 @@ class Options(C.Structure):
                 ("prefetch_postings", C.c_uint32), ("cta_warps", C.c_uint32), ("cta_prefetch", C.c_uint32),
                 ("cta_split", C.c_uint32), ("cta_slice_docs", C.c_uint32), ("isect_ratio", C.c_uint32),
                 ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("serial_streams", C.c_uint32),
-                ("host_plan", C.c_uint32)]
+                ("host_plan", C.c_uint32), ("compact_store", C.c_uint32)]
 
 
 #: engine options a caller may pass (``bm25f_options`` field names; 0 = library default)

@@ -1360,6 +1360,9 @@ struct bm25f_handle {
   int is_ctas_per_sm = 0;
   bool serial_streams = false;          // option: never run the second-stream kernels beside the first-stream ones
   bool host_plan = false;               // option: never plan a batch on the device (plan.cuh)
+  bool compact_store = false;           // option: release the raw postings after the first bm25f_set_weighting
+  bool raw_dropped = false;             // ... done: 8 bytes a posting stay; no re-weighting, no CTA-kernel queries
+  std::vector<float> norm_host;         // the weighting in force (compact_store: the only one this handle will ever serve)
   unsigned long long* d_term_offsets = nullptr;   // the device planner's copies of term_offsets / term_field
   uint8_t* d_term_field = nullptr;
   unsigned int* h_ctr = nullptr;        // pinned: the device planner's counters of the last executed plan (statistics)
@@ -1617,6 +1620,7 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
   }
   if (opts) h->serial_streams = opts->serial_streams != 0;
   if (opts) h->host_plan = opts->host_plan != 0;
+  if (opts) h->compact_store = opts->compact_store != 0;
   if (h->variant > 5) { delete h; return fail(BM25F_EINVAL, "variant must be 0 (auto), 1 (pipeline), 2 (direct loads), 3 (warp streams), 4 (warp teams) or 5 (candidate-driven)"); }
   if (h->tl_warps < 1 || h->tl_warps > (uint32_t)TM_MAX_WARPS) { delete h; return fail(BM25F_EINVAL, "cta_warps must be 1..%d", TM_MAX_WARPS); }
   if (h->st_slot_bytes < 512 || (h->st_slot_bytes & 511)) { delete h; return fail(BM25F_EINVAL, "subtile_docs must be a multiple of 128, at least 128"); }
@@ -1916,6 +1920,11 @@ int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
     for (uint32_t i = f * 256; i < (f + 1) * 256; ++i)
       if (!(norm[i] > 0.0f) || !std::isfinite(norm[i])) return fail(BM25F_EINVAL, "norm table entry %u is not a positive finite number (or the whole row -1: field not scorable)", i);
   }
+  if (h->raw_dropped) {
+    if (memcmp(h->norm_host.data(), norm, (size_t)h->n_fields * 256 * sizeof(float)) == 0) return 0;   // the same weighting again
+    return fail(BM25F_EINVAL, "compact_store: the raw postings were released after the first bm25f_set_weighting; "
+                              "create another engine to score with a different weighting");
+  }
   CU(cudaMemcpyAsync(h->d_norm, norm, (size_t)h->n_fields * 256 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   // refresh the per-posting impacts (one streaming pass over the store per field run)
   uint64_t t = 0;
@@ -1933,6 +1942,24 @@ int bm25f_set_weighting(bm25f_handle* h, const float* norm) {
   }
   CU(cudaStreamSynchronize(h->stream));
   h->have_weighting = true;
+  h->norm_host.assign(norm, norm + (size_t)h->n_fields * 256);
+  if (h->compact_store) {
+    // the scoring kernels read only the {docid, impact} pairs: 8 of the 16 bytes a posting can go
+    const uint64_t n = h->n_postings + 1024;        // (the padded length of the arrays)
+    uint64_t freed = 0;
+    if (h->d_docids) freed += n * 4;
+    if (h->d_payload) freed += n * 4;
+    if (h->d_lb) freed += n;
+    cudaFree(h->d_docids);
+    cudaFree(h->d_payload);
+    cudaFree(h->d_lb);
+    h->d_docids = nullptr;
+    h->d_payload = nullptr;
+    h->d_lb = nullptr;
+    h->raw_dropped = true;
+    h->device_bytes = h->device_bytes > freed ? h->device_bytes - freed : 0;
+    h->stats.device_bytes = h->device_bytes;
+  }
   return 0;
 }
 
@@ -2412,6 +2439,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
     const bool use_team = !use_isect && stream_ok && qr.after_key == 0ull && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
+    if (cls == 2 && h->raw_dropped)
+      PFAIL(BM25F_EINVAL, "query %u needs the kernels that read the raw postings (k > 256, more than 32 leaves, a non-positive weight or a "
+                          "paging bound) and the engine was created with compact_store", qi);
     uint32_t nsplit;
     if (use_isect) {
       nsplit = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, h->n_docs / 256), std::max<uint64_t>(1, (n_cand + is_split) / (2ull * is_split)));

@@ -117,6 +117,10 @@ typedef struct {
   uint32_t host_plan;            /* 1: always plan batches on the host (default: batches of >= 256 queries that the warp
                                     kernels serve alone - <= 8 leaves a query, positive weights, no NOT clause, no paging
                                     bound, no final() step, k <= 256 - are planned by three small kernels on the device) */
+  uint32_t compact_store;        /* 1: release the raw postings (docid, tf, length byte: 8 of the 16 bytes a posting) after
+                                    the first bm25f_set_weighting; the handle then serves that weighting only, and only
+                                    queries the warp kernels take (k <= 256, <= 32 leaves, positive weights, no paging
+                                    bound past BM25F_MAX_K) - anything else is a loud BM25F_EINVAL */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves

@@ -171,3 +171,27 @@ def test_malformed_posting_lists_are_refused():
     with ix.searcher() as s:
         assert len(s.search(Term("body", 3))) > 0
     ix._engine_cache.clear()
+
+
+def test_compact_store_releases_the_raw_postings():
+    """Option compact_store: 8 of the 16 bytes a posting are released after the first set_weighting; the warp kernels
+    serve the same results, anything that needs the raw postings is refused loudly."""
+    ix = make_corpus(30000, 1500, 23, device="cpu")
+    qs = make_queries(300, 1500, 3, 1, 6, "mixed").queries
+    qs[5] = And([Term("body", 3), Not(Term("body", 4))])
+    with ix.searcher() as s:
+        full_bytes = s.engine.stats()["device_bytes"]
+    ix._engine_cache.clear()
+    o = NumpyOracle(ix)
+    with ix.searcher(compact_store=1) as s:
+        assert s.engine.stats()["device_bytes"] < 0.62 * full_bytes
+        for limit in (10, 100):
+            res = s.search_batch(qs, limit=limit)
+            assert_batch_parity(o, qs, res, limit)
+        with pytest.raises(RuntimeError, match="compact_store"):
+            s.search_batch(qs[:4], limit=300)                     # k > 256: the CTA kernels read the raw store
+        with pytest.raises(RuntimeError, match="compact_store"):
+            ix.searcher(weighting=BM25F(B=0.3), compact_store=1).search(qs[0], limit=10)   # another weighting, same engine
+        res = s.search_batch(qs, limit=10)                        # the engine still serves its weighting
+        assert_batch_parity(o, qs, res, 10)
+    ix._engine_cache.clear()
