@@ -1,3 +1,7 @@
 cd /root/repo; mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/r2_gputests.log 2>&1; echo "pytest rc=$?"; tail -12 gpurun_out/r2_gputests.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()"; echo "smoke rc=$?"
+show='
+import sys, json
+for l in sys.stdin:
+    d=json.loads(l); print({k: d[k] for k in ("opt","mode","parity","ms_total","ms_score","ms_stream","ms_merge","items","post_stream","post_lookup")})'
+timeout 500 python tools/tune.py --config 4 --queries 50000 --steps 3 --check 8 --opts default isect_ratio=2 isect_ratio=4 isect_or_limit=10000 isect_or_limit=160000 serial_streams=1 2> gpurun_out/tune.err | python -c "$show"
+tail -2 gpurun_out/tune.err
