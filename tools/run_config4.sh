@@ -1,3 +1,4 @@
+# Round-2 measurement script (run through gpurun): see profiles/r02_* for what it produced.
 N=$1
 cd /root/repo; mkdir -p gpurun_out
 if [ $N = 1 ]; then

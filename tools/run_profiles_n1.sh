@@ -1,3 +1,4 @@
+# Round-2 measurement script (run through gpurun): see profiles/r02_* for what it produced.
 cd /root/repo; mkdir -p gpurun_out
 timeout 400 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err; echo "bench rc=$?"
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_ref_n1.json 2> gpurun_out/r02_bench_ref_n1.err; echo "ref rc=$?"
