@@ -1046,11 +1046,23 @@ __global__ void k_merge_topk(const unsigned long long* __restrict__ keys_in, con
   if (n_lists > 0)
     for (int i = tid; i < k; i += nt) buf[i] = keys_in[start + i];
   __syncthreads();
+  // Every list is sorted descending (the scoring kernels and this kernel write them that way) and so is buf[0, kp):
+  // the next list goes into the upper half back to front, which makes buf bitonic, and one bitonic MERGE
+  // (log2(2 kp) compare-exchange rounds instead of the ~log^2 of a sort) puts the 2 kp keys in descending order.
   for (int l = 1; l < n_lists; ++l) {
-    for (int i = tid; i < kp; i += nt) buf[kp + i] = (i < k) ? keys_in[start + l * stride + i] : 0ull;
+    for (int i = tid; i < kp; i += nt) buf[2 * kp - 1 - i] = (i < k) ? keys_in[start + l * stride + i] : 0ull;
     __syncthreads();
-    bitonic_sort_desc(buf, 2 * kp, Team{tid, nt, 0});
-    for (int i = k + tid; i < 2 * kp; i += nt) buf[i] = 0ull;
+    for (int j = kp; j > 0; j >>= 1) {
+      for (int i = tid; i < 2 * kp; i += nt) {
+        const int x = i ^ j;
+        if (x > i) {
+          const unsigned long long ai = buf[i], ax = buf[x];
+          if (ai < ax) { buf[i] = ax; buf[x] = ai; }
+        }
+      }
+      __syncthreads();
+    }
+    for (int i = k + tid; i < kp; i += nt) buf[i] = 0ull;
     __syncthreads();
   }
   for (int i = tid; i < k; i += nt) keys_out[(size_t)q * k + i] = buf[i];

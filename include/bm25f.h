@@ -233,7 +233,8 @@ int  bm25f_collect(bm25f_handle* h, bm25f_plan* plan, float* out_scores, uint32_
                    uint32_t* out_counts, uint64_t* out_totals);
 
 /* Merge n_lists device-resident top-k key lists per query (layout [n_lists][n_queries][k], as an
- * all-gather of per-shard results produces) into d_out_keys [n_queries][k].  Runs on `stream`
+ * all-gather of per-shard results produces: every list in descending key order, empty slots 0 at its end, which
+ * is how bm25f_execute and this call write them) into d_out_keys [n_queries][k].  Runs on `stream`
  * (a cudaStream_t, or NULL for the handle's current stream). */
 int  bm25f_merge_keys(bm25f_handle* h, const uint64_t* d_keys, int n_lists, uint32_t n_queries, int k,
                       uint64_t* d_out_keys, void* stream);
