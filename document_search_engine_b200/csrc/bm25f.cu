@@ -2758,10 +2758,9 @@ int bm25f_execute(bm25f_handle* h, bm25f_plan* p) {
     sp.prof = h->d_prof;
     // The stream kernel (one fat CTA per SM) and the candidate-driven kernel (no shared memory, few
     // registers) fit on an SM together and stall on different things: launch them side by side.
-    // (for k <= 32 only: with more keys a lane neither kernel leaves the other enough registers, the second one
-    // would trickle in behind the first one's CTAs - measured on config 4, top-100: 154.7 ms side by side, 145.7 ms
-    // one after the other)
-    const bool side = p->n_w4 && (p->n_is || p->n_w8) && !h->serial_streams && p->k <= 32;
+    // (a final() step with more than one key a lane: the FINAL instantiations need too many registers to share an
+    // SM, the second kernel would trickle in behind the first one's CTAs - run them one after the other)
+    const bool side = p->n_w4 && (p->n_is || p->n_w8) && !h->serial_streams && (!p->final_mode || p->k <= 32);
     cudaStream_t ax = side ? h->aux_stream : st;
     if (side) {
       CU(cudaEventRecord(h->ev_fork, st));

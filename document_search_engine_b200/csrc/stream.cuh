@@ -222,7 +222,10 @@ __device__ __forceinline__ void and_four(const SubCtx& cx, float w, uint32_t g, 
 // Requires: k <= 32 * KR, <= ST_MAX_LEAVES leaves, every leaf weight > 0, no after_key, no postings of
 // deleted documents in the store (bm25f_create compacts them away).
 template <int KR, bool FINAL>
-__global__ void __launch_bounds__(ST_MAX_WARPS * 32, 1) k_score_stream(StreamParams sp) {
+// (KR >= 4 without final(): a register cap of 88 - the bound of a 736-thread CTA - instead of the 92 / 96 the compiler
+// would take; it settles at 80 without spills, and one k_score_isect<4 / 8> CTA, 72 / 80 registers x 256 threads, then
+// fits on the SM beside this kernel's 512 threads: config 4, top-100, 147.4 -> 128.3 ms per 50k-query step)
+__global__ void __launch_bounds__((KR >= 4 && !FINAL) ? 736 : ST_MAX_WARPS * 32, 1) k_score_stream(StreamParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
