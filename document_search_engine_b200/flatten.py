@@ -38,10 +38,15 @@ def _text(field, btext):
     return btext.decode("utf-8") if isinstance(btext, (bytes, bytearray)) else btext
 
 
-def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool = True) -> FlatIndex:
-    """Flatten the postings of ``fields`` (default: every indexed field) of a Whoosh-style ``reader``."""
+def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool = True,
+                   date_fields: Sequence[str] = ()) -> FlatIndex:
+    """Flatten the postings of ``fields`` (default: every indexed field) of a Whoosh-style ``reader``.
+    ``date_fields`` (the reference's ``date``): instead of Whoosh's tiered numeric terms these fields get the flat
+    index's own year / month / day tokens, built from the documents' stored values (``dates.py``), which is what
+    ``DateRange`` queries expand to."""
     schema = reader.schema
     names = list(fields) if fields is not None else list(reader.indexed_field_names())
+    names = [n for n in names if n not in date_fields]
     n_docs = int(reader.doc_count_all())
     offs: List[int] = [0]
     docids: List[np.ndarray] = []
@@ -81,8 +86,31 @@ def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool 
                 lengths[f, d] = reader.doc_field_length(d, name, 0)
     deleted = np.fromiter((1 if reader.is_deleted(d) else 0 for d in range(n_docs)), dtype=np.uint8, count=n_docs)
     stored_docs = None
-    if stored:
+    if stored or date_fields:
         stored_docs = [dict(reader.stored_fields(d)) if not deleted[d] else {} for d in range(n_docs)]
+    if date_fields:
+        from .dates import tier_tokens
+        for name in date_fields:
+            f = len(names)
+            names.append(name)
+            scorable.append(False)
+            lists = {}
+            for d, sf in enumerate(stored_docs):
+                if sf.get(name) is not None:
+                    for tok in tier_tokens(sf[name]):
+                        lists.setdefault(tok, []).append(d)
+            for tok in sorted(lists):
+                a = np.asarray(lists[tok], dtype=np.uint32)
+                terms[(f, tok)] = len(term_field)
+                term_field.append(f)
+                df.append(int(a.size))
+                docids.append(a)
+                tfs.append(np.ones(a.size, dtype=np.float32))
+                offs.append(offs[-1] + a.size)
+        lengths = np.concatenate([lengths, np.zeros((len(date_fields), n_docs), dtype=np.int64)])
+        totals = np.concatenate([totals, np.zeros(len(date_fields), dtype=np.uint64)])
+        if not stored:
+            stored_docs = None
     cat = (lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt))
     return FlatIndex(field_names=names, n_docs_all=n_docs, term_offsets=np.asarray(offs, dtype=np.uint64),
                      docids=cat(docids, np.uint32), tfs=cat(tfs, np.float32),
@@ -92,11 +120,11 @@ def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool 
                      deleted=deleted if deleted.any() else None, stored=stored_docs, scorable=scorable)
 
 
-def flatten_index(ix, fields: Optional[Sequence[str]] = None, stored: bool = True) -> FlatIndex:
+def flatten_index(ix, fields: Optional[Sequence[str]] = None, stored: bool = True, date_fields: Sequence[str] = ()) -> FlatIndex:
     """``flatten_reader`` over ``ix.reader()`` (a ``whoosh.index.Index``, e.g. ``my_index.get_idx('index')``)."""
     reader = ix.reader()
     try:
-        return flatten_reader(reader, fields=fields, stored=stored)
+        return flatten_reader(reader, fields=fields, stored=stored, date_fields=date_fields)
     finally:
         close = getattr(reader, "close", None)
         if close is not None:

@@ -270,12 +270,19 @@ class FlatIndex:
     @classmethod
     def from_documents(cls, docs: Sequence[Mapping[str, object]], fields: Sequence[str],
                        analyzer=None, stored: Optional[Sequence[str]] = None,
-                       deleted: Iterable[int] = (), id_fields: Sequence[str] = ()) -> "FlatIndex":
+                       deleted: Iterable[int] = (), id_fields: Sequence[str] = (),
+                       date_fields: Sequence[str] = ()) -> "FlatIndex":
         """Build from tokenised documents: ``doc[field]`` is a token list or a string
         split on whitespace by default.  Token boosts are all 1 so ``tf`` is the term
         count (W7).  ``id_fields``: fields indexed like Whoosh's ``ID`` type (the reference's ``book``,
         ``my_index.py:152``): the whole value is one term, posting weight 1 (Existence format), no length
-        is stored and the field is not scorable (W15)."""
+        is stored and the field is not scorable (W15).  ``date_fields``: fields whose value is a date (the
+        reference's ``date=DATETIME``, ``my_index.py:150-175``): filed under a year, a month and a day token
+        (``dates.tier_tokens``) so that ``DateRange`` queries become OR-groups of posting lists; not scorable either.
+        A date field that is not in ``fields`` is appended to them."""
+        from .dates import tier_tokens
+        fields = list(fields) + [f for f in date_fields if f not in fields]
+        id_fields = list(id_fields) + list(date_fields)
         analyzer = analyzer or (lambda text: text.split())
         n = len(docs)
         nf = len(fields)
@@ -285,6 +292,10 @@ class FlatIndex:
             for f, name in enumerate(fields):
                 v = doc.get(name)
                 if v is None:
+                    continue
+                if name in date_fields:
+                    for tok in tier_tokens(v):
+                        postings.setdefault((f, tok), {})[d] = 1.0
                     continue
                 if name in id_fields:
                     postings.setdefault((f, v), {})[d] = 1.0

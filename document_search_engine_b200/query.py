@@ -312,6 +312,39 @@ class Wildcard(MultiTerm):
         return self
 
 
+class DateRange(MultiTerm):
+    """``date:[oct 1970 to dec 8 1970]`` / ``date:"feb 1964"`` (reference ``search-form.html:26``, ``:39``; parsed by
+    Whoosh's ``DateParserPlugin``, ``my_flask.py:189-193``).  [W] ``query.DateRange`` is a ``NumericRange`` over the
+    DATETIME field: it compiles to the ``Or`` of the tiered numeric terms that cover the range inside a
+    ``ConstantScoreQuery(boost)`` - a matching document scores ``boost``, and adds it to the other clauses' scores
+    inside an ``And``.  The flat index files every document date under a year, a month and a day token of a
+    non-scorable field (``dates.py``), so the same rewrite gives an OR-group of ordinary posting lists whose
+    postings score exactly ``boost``.  ``start`` / ``end`` are datetimes or dates, inclusive, ``None`` = open."""
+
+    def __init__(self, fieldname: str, start=None, end=None, boost: float = 1.0):
+        MultiTerm.__init__(self, fieldname, "[%s to %s]" % ("" if start is None else start, "" if end is None else end), boost)
+        self.start = start
+        self.end = end
+
+    def __str__(self):
+        return "%s:%s" % (self.fieldname, self.text)
+
+    def expand(self, lexicon: Sequence[str]) -> Query:
+        from . import dates
+        days = [w for w in lexicon if w.startswith("D")]
+        if not days:
+            return NullQuery
+        lo = dates.first_day(self.start) if self.start is not None else dates.date(int(days[0][1:5]), 1, 1)
+        hi = dates.last_day(self.end) if self.end is not None else dates.date(int(days[-1][1:5]), 12, 31)
+        have = set(lexicon)
+        toks = [t for t in dates.range_cover(lo, hi) if t in have]
+        if not toks:
+            return NullQuery
+        if len(toks) == 1:
+            return Term(self.fieldname, toks[0], boost=self.boost)
+        return Or([Term(self.fieldname, t, boost=self.boost) for t in toks])
+
+
 def has_multiterm(q: Query) -> bool:
     if isinstance(q, MultiTerm):
         return True
@@ -472,6 +505,7 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
 # --------------------------------------------------------------------------
 
 _TOKEN_RE = re.compile(r"\s*(?:(\w+):)?([^\s()]+)")
+_DATE_EXPR_RE = re.compile(r"\b(\w+):(?:\[([^\]]*)\]|\"([^\"]*)\")")
 
 
 class QueryParser:
@@ -481,21 +515,42 @@ class QueryParser:
     (lower-casing, stemming ...); the default lower-cases.
     """
 
-    def __init__(self, fieldname: str, schema=None, analyzer=None, termclass=Term):
+    def __init__(self, fieldname: str, schema=None, analyzer=None, termclass=Term, date_fields=("date",)):
         self.fieldname = fieldname
         self.schema = schema
         self.analyzer = analyzer or (lambda field, text: [text.lower()])
         self.termclass = termclass
+        #: fields whose values are dates: ``field:[a to b]``, ``field:"feb 1964"``, ``field:1964`` become ``DateRange``
+        #: (what ``qp.add_plugin(DateParserPlugin())`` does in the reference, ``my_flask.py:190``)
+        self.date_fields = tuple(date_fields)
 
     def add_plugin(self, plugin):  # accepted for call-compatibility (my_flask.py:190)
         return None
 
     def parse(self, text: str) -> Query:
+        from . import dates
+        held: List[Query] = []
+
+        def hold(m):
+            if m.group(1) not in self.date_fields:
+                return m.group(0)
+            expr = m.group(2) if m.group(2) is not None else m.group(3)
+            start, end = dates.parse_range(expr)                 # DateParseError: the caller redirects (my_flask.py:193-196)
+            held.append(DateRange(m.group(1), start, end))
+            return " \x00%d " % (len(held) - 1)
+        text = _DATE_EXPR_RE.sub(hold, text or "")
         nodes: List[object] = []          # Query nodes and the markers "AND" / "OR"
         for m in _TOKEN_RE.finditer(text or ""):
             field, tok = m.group(1), m.group(2)
             if field is None and tok in ("AND", "OR", "NOT"):
                 nodes.append(tok)
+                continue
+            if field is None and tok.startswith("\x00"):
+                nodes.append(held[int(tok[1:])])
+                continue
+            if field in self.date_fields:
+                start, end = dates.parse_span(tok)
+                nodes.append(DateRange(field, start, end))
                 continue
             field = field or self.fieldname
             if any(ch in Wildcard.SPECIAL_CHARS for ch in tok):

@@ -31,6 +31,27 @@ def _expand(q, ix):
     return sorted(t for (ff, t) in (ix.terms or {}) if ff == f and isinstance(t, str) and fits(t))
 
 
+def date_range_docs(sub, fieldname, start, end):
+    """Local docnums of ``sub`` whose stored ``fieldname`` date lies in ``[start, end]`` (``None`` = open), by brute
+    force over the stored fields - deliberately not through the index's date tokens, which are what is under test.
+    Whoosh: query.DateRange -> NumericRange over the DATETIME field (reference search-form.html:26, :39)."""
+    from datetime import datetime
+    out = []
+    for d, sf in enumerate(sub.stored or []):
+        v = sf.get(fieldname)
+        if v is None:
+            continue
+        when = v if isinstance(v, datetime) else datetime(v.year, v.month, v.day)
+        if (start is None or _as_dt(start) <= when) and (end is None or when <= _as_dt(end)):
+            out.append(d)
+    return np.asarray(out, dtype=np.int64)
+
+
+def _as_dt(v):
+    from datetime import datetime
+    return v if isinstance(v, datetime) else datetime(v.year, v.month, v.day)
+
+
 def lower_query(q, ix=None):
     """``(groups, negatives, kind)``: ``groups`` is a list of OR-groups, each a list of
     ``(fieldname, text, boost)``; all groups must match (W10) and no leaf of ``negatives``
@@ -42,6 +63,9 @@ def lower_query(q, ix=None):
         return [[(q.fieldname, None, q.boost)]], [], "every"
     if name == "Term":
         return [[(q.fieldname, q.text, q.boost)]], [], "groups"
+    if name == "DateRange":
+        # constant score: every document of the range scores the boost (ConstantScoreQuery)
+        return [[(q.fieldname, ("daterange", q.start, q.end), q.boost)]], [], "groups"
     if name in ("Prefix", "Wildcard"):
         words = _expand(q, ix)
         if not words:
@@ -60,6 +84,10 @@ def lower_query(q, ix=None):
                 else:
                     flat.extend((s.fieldname, w, b) for w in words)
                 continue
+            if sn == "DateRange":
+                leaf = (s.fieldname, ("daterange", s.start, s.end), s.boost * q.boost)
+                (groups if name == "And" else flat).append([leaf] if name == "And" else leaf)
+                continue
             if sn == "Term":
                 (groups if name == "And" else flat).append(
                     [(s.fieldname, s.text, s.boost * q.boost)] if name == "And" else (s.fieldname, s.text, s.boost * q.boost))
@@ -70,6 +98,8 @@ def lower_query(q, ix=None):
                 for t in inner:
                     if type(t).__name__ in ("Prefix", "Wildcard"):
                         neg.extend((t.fieldname, w) for w in _expand(t, ix))
+                    elif type(t).__name__ == "DateRange":
+                        neg.append((t.fieldname, ("daterange", t.start, t.end)))
                     else:
                         neg.append((t.fieldname, t.text))
             else:
@@ -104,6 +134,11 @@ class NumpyOracle:
 
     def leaf_scores(self, sub, fieldname, text, boost):
         """(local docids, float64 scores) of one leaf in one shard; deleted docs removed (W9)."""
+        if isinstance(text, tuple) and text and text[0] == "daterange":
+            d = date_range_docs(sub, fieldname, text[1], text[2])
+            if sub.deleted is not None:
+                d = d[sub.deleted[d] == 0]
+            return d, np.full(d.size, float(boost))
         tid = sub.term_id(fieldname, text)
         if tid < 0:
             return np.zeros(0, np.int64), np.zeros(0, np.float64)

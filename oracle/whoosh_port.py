@@ -214,6 +214,14 @@ class OracleSearcher:
                 return ms[0]
             m = _binary_tree(UnionMatcher, ms)
             return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
+        if name == "DateRange":
+            # Whoosh query.DateRange = NumericRange over the DATETIME field inside ConstantScoreQuery(boost): every
+            # live document whose date lies in the range scores the boost (reference search-form.html:26, :39;
+            # my_flask.py:189-193).  Evaluated over the stored dates, not through the index's date tokens.
+            from oracle.numpy_oracle import date_range_docs
+            ids = [int(d) for d in date_range_docs(sub, q.fieldname, q.start, q.end)
+                   if not (sub.deleted is not None and sub.deleted[d])]
+            return ConstMatcher(ids, q.boost) if ids else NullMatcher()
         if name == "_Null":
             return NullMatcher()
         raise NotImplementedError(name)

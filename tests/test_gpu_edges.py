@@ -195,3 +195,20 @@ def test_compact_store_releases_the_raw_postings():
         res = s.search_batch(qs, limit=10)                        # the engine still serves its weighting
         assert_batch_parity(o, qs, res, 10)
     ix._engine_cache.clear()
+
+
+def test_date_ranges_f3():
+    """``date:[oct 1970 to dec 8 1970]`` / ``hospital date:"feb 1964"`` (search-form.html:26, :39): DateRange queries
+    expand on the host into the index's year / month / day posting lists and run on the ordinary kernels; the oracle
+    evaluates them over the stored dates."""
+    from tests.test_dates import corpus, queries
+    from document_search_engine_b200 import QueryParser
+    ix = corpus(3000, seed=11)
+    qp = QueryParser("body")
+    qs = queries() + [qp.parse('w5 date:"feb 1966"'), qp.parse("date:[oct 1965 to dec 8 1967]"), qp.parse("w1 OR w2 date:1968"),
+                      qp.parse("date:[to 1964]"), qp.parse("w3 NOT date:[1965 to 1970]")]
+    for limit in (10, 100):
+        res = check(ix, qs, limit=limit)
+    assert len(res[0]) > 0 and res[4].is_empty()
+    one = check(ix, [queries()[5]], limit=5)[0]                 # a single day, boost 2.5: every hit scores the boost
+    assert all(abs(h.score - 2.5) < 1e-6 for h in one)
