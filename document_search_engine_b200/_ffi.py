@@ -28,7 +28,7 @@ EXPORTS = (
     "bm25f_prepare", "bm25f_prepare_arena", "bm25f_execute", "bm25f_fetch", "bm25f_plan_device_results", "bm25f_synchronize",
     "bm25f_set_stream", "bm25f_plan_destroy", "bm25f_search_batch", "bm25f_merge_keys", "bm25f_decode_keys", "bm25f_get_stats",
     "bm25f_reset_stats", "bm25f_submit", "bm25f_collect", "bm25f_set_final_date", "bm25f_fetch_final",
-    "bm25f_plan_device_final", "bm25f_merge_final_lists", "bm25f_plan_gather_span", "bm25f_merge_gathered",
+    "bm25f_plan_device_final", "bm25f_merge_final_lists", "bm25f_plan_gather_span", "bm25f_merge_gathered", "bm25f_put_lists",
 )
 
 
@@ -52,7 +52,8 @@ class Options(C.Structure):
                 ("prefetch_postings", C.c_uint32), ("cta_warps", C.c_uint32), ("cta_prefetch", C.c_uint32),
                 ("cta_split", C.c_uint32), ("cta_slice_docs", C.c_uint32), ("isect_ratio", C.c_uint32),
                 ("isect_split", C.c_uint32), ("isect_or_limit", C.c_uint32), ("serial_streams", C.c_uint32),
-                ("host_plan", C.c_uint32), ("compact_store", C.c_uint32)]
+                ("host_plan", C.c_uint32), ("compact_store", C.c_uint32),
+                ("filter_postings", C.c_uint32)]
 
 
 #: engine options a caller may pass (``bm25f_options`` field names; 0 = library default)
@@ -104,6 +105,7 @@ def load_library(path: Optional[str] = None):
     lib.bm25f_plan_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     lib.bm25f_synchronize.argtypes = [vp]
     lib.bm25f_set_stream.argtypes = [vp, vp, i32]
+    lib.bm25f_put_lists.argtypes = [vp, u32, vp, vp, C.POINTER(u32)]
     lib.bm25f_plan_destroy.argtypes = [vp]
     lib.bm25f_plan_destroy.restype = None
     lib.bm25f_search_batch.argtypes = [vp, C.POINTER(QueryBatchDesc), i32, vp, vp, vp, vp]
@@ -370,6 +372,18 @@ class Engine:
             _check(self.lib, self.lib.bm25f_set_stream(self._h, None, 1))
         else:
             _check(self.lib, self.lib.bm25f_set_stream(self._h, C.c_void_p(stream), 0))
+
+    def put_lists(self, lists) -> int:
+        """Hand the library per-batch document lists (``bm25f_put_lists``: phrase filters); ``lists`` are ascending
+        local docnum arrays.  Returns the ``leaf_term`` id of the first one; they replace the previous call's lists."""
+        offs = np.zeros(len(lists) + 1, dtype=np.uint64)
+        if lists:
+            np.cumsum([len(x) for x in lists], out=offs[1:])
+        docs = (np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint32) for x in lists]))
+                if lists else np.zeros(0, np.uint32))
+        first = C.c_uint32()
+        _check(self.lib, self.lib.bm25f_put_lists(self._h, len(lists), _ptr(offs), _ptr(docs), C.byref(first)))
+        return int(first.value)
 
     def stats(self) -> dict:
         s = Stats()

@@ -1372,6 +1372,10 @@ struct bm25f_handle {
   int is_ctas_per_sm = 0;
   bool serial_streams = false;          // option: never run the second-stream kernels beside the first-stream ones
   bool host_plan = false;               // option: never plan a batch on the device (plan.cuh)
+  // per-batch document lists (bm25f_put_lists): a region of `pairs` behind the index's postings; term ids
+  // n_terms + 1 + i (term n_terms is the padding between the two regions and is never valid)
+  uint64_t dyn_base = 0, dyn_cap = 0;
+  uint32_t dyn_terms = 0;
   bool compact_store = false;           // option: release the raw postings after the first bm25f_set_weighting
   bool raw_dropped = false;             // ... done: 8 bytes a posting stay; no re-weighting, no CTA-kernel queries
   std::vector<float> norm_host;         // the weighting in force (compact_store: the only one this handle will ever serve)
@@ -1824,10 +1828,12 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     }
   }
   RCT(dev_alloc(&h->d_payload, P + pad, h));
-  RCT(dev_alloc(&h->d_pairs, P + pad, h));
+  h->dyn_base = P + pad;
+  h->dyn_cap = (opts && opts->filter_postings) ? opts->filter_postings : (1u << 20);
+  RCT(dev_alloc(&h->d_pairs, P + pad + h->dyn_cap + pad, h));
   CUT(cudaMemsetAsync(h->d_docids + P, 0xFF, pad * 4, h->stream));
   CUT(cudaMemsetAsync(h->d_payload + P, 0, pad * 4, h->stream));
-  CUT(cudaMemsetAsync(h->d_pairs + P, 0xFF, pad * 8, h->stream));
+  CUT(cudaMemsetAsync(h->d_pairs + P, 0xFF, (pad + h->dyn_cap + pad) * 8, h->stream));
 
   CUT(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
   int flag = 0;
@@ -1861,8 +1867,8 @@ int bm25f_create(const bm25f_index_desc* desc, int device, const bm25f_options* 
     t = t2;
   }
   // the device planner's view of the posting lists (after the compaction above)
-  RCT(dev_alloc(&h->d_term_offsets, h->n_terms + 1, h));
-  RCT(dev_alloc(&h->d_term_field, h->n_terms + 1, h));
+  RCT(dev_alloc(&h->d_term_offsets, h->n_terms + 2 + BM25F_MAX_FILTER_LISTS, h));
+  RCT(dev_alloc(&h->d_term_field, h->n_terms + 2 + BM25F_MAX_FILTER_LISTS, h));
   CUT(cudaMemcpyAsync(h->d_term_offsets, h->term_offsets.data(), (h->n_terms + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   if (h->n_terms) CUT(cudaMemcpyAsync(h->d_term_field, h->term_field.data(), h->n_terms, cudaMemcpyHostToDevice, h->stream));
   CUT(cudaHostAlloc(reinterpret_cast<void**>(&h->h_ctr), PL_CTR_BYTES, cudaHostAllocDefault));
@@ -2000,6 +2006,11 @@ namespace {
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) & ~(a - 1); }
 
 // BM25F_TERM_EVERY(field) -> the field's pseudo posting list; an unknown field matches nothing
+// a resolved leaf_term names a posting list of the index, an Every(field) list, or a list of the last bm25f_put_lists
+inline bool valid_term(const bm25f_handle* h, uint32_t term) {
+  return term < h->n_terms || (term > h->n_terms && term <= h->n_terms + h->dyn_terms);
+}
+
 inline uint32_t resolve_term(const bm25f_handle* h, uint32_t term) {
   if (term >= BM25F_TERM_EVERY_BASE && term != BM25F_TERM_UNKNOWN) {
     const uint32_t f = term - BM25F_TERM_EVERY_BASE;
@@ -2099,7 +2110,8 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
   if (bad_q) DECLINE("has more than 8 leaves or groups, a NOT clause or malformed groups");
   // (2) per leaf: finite weight; a known term must be in range and carry a positive weight (an unknown term's leaf is
   // dropped: its weight - 0 for a term no shard knows - does not matter)
-  const uint32_t n_lists = (uint32_t)(h->n_real_terms + h->n_fields);
+  const uint32_t n_lists = (uint32_t)h->n_terms;                   // (n_real_terms + the Every lists)
+  const uint32_t dyn_lo = (uint32_t)h->n_terms + 1u, dyn_hi = (uint32_t)h->n_terms + h->dyn_terms;   // bm25f_put_lists
   const uint32_t n_fields = h->n_fields;
   uint32_t bad_l = 0;
   for (uint32_t i = 0; i < NL; ++i) {
@@ -2108,14 +2120,15 @@ int prepare_on_device(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_
     const uint32_t unknown = (t == BM25F_TERM_UNKNOWN) | ((t >= BM25F_TERM_EVERY_BASE) & (t - BM25F_TERM_EVERY_BASE >= n_fields));
     const uint32_t every = (t >= BM25F_TERM_EVERY_BASE) & (unknown ^ 1u);
     const uint32_t finite = (std::fabs(w) <= 3.402823466e+38f);               // false for NaN and infinities
-    bad_l |= (finite ^ 1u) | ((unknown ^ 1u) & (((every ^ 1u) & (t >= n_lists)) | (uint32_t)!(w > 1e-30f)));
+    const uint32_t in_range = (t < n_lists) | ((t >= dyn_lo) & (t <= dyn_hi));
+    bad_l |= (finite ^ 1u) | ((unknown ^ 1u) & (((every ^ 1u) & (in_range ^ 1u)) | (uint32_t)!(w > 1e-30f)));
   }
   if (bad_l) DECLINE("has a non-finite or non-positive weight, or names a posting list out of range");
   const uint32_t sample = NL >= 8192 ? 8u : 1u;
   uint64_t total = 0;
   for (uint32_t i = 0; i < NL; i += sample) {
     const uint32_t term = resolve_term(h, lterm[i]);
-    if (term != BM25F_TERM_UNKNOWN) total += h->term_offsets[term + 1] - h->term_offsets[term];
+    if (term != BM25F_TERM_UNKNOWN && term < h->n_terms) total += h->term_offsets[term + 1] - h->term_offsets[term];
   }
   total *= sample;
 #undef DECLINE
@@ -2354,7 +2367,7 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
     bool gseen[32];
     for (uint32_t g = 0; g < G; ++g) { gsize[g] = 0; gseen[g] = false; }
     uint32_t prev_g = 0, n_neg_in = 0;
-    bool all_pos = true;
+    bool all_pos = true, has_dyn = false;
     for (uint32_t i = a; i < e; ++i) {
       const uint32_t g = b->leaf_group[i];
       const bool neg = (g == BM25F_GROUP_NOT);             // a leaf of a NOT clause: excludes, never scores
@@ -2363,7 +2376,8 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
       if (!neg) gseen[g] = true;
       const uint32_t term = resolve_term(h, b->leaf_term[i]);
       if (term != BM25F_TERM_UNKNOWN) {
-        if (term >= h->n_real_terms + h->n_fields) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, b->leaf_term[i]);
+        if (!valid_term(h, term)) PFAIL(BM25F_EINVAL, "query %u: leaf_term %u out of range", qi, b->leaf_term[i]);
+        if (term > h->n_terms) has_dyn = true;
         if (!neg) gsize[g] += h->term_offsets[term + 1] - h->term_offsets[term];
       }
       if (neg) { ++n_neg_in; continue; }
@@ -2451,6 +2465,9 @@ int prepare_impl(bm25f_handle* h, const bm25f_query_batch* b, int k, bm25f_plan*
                                    : g0 * (uint64_t)(nlq - 1) * h->is_ratio < P)));
     const bool use_team = !use_isect && stream_ok && qr.after_key == 0ull && n_neg == 0 && !final_mode && k <= 32 && (h->variant == 4 || (h->variant == 0 && !(qr.flags & QF_SIMPLE_OR)));
     const int cls = use_isect ? 3 : stream_ok ? (use_team ? 1 : 0) : 2;
+    if (cls == 2 && has_dyn)
+      PFAIL(BM25F_EINVAL, "query %u uses a bm25f_put_lists list and needs the CTA kernels (k > 256, more than 32 leaves, a non-positive "
+                          "weight or a paging bound): per-batch lists are served by the warp kernels only", qi);
     if (cls == 2 && h->raw_dropped)
       PFAIL(BM25F_EINVAL, "query %u needs the kernels that read the raw postings (k > 256, more than 32 leaves, a non-positive weight or a "
                           "paging bound) and the engine was created with compact_store", qi);
@@ -3180,6 +3197,47 @@ int bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_querie
     k_decode_keys<<<n_queries, 64, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_keys), n_queries, k, d_scores, d_docids, d_counts);
     CU(cudaGetLastError());
   }
+  return 0;
+}
+
+int bm25f_put_lists(bm25f_handle* h, uint32_t n_lists, const uint64_t* offsets, const uint32_t* docids, uint32_t* first_term) {
+  if (!h || !first_term || (n_lists && (!offsets || (offsets[n_lists] && !docids)))) return fail(BM25F_EINVAL, "null argument");
+  if (n_lists > BM25F_MAX_FILTER_LISTS) return fail(BM25F_EINVAL, "at most %d lists a batch", BM25F_MAX_FILTER_LISTS);
+  if (n_lists && offsets[0] != 0) return fail(BM25F_EINVAL, "offsets must start at 0");
+  const uint64_t total = n_lists ? offsets[n_lists] : 0;
+  if (total > h->dyn_cap) return fail(BM25F_EINVAL, "%llu postings in the lists, room for %llu (option filter_postings)", (unsigned long long)total, (unsigned long long)h->dyn_cap);
+  for (uint32_t l = 0; l < n_lists; ++l) {
+    if (offsets[l + 1] < offsets[l] || offsets[l + 1] > total) return fail(BM25F_EINVAL, "offsets not monotonic at list %u", l);
+    for (uint64_t i = offsets[l]; i < offsets[l + 1]; ++i)
+      if (docids[i] >= h->n_docs || (i > offsets[l] && docids[i] <= docids[i - 1]))
+        return fail(BM25F_EINVAL, "list %u: docids must be < n_docs_all and strictly ascending", l);
+  }
+  for (auto& A : h->arenas)
+    if (A.submitted) return fail(BM25F_EINVAL, "a submitted batch is in flight: bm25f_collect it before replacing the lists");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));            // nothing may still be reading the previous lists
+  CU(cudaStreamSynchronize(h->copy_stream));
+  // {docid, impact 1.0}, then a run of end markers: rows and prefetches may read past the last posting of the last list
+  const size_t pad = 1024;
+  std::vector<uint2> pairs(total + pad);
+  const uint32_t one = 0x3F800000u;
+  for (uint64_t i = 0; i < total; ++i) pairs[i] = make_uint2(docids[i], one);
+  for (size_t i = 0; i < pad; ++i) pairs[total + i] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+  CU(cudaMemcpyAsync(h->d_pairs + h->dyn_base, pairs.data(), pairs.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+  // term table: [0, n_terms) the index, n_terms the padding between the regions, then the lists (pseudo-field n_fields)
+  h->term_offsets.resize(h->n_terms + 1);
+  h->term_field.resize(h->n_terms);
+  h->term_offsets.push_back(h->dyn_base);
+  h->term_field.push_back((uint8_t)h->n_fields);
+  for (uint32_t l = 0; l < n_lists; ++l) {
+    h->term_offsets.push_back(h->dyn_base + offsets[l + 1]);
+    h->term_field.push_back((uint8_t)h->n_fields);
+  }
+  h->dyn_terms = n_lists;
+  CU(cudaMemcpyAsync(h->d_term_offsets + h->n_terms, h->term_offsets.data() + h->n_terms, ((size_t)n_lists + 2) * 8, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->d_term_field + h->n_terms, h->term_field.data() + h->n_terms, (size_t)n_lists + 1, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));            // (the sources are locals)
+  *first_term = (uint32_t)h->n_terms + 1u;
   return 0;
 }
 

@@ -95,7 +95,8 @@ class FlatIndex:
                  doc_base: int = 0,
                  global_doc_count_all: Optional[int] = None,
                  term_weight_total: Optional[np.ndarray] = None,
-                 scorable: Optional[Sequence[bool]] = None):
+                 scorable: Optional[Sequence[bool]] = None,
+                 positions: Optional[Dict[int, Tuple[np.ndarray, np.ndarray]]] = None):
         self.field_names = list(field_names)
         self.n_docs_all = int(n_docs_all)
         self.term_offsets = np.ascontiguousarray(term_offsets, dtype=np.uint64)
@@ -125,6 +126,11 @@ class FlatIndex:
         self.scorable = [True] * len(self.field_names) if scorable is None else [bool(x) for x in scorable]
         if len(self.scorable) != len(self.field_names):
             raise ValueError("scorable must have one entry per field")
+        #: word order, for phrases (Whoosh: the ``positions`` posting format of a ``TEXT(phrase=True)`` field; reference
+        #: ``my_index.py:172-177``): per field index ``f`` the documents' token sequences as posting-list ids,
+        #: ``(offsets[n_docs_all + 1], ids[sum of lengths])``, -1 for a token that is not indexed.  Host side only.
+        self.positions = {int(f): (np.ascontiguousarray(o, dtype=np.int64), np.ascontiguousarray(i, dtype=np.int32))
+                          for f, (o, i) in (positions or {}).items()}
         self.schema = Schema(self.field_names, stored=self._stored_names())
         #: identifies this index object in caches that must not hold on to it (Searcher.pack)
         self.token = next(_TOKENS)
@@ -287,7 +293,9 @@ class FlatIndex:
         n = len(docs)
         nf = len(fields)
         postings: Dict[Tuple[int, object], Dict[int, float]] = {}
+        nf = len(fields)
         lengths = np.zeros((nf, n), dtype=np.int64)
+        sequences: Dict[int, List[list]] = {f: [] for f, name in enumerate(fields) if name not in id_fields}
         for d, doc in enumerate(docs):
             for f, name in enumerate(fields):
                 v = doc.get(name)
@@ -301,6 +309,9 @@ class FlatIndex:
                     postings.setdefault((f, v), {})[d] = 1.0
                     continue
                 toks = analyzer(v) if isinstance(v, str) else list(v)
+                while len(sequences[f]) < d:
+                    sequences[f].append([])
+                sequences[f].append(toks)
                 lengths[f, d] = len(toks)
                 for t in toks:
                     p = postings.setdefault((f, t), {})
@@ -325,7 +336,13 @@ class FlatIndex:
         stored_docs = None
         if stored:
             stored_docs = [{k: doc[k] for k in stored if k in doc} for doc in docs]
-        return cls(field_names=fields, n_docs_all=n, term_offsets=offs,
+        positions = {}
+        for f, seqs in sequences.items():
+            seqs = seqs + [[]] * (n - len(seqs))
+            po = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([len(x) for x in seqs], out=po[1:])
+            positions[f] = (po, np.fromiter((terms[(f, t)] for x in seqs for t in x), dtype=np.int32, count=int(po[-1])))
+        return cls(field_names=fields, n_docs_all=n, term_offsets=offs, positions=positions,
                    docids=np.array(dl, dtype=np.uint32), tfs=np.array(tl, dtype=np.float32),
                    term_field=np.array([k[0] for k in keys], dtype=np.uint8),
                    len_bytes=lb, field_length_total=lengths.sum(axis=1).astype(np.uint64),
@@ -355,7 +372,44 @@ class FlatIndex:
                          stored=None if self.stored is None else self.stored[lo:hi],
                          doc_base=self.doc_base + lo,
                          global_doc_count_all=self.global_doc_count_all,
-                         term_weight_total=self.term_weight_total, scorable=self.scorable)
+                         term_weight_total=self.term_weight_total, scorable=self.scorable,
+                         positions={f: (o[lo:hi + 1] - o[lo], i[int(o[lo]):int(o[hi])]) for f, (o, i) in self.positions.items()})
+
+    # ---- phrases (host side) ----------------------------
+    def phrase_docs(self, fieldname, words: Sequence[object], slop: int = 1) -> np.ndarray:
+        """Local docnums (ascending) in which ``words`` occur in this order, every word at most ``slop`` positions
+        after the one before (``slop=1``: adjacent) - the documents Whoosh's ``Phrase(fieldname, words, slop)`` lets
+        through its ``SpanNear`` chain.  Needs the field's word order (``positions``)."""
+        f = self.field_index(fieldname)
+        if f < 0:
+            return np.zeros(0, np.uint32)
+        if f not in self.positions:
+            raise NotImplementedError("field %r was flattened without positions: no phrase queries on it" % fieldname)
+        tids = [self.term_id(fieldname, w) for w in words]
+        if not tids or min(tids) < 0:
+            return np.zeros(0, np.uint32)
+        cand = None
+        for t in sorted(set(tids), key=lambda t: int(self.term_offsets[t + 1] - self.term_offsets[t])):
+            d = self.docids[int(self.term_offsets[t]):int(self.term_offsets[t + 1])]
+            cand = d if cand is None else np.intersect1d(cand, d, assume_unique=True)
+            if cand.size == 0:
+                return np.zeros(0, np.uint32)
+        offs, ids = self.positions[f]
+        out = []
+        for d in cand.tolist():
+            seq = ids[int(offs[d]):int(offs[d + 1])]
+            ends = np.nonzero(seq == tids[0])[0]
+            for t in tids[1:]:
+                if ends.size == 0:
+                    break
+                pos = np.nonzero(seq == t)[0]
+                # keep the positions that follow some kept position of the previous word by 1 .. slop
+                j = np.searchsorted(ends, pos, side="left")             # ends[j - 1] < pos
+                ok = (j > 0) & (pos - ends[np.maximum(j - 1, 0)] <= slop)
+                ends = pos[ok]
+            if ends.size:
+                out.append(d)
+        return np.asarray(out, dtype=np.uint32)
 
     # ---- persistence (the "checkpoint": a flattened index file) --------------
     def save(self, path: str) -> None:
@@ -374,7 +428,9 @@ class FlatIndex:
                  doc_base=self.doc_base, global_doc_count_all=self.global_doc_count_all,
                  dict_field=tf_, dict_text=tt_, dict_id=ti_, scorable=np.array(self.scorable, dtype=np.uint8),
                  term_weight_total=(self.term_weight_total if self.term_weight_total is not None else np.zeros(0, np.float64)),
-                 stored_json=np.array("" if self.stored is None else json.dumps(list(self.stored), default=str)))
+                 stored_json=np.array("" if self.stored is None else json.dumps(list(self.stored), default=str)),
+                 pos_fields=np.array(sorted(self.positions), dtype=np.int64),
+                 **{"pos_%s_%d" % (kind, f): arr for f, pair in self.positions.items() for kind, arr in zip(("off", "ids"), pair)})
 
     @classmethod
     def load(cls, path: str) -> "FlatIndex":
@@ -394,4 +450,5 @@ class FlatIndex:
                    doc_base=int(z["doc_base"]), global_doc_count_all=int(z["global_doc_count_all"]),
                    scorable=[bool(x) for x in z["scorable"]] if "scorable" in z.files else None,
                    term_weight_total=(z["term_weight_total"] if "term_weight_total" in z.files and z["term_weight_total"].size else None),
-                   stored=(json.loads(str(z["stored_json"])) if "stored_json" in z.files and str(z["stored_json"]) else None))
+                   stored=(json.loads(str(z["stored_json"])) if "stored_json" in z.files and str(z["stored_json"]) else None),
+                   positions=({int(f): (z["pos_off_%d" % f], z["pos_ids_%d" % f]) for f in z["pos_fields"]} if "pos_fields" in z.files else None))

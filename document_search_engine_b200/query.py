@@ -345,6 +345,79 @@ class DateRange(MultiTerm):
         return Or([Term(self.fieldname, t, boost=self.boost) for t in toks])
 
 
+#: pseudo-field of the leaves that stand for a per-batch document list (``Phrase`` filters); never in a schema
+FILTER_FIELD = "\x00filter"
+
+
+class Phrase(Query):
+    """``"dead sea"`` / ``exact:"way toward health"~2`` (reference ``search-form.html:20-40``; Whoosh ``query.Phrase``).
+    [W] ``Phrase.matcher``: a word that is not in the field -> NullMatcher; else the ``SpanNear`` chain of the words'
+    term matchers, ordered, every word 1 .. ``slop`` positions after the one before (``slop=1``: adjacent), over an
+    IntersectionMatcher - so a matching document scores the SUM of its words' BM25F scores, and the positions only
+    decide whether it matches.  The engine does the same in two steps: the host finds the documents that pass the
+    positional test (``FlatIndex.phrase_docs``, over the candidates of the rarest word), hands them to the library as a
+    per-batch posting list (``bm25f_put_lists``), and the query runs as ``And(words..., that list)`` - the list is
+    the smallest group, so the candidate-driven kernel walks it and looks the words' postings up."""
+
+    def __init__(self, fieldname: str, words: Sequence[object], slop: int = 1, boost: float = 1.0):
+        self.fieldname = fieldname
+        self.words = list(words)
+        self.slop = int(slop)
+        self.boost = float(boost)
+
+    def __eq__(self, other):
+        return (isinstance(other, Phrase) and other.fieldname == self.fieldname and other.words == self.words
+                and other.slop == self.slop and other.boost == self.boost)
+
+    def __hash__(self):
+        return hash(("Phrase", self.fieldname, tuple(self.words), self.slop, self.boost))
+
+    def __repr__(self):
+        return "Phrase(%r, %r%s%s)" % (self.fieldname, self.words, "" if self.slop == 1 else ", slop=%d" % self.slop,
+                                      "" if self.boost == 1.0 else ", boost=%s" % self.boost)
+
+    def __str__(self):
+        return '%s:"%s"%s' % (self.fieldname, " ".join(str(w) for w in self.words), "" if self.slop == 1 else "~%d" % self.slop)
+
+    def leaves(self):
+        return iter(())
+
+    def normalize(self):
+        # [W] Phrase.normalize: no words -> NullQuery, one word -> its Term
+        if not self.words:
+            return NullQuery
+        if len(self.words) == 1:
+            return Term(self.fieldname, self.words[0], boost=self.boost)
+        return self
+
+
+def has_phrase(q: Query) -> bool:
+    if isinstance(q, Phrase):
+        return True
+    if isinstance(q, _Compound):
+        return any(has_phrase(s) for s in q.subqueries)
+    if isinstance(q, Not):
+        return has_phrase(q.query)
+    return False
+
+
+def expand_phrases(q: Query, register) -> Query:
+    """Replace every ``Phrase`` by ``And(its words..., Term(FILTER_FIELD, i))`` where ``i = register(phrase)`` numbers
+    the document list that will stand for the phrase's positional test in this batch (``Not(Phrase)``: the list alone)."""
+    if isinstance(q, Phrase):
+        q = q.normalize()
+        if not isinstance(q, Phrase):
+            return q
+        return And([Term(q.fieldname, w) for w in q.words] + [Term(FILTER_FIELD, register(q))], boost=q.boost)
+    if isinstance(q, _Compound):
+        return type(q)([expand_phrases(s, register) for s in q.subqueries], boost=q.boost)
+    if isinstance(q, Not):
+        if isinstance(q.query, Phrase) and len(q.query.words) > 1:
+            return Not(Term(FILTER_FIELD, register(q.query)))
+        return Not(expand_phrases(q.query, register))
+    return q
+
+
 def has_multiterm(q: Query) -> bool:
     if isinstance(q, MultiTerm):
         return True
@@ -506,6 +579,7 @@ def lower(q: Query) -> Tuple[List[Leaf], int, str]:
 
 _TOKEN_RE = re.compile(r"\s*(?:(\w+):)?([^\s()]+)")
 _DATE_EXPR_RE = re.compile(r"\b(\w+):(?:\[([^\]]*)\]|\"([^\"]*)\")")
+_PHRASE_RE = re.compile(r"(?:\b(\w+):)?\"([^\"]*)\"(?:~(\d+))?")
 
 
 class QueryParser:
@@ -539,6 +613,16 @@ class QueryParser:
             held.append(DateRange(m.group(1), start, end))
             return " \x00%d " % (len(held) - 1)
         text = _DATE_EXPR_RE.sub(hold, text or "")
+
+        def hold_phrase(m):
+            # Whoosh's PhrasePlugin: the quoted words are analysed like any other text of the field
+            field = m.group(1) or self.fieldname
+            if m.group(1) and self.schema is not None and hasattr(self.schema, "names") and field not in self.schema.names():
+                field = self.fieldname
+            words = [t for w in m.group(2).split() for t in self.analyzer(field, w)]
+            held.append(Phrase(field, words, slop=int(m.group(3) or 1)).normalize())
+            return " \x00%d " % (len(held) - 1)
+        text = _PHRASE_RE.sub(hold_phrase, text)
         nodes: List[object] = []          # Query nodes and the markers "AND" / "OR"
         for m in _TOKEN_RE.finditer(text or ""):
             field, tok = m.group(1), m.group(2)

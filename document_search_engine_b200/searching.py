@@ -27,12 +27,17 @@ from typing import Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _ffi
-from .query import And, Or, Query, Term, UnsupportedQuery, expand_multiterms, has_multiterm, lower
+from .query import (FILTER_FIELD, And, Or, Query, Term, UnsupportedQuery, expand_multiterms, expand_phrases, has_multiterm,
+                    has_phrase, lower)
 from .scoring import BM25F, instantiate
 
 #: one lowered leaf as ``Searcher.pack`` keeps it: posting-list id (or -1 / -2 - field), boost, group
 _LEAF_REC = np.dtype([("tid", "<i8"), ("boost", "<f8"), ("group", "u1"), ("pad", "V7")])
 _LEAF_STRUCT = struct.Struct("<qdB7x")
+#: ``tid`` of the leaf that stands for per-batch document list ``i`` (a phrase's positional test): ``_FILTER_TID - i``
+_FILTER_TID = -1000
+#: its weight: positive for the library, invisible next to any float32 score
+FILTER_WEIGHT = 1e-29
 
 #: bound on the per-call tile-boundary table (bytes); larger batches are split
 BOUNDS_BYTES_PER_CALL = 1 << 30
@@ -352,12 +357,13 @@ class Searcher:
             self._term_w = tw
         return tw
 
-    def _lower_one(self, q: Query):
+    def _lower_one(self, q: Query, register=None):
         """``(index, n_leaves, n_groups, packed leaf records, query)`` of one query: what ``pack`` needs, remembered
         on the query object.  A leaf record is ``_LEAF_REC``: posting-list id (-1: unknown term or field, W10;
         ``-2 - f``: ``Every`` on field ``f``), boost, group."""
         ix = self.ix
         cls = type(q)
+        cacheable = True
         if cls is Term:
             leaves, g = [(ix.term_id(q.fieldname, q.text), q.boost, 0)], 1
         elif (cls is And or cls is Or) and 0 < len(q.subqueries) <= 32 and all([type(t) is Term for t in q.subqueries]):
@@ -365,6 +371,14 @@ class Searcher:
             leaves = [(ix.term_id(t.fieldname, t.text), t.boost * qb, i if conj else 0) for i, t in enumerate(q.subqueries)]
             g = len(leaves) if conj else 1
         else:
+            if has_phrase(q):
+                # a phrase is And(its words, the documents that pass the positional test): the latter is a per-batch
+                # list (bm25f_put_lists), numbered by ``register``; such a lowering is not remembered on the query
+                if register is None:
+                    raise UnsupportedQuery("phrase queries are served by search() / search_page() / search_batch(), "
+                                           "not by pre-packed batches: %r" % (q,))
+                q = expand_phrases(q, register)
+                cacheable = False
             if has_multiterm(q):
                 # Prefix / Wildcard: Whoosh's MultiTerm.matcher expands the pattern over the field's lexicon into an
                 # Or of Terms (reference UI: book:tes?, search-form.html:20-40); same rewrite here, on the host
@@ -382,11 +396,12 @@ class Searcher:
                     raise UnsupportedQuery("more than %d leaves in one query" % _ffi.MAX_LEAVES_PER_QUERY)
                 if g > 32:
                     raise UnsupportedQuery("more than 32 AND-groups in one query")
-                leaves = [(ix.term_id(lf.fieldname, lf.text), lf.boost, lf.group) for lf in low]
-        return (ix.token, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]))
+                leaves = [((_FILTER_TID - lf.text) if lf.fieldname == FILTER_FIELD else ix.term_id(lf.fieldname, lf.text), lf.boost, lf.group)
+                          for lf in low]
+        return (ix.token, len(leaves), g, b"".join([_LEAF_STRUCT.pack(tid, boost, group) for tid, boost, group in leaves]), cacheable)
 
     def pack(self, queries: Sequence[Query], after_keys: Optional[np.ndarray] = None,
-             after_lo: Optional[np.ndarray] = None) -> _ffi.PackedBatch:
+             after_lo: Optional[np.ndarray] = None, filters_ok: bool = False) -> _ffi.PackedBatch:
         """Lower query trees to the ``bm25f_query_batch`` layout.  Leaf weights ``idf * (K1 + 1) * boost`` are
         evaluated in float64 and rounded once (numpy gathers over a per-term table).  The lowered form of a query
         is remembered on the query object (query trees are values: the reference builds one per request,
@@ -397,14 +412,24 @@ class Searcher:
         ngroups: List[int] = []
         blobs: List[bytes] = []
         lower1 = self._lower_one
+        phrases: List[Query] = []             # the batch's distinct phrases = its per-batch document lists
+
+        def register(p):
+            try:
+                return phrases.index(p)
+            except ValueError:
+                phrases.append(p)
+                return len(phrases) - 1
+        reg = register if filters_ok else None
         gc_was_on = gc.isenabled()
         gc.disable()                             # thousands of small objects: a collection in here costs more than the loop
         try:
             for q in queries:
                 c = q.__dict__.get("_lowered")
                 if c is None or c[0] != token:
-                    c = lower1(q)
-                    q.__dict__["_lowered"] = c
+                    c = lower1(q, reg)
+                    if c[4]:
+                        q.__dict__["_lowered"] = c
                 counts.append(c[1])
                 ngroups.append(c[2])
                 blobs.append(c[3])
@@ -421,7 +446,15 @@ class Searcher:
             w[known] = self._term_weights()[tids[known]]
             w *= rec["boost"]
         terms = np.where(known, tids, _ffi.TERM_UNKNOWN).astype(np.uint32)
-        ev = tids <= -2                               # Every(field): constant-score pseudo lists, weight = boost
+        if phrases:
+            # [W] Phrase: the positions decide whether a document matches, the score is the words' alone.  The
+            # documents that pass go to the library as posting lists; their leaves get a weight far below float32
+            # resolution of any score (and above the library's "positive weight" bar)
+            first = self.engine.put_lists([self.ix.phrase_docs(p.fieldname, p.words, p.slop) for p in phrases])
+            flt = tids <= _FILTER_TID
+            terms[flt] = (first + (_FILTER_TID - tids[flt])).astype(np.uint32)
+            w[flt] = FILTER_WEIGHT
+        ev = (tids <= -2) & (tids > _FILTER_TID)      # Every(field): constant-score pseudo lists, weight = boost
         if ev.any():
             terms[ev] = (_ffi.TERM_EVERY_BASE + (-2 - tids[ev])).astype(np.uint32)
             w[ev] = rec["boost"][ev]
@@ -520,7 +553,7 @@ class Searcher:
             first = True
             while active:
                 k = FINAL_MAX_K if limit is None else min(limit, FINAL_MAX_K)
-                batch = self.pack([queries[i] for i in active], after_hi, after_lo)
+                batch = self.pack([queries[i] for i in active], after_hi, after_lo, filters_ok=True)
                 final, docids, counts, tot = self.engine.search_batch_final(batch, k)
                 nxt, nh, nlo = [], [], []
                 for j, i in enumerate(active):
@@ -544,7 +577,7 @@ class Searcher:
             return [Results(self, queries[i], tops[i], int(totals[i]), runtime=dt) for i in range(nq)]
         if limit is not None and limit <= _ffi.MAX_K:
             # one pass serves every query: the per-query Results are made when somebody looks at them
-            scores, docids, counts, tot = self._run_packed(self.pack(queries), limit)
+            scores, docids, counts, tot = self._run_packed(self.pack(queries, filters_ok=True), limit)
             return BatchResults(self, queries, scores, docids, counts, tot, time.perf_counter() - t_start)
         want = [limit if limit is not None else None] * nq
         tops: List[list] = [[] for _ in range(nq)]
@@ -554,7 +587,7 @@ class Searcher:
         first = True
         while active:
             k = _ffi.MAX_K if limit is None else min(limit, _ffi.MAX_K)
-            batch = self.pack([queries[i] for i in active], after)
+            batch = self.pack([queries[i] for i in active], after, filters_ok=True)
             scores, docids, counts, tot = self._run_packed(batch, k)
             nxt, nxt_after = [], []
             for j, i in enumerate(active):

@@ -121,6 +121,8 @@ typedef struct {
                                     the first bm25f_set_weighting; the handle then serves that weighting only, and only
                                     queries the warp kernels take (k <= 256, <= 32 leaves, positive weights, no paging
                                     bound past BM25F_MAX_K) - anything else is a loud BM25F_EINVAL */
+  uint32_t filter_postings;      /* room for the per-batch document lists of bm25f_put_lists, in postings (8 bytes each);
+                                    default 1 << 20 */
 } bm25f_options;
 
 /* A batch of lowered queries: every query is an AND of groups, every group an OR of leaves
@@ -262,6 +264,17 @@ int  bm25f_decode_keys(bm25f_handle* h, const uint64_t* d_keys, uint32_t n_queri
                        float* d_scores, uint32_t* d_docids, uint32_t* d_counts, void* stream);
 
 /* Timings are folded in by bm25f_synchronize / bm25f_fetch. */
+/* Per-batch document lists (phrase queries: reference search-form.html:20-40, `"dead sea"`; Whoosh query.Phrase).
+ * Whoosh scores a phrase as the AND of its words and lets the positions decide only WHETHER a document matches; the
+ * host finds the documents that pass the positional test and hands them over as posting lists with impact 1: list i of
+ * this call is leaf_term `*first_term + i` until the next call replaces them all.  A phrase is then the query
+ * And(words..., its list) with a tiny positive weight (e.g. 1e-29) on the list's leaf.  Such leaves are served by the
+ * warp kernels (k <= 256, <= 32 leaves a query, positive weights, no paging bound); docids are local, strictly
+ * ascending, < n_docs_all; `offsets` [n_lists + 1] starts at 0.  Waits for the handle's stream; refused while a
+ * submitted batch is in flight. */
+#define BM25F_MAX_FILTER_LISTS 4096
+int  bm25f_put_lists(bm25f_handle* h, uint32_t n_lists, const uint64_t* offsets, const uint32_t* docids, uint32_t* first_term);
+
 int  bm25f_get_stats(bm25f_handle* h, bm25f_stats* out);
 int  bm25f_reset_stats(bm25f_handle* h);
 

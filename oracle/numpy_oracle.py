@@ -52,6 +52,30 @@ def _as_dt(v):
     return v if isinstance(v, datetime) else datetime(v.year, v.month, v.day)
 
 
+def phrase_docs(sub, fieldname, words, slop):
+    """Local docnums of ``sub`` that contain ``words`` in order, each 1 .. ``slop`` positions after the one before
+    (Whoosh query.Phrase -> spans.SpanNear chain, ordered; slop 1 = adjacent): a plain scan of every document's token
+    sequence (``FlatIndex.positions``), independent of the engine's candidate-driven ``FlatIndex.phrase_docs``."""
+    if fieldname not in sub.field_names:
+        return np.zeros(0, np.int64)
+    f = sub.field_names.index(fieldname)
+    tids = [sub.term_id(fieldname, w) for w in words]
+    if min(tids) < 0:
+        return np.zeros(0, np.int64)
+    offs, ids = sub.positions[f]
+    out = []
+    for d in range(offs.size - 1):
+        seq = ids[int(offs[d]):int(offs[d + 1])].tolist()
+        ends = [p for p, t in enumerate(seq) if t == tids[0]]
+        for t in tids[1:]:
+            ends = [p for p, x in enumerate(seq) if x == t and any(1 <= p - e <= slop for e in ends)]
+            if not ends:
+                break
+        if ends:
+            out.append(d)
+    return np.asarray(out, dtype=np.int64)
+
+
 def lower_query(q, ix=None):
     """``(groups, negatives, kind)``: ``groups`` is a list of OR-groups, each a list of
     ``(fieldname, text, boost)``; all groups must match (W10) and no leaf of ``negatives``
@@ -63,6 +87,14 @@ def lower_query(q, ix=None):
         return [[(q.fieldname, None, q.boost)]], [], "every"
     if name == "Term":
         return [[(q.fieldname, q.text, q.boost)]], [], "groups"
+    if name == "Phrase":
+        # the words' scores add up (IntersectionMatcher under the span filter); the positional test is one more
+        # "group" that scores nothing
+        if not q.words:
+            return [], [], "null"
+        if len(q.words) == 1:
+            return [[(q.fieldname, q.words[0], q.boost)]], [], "groups"
+        return ([[(q.fieldname, w, q.boost)] for w in q.words] + [[(q.fieldname, ("phrase", tuple(q.words), q.slop), 0.0)]]), [], "groups"
     if name == "DateRange":
         # constant score: every document of the range scores the boost (ConstantScoreQuery)
         return [[(q.fieldname, ("daterange", q.start, q.end), q.boost)]], [], "groups"
@@ -84,6 +116,14 @@ def lower_query(q, ix=None):
                 else:
                     flat.extend((s.fieldname, w, b) for w in words)
                 continue
+            if sn == "Phrase" and name == "And" and len(s.words) > 1:
+                groups.extend([(s.fieldname, w, s.boost * q.boost)] for w in s.words)
+                groups.append([(s.fieldname, ("phrase", tuple(s.words), s.slop), 0.0)])
+                continue
+            if sn == "Phrase" and len(s.words) == 1:
+                leaf = (s.fieldname, s.words[0], s.boost * q.boost)
+                (groups if name == "And" else flat).append([leaf] if name == "And" else leaf)
+                continue
             if sn == "DateRange":
                 leaf = (s.fieldname, ("daterange", s.start, s.end), s.boost * q.boost)
                 (groups if name == "And" else flat).append([leaf] if name == "And" else leaf)
@@ -100,6 +140,8 @@ def lower_query(q, ix=None):
                         neg.extend((t.fieldname, w) for w in _expand(t, ix))
                     elif type(t).__name__ == "DateRange":
                         neg.append((t.fieldname, ("daterange", t.start, t.end)))
+                    elif type(t).__name__ == "Phrase":
+                        neg.append((t.fieldname, ("phrase", tuple(t.words), t.slop) if len(t.words) > 1 else t.words[0]))
                     else:
                         neg.append((t.fieldname, t.text))
             else:
@@ -134,6 +176,11 @@ class NumpyOracle:
 
     def leaf_scores(self, sub, fieldname, text, boost):
         """(local docids, float64 scores) of one leaf in one shard; deleted docs removed (W9)."""
+        if isinstance(text, tuple) and text and text[0] == "phrase":
+            d = phrase_docs(sub, fieldname, text[1], text[2])
+            if sub.deleted is not None:
+                d = d[sub.deleted[d] == 0]
+            return d, np.zeros(d.size, np.float64)
         if isinstance(text, tuple) and text and text[0] == "daterange":
             d = date_range_docs(sub, fieldname, text[1], text[2])
             if sub.deleted is not None:

@@ -214,6 +214,22 @@ class OracleSearcher:
                 return ms[0]
             m = _binary_tree(UnionMatcher, ms)
             return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
+        if name == "Phrase":
+            # Whoosh query.Phrase.matcher: a word missing from the field -> NullMatcher; else SpanNear.build(terms, slop,
+            # ordered) = a left-deep chain of SpanNear2 over IntersectionMatchers: the positions decide whether a
+            # document matches, its score is the intersection's (the sum of the words' scores); then the boost.
+            if not q.words:
+                return NullMatcher()
+            ms = [self._matcher(_T(q.fieldname, w), sub) for w in q.words]
+            if any(isinstance(m, NullMatcher) for m in ms):
+                return NullMatcher()
+            m = ms[0]
+            for x in ms[1:]:
+                m = IntersectionMatcher(m, x)
+            if len(ms) > 1:
+                from oracle.numpy_oracle import phrase_docs
+                m = FilterMatcher(m, set(int(d) for d in phrase_docs(sub, q.fieldname, q.words, q.slop)))
+            return m if q.boost == 1.0 else BoostMatcher(m, q.boost)
         if name == "DateRange":
             # Whoosh query.DateRange = NumericRange over the DATETIME field inside ConstantScoreQuery(boost): every
             # live document whose date lies in the range scores the boost (reference search-form.html:26, :39;
@@ -367,6 +383,36 @@ class ConstMatcher:
 
     def score(self):
         return self.w
+
+
+class FilterMatcher:
+    """The span filter of a phrase: the child's documents that are in ``allowed``, scored by the child."""
+
+    def __init__(self, child, allowed):
+        self.c = child
+        self.allowed = allowed
+        self._find()
+
+    def _find(self):
+        while self.c.is_active() and self.c.id() not in self.allowed:
+            self.c.next()
+
+    def is_active(self):
+        return self.c.is_active()
+
+    def id(self):
+        return self.c.id()
+
+    def next(self):
+        self.c.next()
+        self._find()
+
+    def skip_to(self, d):
+        self.c.skip_to(d)
+        self._find()
+
+    def score(self):
+        return self.c.score()
 
 
 class BoostMatcher:

@@ -212,3 +212,32 @@ def test_date_ranges_f3():
     assert len(res[0]) > 0 and res[4].is_empty()
     one = check(ix, [queries()[5]], limit=5)[0]                 # a single day, boost 2.5: every hit scores the boost
     assert all(abs(h.score - 2.5) < 1e-6 for h in one)
+
+
+def test_phrases_f3():
+    """Quoted phrases (search-form.html:20-40; Whoosh query.Phrase): the host finds the documents that pass the
+    positional test, the library takes them as per-batch posting lists (bm25f_put_lists) and scores
+    And(words, list); the oracle restates Whoosh's SpanNear semantics over the stored word order."""
+    from tests.test_phrases import corpus, phrases
+    from document_search_engine_b200 import Phrase, QueryParser
+    ix = corpus(5000, seed=21, vocab=30)
+    qp = QueryParser("body")
+    qs = phrases() + [And([Term("body", "w0"), Phrase("body", ["w1", "w2"])]),
+                      And([Phrase("body", ["w1", "w2"]), Phrase("body", ["w2", "w1"], boost=3.0)]),
+                      And([Term("body", "w0"), Not(Phrase("body", ["w1", "w2"]))]),
+                      qp.parse('w3 "w4 w5"~2 NOT "w6 w7"'), qp.parse('title:"w1 w2" w3'), Term("body", "w1"),
+                      Or([Term("body", "w1"), Term("body", "w2")])]
+    for limit in (10, 100):
+        res = check(ix, qs, limit=limit)
+    assert len(res[0]) > 0 and res[6].is_empty() and res[8].is_empty()
+    # many queries in one batch (the device planner's path), every phrase its own list
+    many = [Phrase("body", ["w%d" % (i % 30), "w%d" % ((i * 7 + 1) % 30)], slop=1 + i % 3) for i in range(300)]
+    check(ix, many, limit=10)
+    # pre-packed batches cannot carry per-batch lists
+    from document_search_engine_b200.query import UnsupportedQuery
+    with ix.searcher() as s:
+        with pytest.raises(UnsupportedQuery):
+            s.pack([Phrase("body", ["w1", "w2"])])
+        page = s.search_page(qp.parse('"w1 w2"'), 2, 5)
+        assert page.pagenum == 2 and page.total == len(NumpyOracle(ix).match_all(Phrase("body", ["w1", "w2"]))[0])
+    ix._engine_cache.clear()
