@@ -55,17 +55,26 @@ def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool 
     df: List[int] = []
     terms = {}
     scorable = []
+    pos_triples = {}                      # field -> (docs, positions, term ids) of every occurrence, for phrases
     for f, name in enumerate(names):
         field = schema[name]
         scorable.append(bool(getattr(field, "scorable", False)))
         for btext in reader.lexicon(name):
             m = reader.postings(name, btext)
+            has_pos = callable(getattr(m, "supports", None)) and m.supports("positions")
             ids, ws = [], []
             # deleted documents stay in the flat postings with the ``deleted`` flags beside them: the library drops
             # them at upload (W9), and a raw matcher may or may not have filtered them already
             while m.is_active():
                 ids.append(m.id())
                 ws.append(m.weight())
+                if has_pos:
+                    # Whoosh's positions format (TEXT(phrase=True), reference my_index.py:172-177): the word order
+                    ps = list(m.value_as("positions"))
+                    t3 = pos_triples.setdefault(f, ([], [], []))
+                    t3[0].extend([ids[-1]] * len(ps))
+                    t3[1].extend(ps)
+                    t3[2].extend([len(term_field)] * len(ps))
                 m.next()
             a = np.asarray(ids, dtype=np.uint32)
             if a.size > 1 and not (a[1:] > a[:-1]).all():
@@ -111,8 +120,18 @@ def flatten_reader(reader, fields: Optional[Sequence[str]] = None, stored: bool 
         totals = np.concatenate([totals, np.zeros(len(date_fields), dtype=np.uint64)])
         if not stored:
             stored_docs = None
+    positions = {}
+    for f, (pd, pp, pt) in pos_triples.items():
+        pd, pp, pt = np.asarray(pd, np.int64), np.asarray(pp, np.int64), np.asarray(pt, np.int32)
+        dlen = np.zeros(n_docs, dtype=np.int64)
+        np.maximum.at(dlen, pd, pp + 1)                       # a gap (a removed stop word) stays -1
+        po = np.zeros(n_docs + 1, dtype=np.int64)
+        np.cumsum(dlen, out=po[1:])
+        seq = np.full(int(po[-1]), -1, dtype=np.int32)
+        seq[po[pd] + pp] = pt
+        positions[f] = (po, seq)
     cat = (lambda parts, dt: np.concatenate(parts).astype(dt) if parts else np.zeros(0, dt))
-    return FlatIndex(field_names=names, n_docs_all=n_docs, term_offsets=np.asarray(offs, dtype=np.uint64),
+    return FlatIndex(positions=positions, field_names=names, n_docs_all=n_docs, term_offsets=np.asarray(offs, dtype=np.uint64),
                      docids=cat(docids, np.uint32), tfs=cat(tfs, np.float32),
                      term_field=np.asarray(term_field, dtype=np.uint8),
                      len_bytes=np.stack([lengths_to_bytes(lengths[f]) for f in range(len(names))]) if names else np.zeros((0, n_docs), np.uint8),

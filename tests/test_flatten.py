@@ -18,8 +18,16 @@ class _FieldType:
 
 
 class _Matcher:
-    def __init__(self, ids, weights):
+    def __init__(self, ids, weights, positions=None):
         self.ids, self.w, self.i = ids, weights, 0
+        self.positions = positions            # per posting: the word's positions in that document (Whoosh "positions")
+
+    def supports(self, astype):
+        return astype == "positions" and self.positions is not None
+
+    def value_as(self, astype):
+        assert astype == "positions"
+        return self.positions[self.i]
 
     def is_active(self):
         return self.i < len(self.ids)
@@ -58,8 +66,14 @@ class FakeWhooshReader:
         return int(self.ix.df[tid]) if self.stored_df is None else int(self.stored_df[tid])
 
     def postings(self, name, btext):
-        d, w = self.ix.postings(self._tid(name, btext))
-        return _Matcher(d, w)
+        tid = self._tid(name, btext)
+        d, w = self.ix.postings(tid)
+        f = self.ix.field_names.index(name)
+        pos = None
+        if f in self.ix.positions:
+            offs, ids = self.ix.positions[f]
+            pos = [np.nonzero(ids[int(offs[x]):int(offs[x + 1])] == tid)[0].tolist() for x in d.tolist()]
+        return _Matcher(d, w, pos)
 
     def doc_field_length(self, docnum, name, default=0):
         b = int(self.ix.len_bytes[self.ix.field_names.index(name), docnum])
@@ -104,6 +118,11 @@ def test_round_trip_through_the_reader_api():
         d1, w1 = flat.postings(ftid)
         assert np.array_equal(d0, d1) and np.array_equal(w0, w1)
     assert flat.stored_fields(7) == src.stored_fields(7)
+    # the word order comes back from the per-posting positions: the same documents pass a phrase's positional test
+    assert sorted(flat.positions) == sorted(src.positions)
+    for words in (["w1", "w2"], ["w1", "w1"], ["w2", "w1", "w3"]):
+        assert flat.phrase_docs("body", words).tolist() == src.phrase_docs("body", words).tolist()
+    assert src.phrase_docs("body", ["w1", "w1"]).size > 0
     queries = [Term("body", "w1"), And([Term("body", "w2"), Term("heading", "h3")]), Or([Term("body", "w5"), Term("book", "ss")]),
                And([Term("body", "w1"), Not(Term("book", "nopr"))])]
     for cls in (OracleSearcher, NumpyOracle):
