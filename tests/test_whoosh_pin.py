@@ -29,12 +29,12 @@ from oracle.numpy_oracle import NumpyOracle                                   # 
 from oracle.whoosh_port import OracleSearcher                                 # noqa: E402
 
 
-def whoosh_index(tmp_path, docs, id_fields=(), deleted=()):
+def whoosh_index(tmp_path, docs, id_fields=(), deleted=(), phrase=False):
     """``docs``: list of {field: token list | id string}; one commit = one segment, docnum = position."""
     from whoosh import fields, index
     from whoosh.analysis import SpaceSeparatedTokenizer
     names = sorted({k for d in docs for k in d})
-    schema = fields.Schema(**{n: (fields.ID() if n in id_fields else fields.TEXT(analyzer=SpaceSeparatedTokenizer(), phrase=False))
+    schema = fields.Schema(**{n: (fields.ID() if n in id_fields else fields.TEXT(analyzer=SpaceSeparatedTokenizer(), phrase=phrase))
                               for n in names})
     ix = index.create_in(str(tmp_path), schema)
     w = ix.writer()
@@ -56,6 +56,8 @@ def to_whoosh(q):
         return wq.Term(q.fieldname, q.text if isinstance(q.text, str) else "t%07d" % q.text, boost=q.boost)
     if name == "Not":
         return wq.Not(to_whoosh(q.query))
+    if name == "Phrase":
+        return wq.Phrase(q.fieldname, list(q.words), slop=q.slop, boost=q.boost)
     cls = {"And": wq.And, "Or": wq.Or}[name]
     return cls([to_whoosh(s) for s in q.subqueries], boost=q.boost)
 
@@ -113,6 +115,32 @@ def test_small_cases_match_whoosh(tmp_path):
         for o in (OracleSearcher(fix, **okw), NumpyOracle(fix, **okw)):
             for q in queries:
                 assert_same(o.search(q, limit=10), whoosh_search(wix, q, 10, **kw), "%s %s %s" % (type(o).__name__, kw, q))
+
+
+def test_phrases_match_whoosh(tmp_path):
+    """query.Phrase (the reference UI's quoted phrases, search-form.html:20-40): which documents pass the positional
+    test, and that they score the sum of their words' scores."""
+    from document_search_engine_b200 import Phrase
+    from tests.test_phrases import corpus, phrases
+    fix = corpus(300, seed=5)
+    offs, ids = fix.positions[0]
+    text_of = {tid: t for (f, t), tid in fix.terms.items()}
+    docs = []
+    for d in range(fix.n_docs_all):
+        doc = {}
+        for f, name in enumerate(fix.field_names):
+            o, i = fix.positions[f]
+            toks = [text_of[int(t)] for t in i[int(o[d]):int(o[d + 1])]]
+            if toks:
+                doc[name] = toks
+        docs.append(doc)
+    deleted = np.nonzero(fix.deleted)[0].tolist()
+    wix = whoosh_index(tmp_path, docs, deleted=deleted, phrase=True)
+    qs = [p for p in phrases() if p.fieldname in fix.field_names] + [
+        And([Term("body", "w0"), Phrase("body", ["w1", "w2"])]), And([Term("body", "w0"), Not(Phrase("body", ["w1", "w2"]))])]
+    for o in (OracleSearcher(fix), NumpyOracle(fix)):
+        for q in qs:
+            assert_same(o.search(q, limit=20), whoosh_search(wix, q, 20), "%s %s" % (type(o).__name__, q))
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.json"))))
