@@ -34,6 +34,17 @@ from .scoring import BM25F, instantiate
 #: one lowered leaf as ``Searcher.pack`` keeps it: posting-list id (or -1 / -2 - field), boost, group
 _LEAF_REC = np.dtype([("tid", "<i8"), ("boost", "<f8"), ("group", "u1"), ("pad", "V7")])
 _LEAF_STRUCT = struct.Struct("<qdB7x")
+_LEAF_STRUCTS = {}
+
+
+def _leaf_struct(n: int) -> struct.Struct:
+    """``n`` leaf records in one ``struct`` call."""
+    st = _LEAF_STRUCTS.get(n)
+    if st is None:
+        st = _LEAF_STRUCTS[n] = struct.Struct("<" + "qdB7x" * n)
+    return st
+
+
 #: ``tid`` of the leaf that stands for per-batch document list ``i`` (a phrase's positional test): ``_FILTER_TID - i``
 _FILTER_TID = -1000
 #: its weight: positive for the library, invisible next to any float32 score
@@ -357,6 +368,26 @@ class Searcher:
             self._term_w = tw
         return tw
 
+    def _make_tid_of(self):
+        """``(fieldname, text) -> posting-list id or -1`` as a closure over the index's dictionary (``FlatIndex.term_id``
+        without the per-call field search)."""
+        ix = self.ix
+        fmap = {name: f for f, name in enumerate(ix.field_names)}
+        terms, vs, slow = ix.terms, ix.vocab_size, ix.term_id
+
+        if terms is not None:
+            def tid_of(fieldname, text):
+                f = fmap.get(fieldname)
+                return -1 if f is None else terms.get((f, text), -1)
+        else:
+            def tid_of(fieldname, text):
+                if type(text) is int:
+                    f = fmap.get(fieldname)
+                    return f * vs + text if f is not None and 0 <= text < vs else -1
+                return slow(fieldname, text)
+        self.__dict__["_tid_of"] = tid_of
+        return tid_of
+
     def _lower_one(self, q: Query, register=None):
         """``(index, n_leaves, n_groups, packed leaf records, query)`` of one query: what ``pack`` needs, remembered
         on the query object.  A leaf record is ``_LEAF_REC``: posting-list id (-1: unknown term or field, W10;
@@ -364,12 +395,23 @@ class Searcher:
         ix = self.ix
         cls = type(q)
         cacheable = True
+        tid_of = self.__dict__.get("_tid_of") or self._make_tid_of()
         if cls is Term:
-            leaves, g = [(ix.term_id(q.fieldname, q.text), q.boost, 0)], 1
+            return (ix.token, 1, 1, _LEAF_STRUCT.pack(tid_of(q.fieldname, q.text), q.boost, 0), True)
         elif (cls is And or cls is Or) and 0 < len(q.subqueries) <= 32 and all([type(t) is Term for t in q.subqueries]):
-            qb, conj = q.boost, cls is And
-            leaves = [(ix.term_id(t.fieldname, t.text), t.boost * qb, i if conj else 0) for i, t in enumerate(q.subqueries)]
-            g = len(leaves) if conj else 1
+            # the common shapes (the reference's form: words joined by AND / OR) skip the general lowering; one
+            # struct call packs all the leaves
+            subs = q.subqueries
+            n = len(subs)
+            qb = q.boost
+            flat = []
+            if cls is And:
+                for i, t in enumerate(subs):
+                    flat += (tid_of(t.fieldname, t.text), t.boost * qb, i)
+            else:
+                for t in subs:
+                    flat += (tid_of(t.fieldname, t.text), t.boost * qb, 0)
+            return (ix.token, n, n if cls is And else 1, _leaf_struct(n).pack(*flat), True)
         else:
             if has_phrase(q):
                 # a phrase is And(its words, the documents that pass the positional test): the latter is a per-batch
