@@ -243,16 +243,22 @@ class ShardedSearcher:
         inflight = None
         slot = 0
 
-        def finish(item):
+        def land(item):
+            # (worker thread) wait for the batch's results to reach the pinned buffer and copy them out of it
             plan, h, ev, Q = item
-            try:
-                ev.synchronize()
-                return self._split_out(h.numpy().copy(), Q, k)
-            finally:
-                plan.close()
+            ev.synchronize()
+            return self._split_out(h.numpy().copy(), Q, k)
 
+        # The wait for batch i and the copy of its results (0.9 MB for 10k queries, ~80 us) run on a helper thread
+        # while this thread stages and launches batch i + 1: at 8 shards the GPU step is 0.47 ms and the host work
+        # of a step was as long.  Both release the GIL (event wait, memcpy).
+        pool = self._bufs.get("pool")
+        if pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            pool = self._bufs["pool"] = ThreadPoolExecutor(max_workers=1, thread_name_prefix="bm25f-results")
         try:
             for batch in batches:
+                fut = pool.submit(land, inflight) if inflight is not None else None
                 plan = self.engine.prepare(batch, k, arena=True)
                 Q = batch.n_queries
                 b = self.run_plan(plan, slot)
@@ -264,17 +270,26 @@ class ShardedSearcher:
                     ev.record(d2h)
                 cur = (plan, h, ev, Q)
                 slot ^= 1
-                if inflight is not None:
-                    prev, inflight = inflight, cur
-                    yield finish(prev)
-                else:
-                    inflight = cur
+                prev, inflight = inflight, cur
+                if fut is not None:
+                    try:
+                        res = fut.result()
+                    finally:
+                        prev[0].close()
+                    yield res
             if inflight is not None:
                 prev, inflight = inflight, None
-                yield finish(prev)
+                try:
+                    res = land(prev)
+                finally:
+                    prev[0].close()
+                yield res
         finally:
             if inflight is not None:
-                finish(inflight)
+                try:
+                    inflight[2].synchronize()
+                finally:
+                    inflight[0].close()
 
     def _d2h_stream(self):
         s = self._bufs.get("d2h_stream")
