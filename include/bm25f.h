@@ -23,6 +23,16 @@
  *       <- Whoosh's multi-segment collection (global docnum = segment offset + local docnum,
  *          one collector over all segments); here: merge of per-GPU local top-k lists
  *          after the NCCL all-gather.
+ *   bm25f_plan_gather_span / bm25f_merge_gathered
+ *       <- the same, as one exchange: the plan's keys and match counts are one device span (one all-gather), then
+ *          merge + decode + sum of the counts in one call.
+ *   bm25f_set_final_date / bm25f_fetch_final / bm25f_merge_final_lists
+ *       <- `DateBM25F.final()` of the reference's date-ordered weightings   reference my_whoosh.py:127-154
+ *   bm25f_put_lists
+ *       <- Whoosh's Phrase matcher (quoted phrases of the search form, reference templates/search-form.html:20-40):
+ *          the documents that pass the positional test, found on the host, become posting lists of one batch.
+ *   bm25f_submit / bm25f_collect
+ *       <- no counterpart in the reference (one request at a time): two batches in flight for servers that batch.
  *   bm25f_get_stats
  *       <- `Results.runtime` (Whoosh records wall time per search; the reference never reads it).
  *
