@@ -91,7 +91,8 @@ def main():
             print(json.dumps({"opt": opt, "mode": m, "parity": bad or "ok", "qps": len(queries) / (ms * 1e-3), "ms_total": ms,
                               "ms_bounds": st["ms_bounds"] / n, "ms_score": st["ms_score"] / n,
                               "ms_merge": st["ms_merge"] / n, "ms_stream": st["ms_stream"] / n,
-                              "post_stream": st["postings_stream"], "post_lookup": st["postings_lookup"],
+                              "post_stream": st["postings_stream"], "post_lookup": st["postings_lookup"], "post_team": st["postings_team"],
+                              "launches": st["n_launches"],
                               "stream_GBs": stream_gbs, "stream_frac_6547": stream_gbs / 6547.2,
                               "step_GBs": gbs, "items": st["n_items"], "ctas_per_sm": st["ctas_per_sm"],
                               "postings": st["postings_touched"]}), flush=True)
